@@ -1,0 +1,97 @@
+"""ctypes binding of libdiffvits_b200.so (C ABI declared in include/diffvits_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiffvits_b200.so")
+
+
+class DVError(RuntimeError):
+    """A libdiffvits_b200 call returned a negative dv_status."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"diffvits_b200 error {code}: {msg}")
+        self.code = code
+
+
+class UnetCfg(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int),
+        ("out_channels", C.c_int),
+        ("n_levels", C.c_int),
+        ("block_out_channels", C.c_int * 8),
+        ("layers_per_block", C.c_int),
+        ("norm_num_groups", C.c_int),
+        ("cross_attention_dim", C.c_int),
+        ("num_heads", C.c_int),
+        ("norm_eps", C.c_float),
+        ("x_channels", C.c_int),
+    ]
+
+
+class GemmSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("L", C.c_int), ("C", C.c_int), ("ld", C.c_int)]
+
+
+class GemmSeg(C.Structure):
+    _fields_ = [("src", C.c_int), ("row_off", C.c_int), ("c0", C.c_int), ("npanels", C.c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/diffvits_b200.h one to one
+_vp, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
+SIGNATURES = {
+    "dv_version": (_i, []),
+    "dv_last_error": (C.c_char_p, []),
+    "dv_plan_create": (_i, [C.POINTER(UnetCfg), _i, _i, _i, C.POINTER(_vp)]),
+    "dv_plan_destroy": (None, [_vp]),
+    "dv_plan_workspace_bytes": (_sz, [_vp]),
+    "dv_plan_param_bytes": (_sz, [_vp]),
+    "dv_plan_manifest_json": (C.c_char_p, [_vp]),
+    "dv_plan_launches_per_forward": (_i, [_vp]),
+    "dv_plan_last_sample_launches": (_i, [_vp]),
+    "dv_plan_bind": (_i, [_vp, _vp, _vp, _vp]),
+    "dv_prompt_prepare": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "dv_set_cond": (_i, [_vp, _vp, _vp]),
+    "dv_unet_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "dv_sample": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp]),
+    "dv_gemm": (_i, [C.POINTER(GemmSrc), _i, C.POINTER(GemmSeg), _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i,
+                     _i, _i, _vp]),
+    "dv_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "dv_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    "dv_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "dv_dpmpp_update": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _f, _sz, _vp]),
+    "dv_unipc_predict": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _sz, _vp]),
+    "dv_unipc_correct": (_i, [_vp, _vp, _vp, _vp, _f, _sz, _vp]),
+    "dv_nct_to_ntc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is the job of __graft_entry__.build / diffvits_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build it with `python -m diffvits_b200.build` (needs nvcc); "
+            "diffvits_b200 has no CPU or PyTorch fallback path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DVError(rc, load().dv_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,201 @@
+// extern "C" surface of libdiffvits_b200.so (declared in include/diffvits_b200.h).
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "engine.h"
+
+struct dv_plan {
+  dv::Plan impl;
+};
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int ck(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return DV_OK;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return DV_ERR_CUDA;
+}
+cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+// There is no CPU path: refuse loudly when no sm_100 device is current.
+int require_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(DV_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return fail(DV_ERR_CUDA, cudaGetErrorString(e));
+  if (major != 10) return fail(DV_ERR_UNSUPPORTED, "diffvits_b200 kernels are built for sm_100a only (compute capability 10.x required)");
+  return DV_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dv_version(void) { return DV_VERSION; }
+const char* dv_last_error(void) { return g_err.c_str(); }
+
+int dv_plan_create(const dv_unet_cfg* cfg, int B, int T, int Tp, dv_plan** out) {
+  if (!cfg || !out) return fail(DV_ERR_INVALID, "null argument");
+  dv_plan* p = new (std::nothrow) dv_plan();
+  if (!p) return fail(DV_ERR_INVALID, "out of host memory");
+  p->impl.cfg = *cfg;
+  p->impl.B = B; p->impl.T = T; p->impl.Tp = Tp;
+  std::string err;
+  int rc = p->impl.build(err);
+  if (rc != DV_OK) {
+    delete p;
+    return fail(rc, err);
+  }
+  *out = p;
+  return DV_OK;
+}
+void dv_plan_destroy(dv_plan* plan) { delete plan; }
+size_t dv_plan_workspace_bytes(const dv_plan* plan) { return plan ? plan->impl.ws_bytes : 0; }
+size_t dv_plan_param_bytes(const dv_plan* plan) { return plan ? plan->impl.param_bytes : 0; }
+const char* dv_plan_manifest_json(const dv_plan* plan) { return plan ? plan->impl.manifest.c_str() : ""; }
+int dv_plan_launches_per_forward(const dv_plan* plan) { return plan ? static_cast<int>(plan->impl.ops.size()) + 3 : 0; }
+int dv_plan_last_sample_launches(const dv_plan* plan) { return plan ? plan->impl.last_sample_launches : 0; }
+
+int dv_plan_bind(dv_plan* plan, void* workspace, const void* params, void* stream) {
+  if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  std::string err;
+  rc = plan->impl.bind(workspace, params, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+int dv_prompt_prepare(dv_plan* plan, const float* ehs, const float* aug, const int32_t* kv_len, void* stream) {
+  if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  std::string err;
+  int rc = plan->impl.prompt_prepare(ehs, aug, kv_len, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+int dv_set_cond(dv_plan* plan, const float* cond, void* stream) {
+  if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  std::string err;
+  int rc = plan->impl.set_cond(cond, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride, float* out,
+                    void* stream) {
+  if (!plan || !sample || !t || !out) return fail(DV_ERR_INVALID, "null argument");
+  std::string err;
+  int launches = 0;
+  int rc = plan->impl.forward(sample, x_only, t, t_stride, out, S(stream), err, &launches);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags,
+              void* stream) {
+  if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  std::string err;
+  int rc = plan->impl.sample(sampler, nsteps, t_in, coef, x, flags, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+
+// ------------------------------------------------------------------------------------------ single kernels
+int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
+            int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
+            int L_out, int impl, void* stream) {
+  if (!srcs || !segs || !w || !out) return fail(DV_ERR_INVALID, "null argument");
+  if (nsrc < 1 || nsrc > dv::GEMM_MAX_SRC || nseg < 1 || nseg > dv::GEMM_MAX_SEG) return fail(DV_ERR_INVALID, "bad nsrc/nseg");
+  if (n_pad % 128 || k_tot % 64) return fail(DV_ERR_INVALID, "n_pad must be a multiple of 128 and k_tot of 64");
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  dv::GemmParams p;
+  memset(&p, 0, sizeof p);
+  std::string err;
+  dv::GemmRefSrc rs[dv::GEMM_MAX_SRC];
+  for (int i = 0; i < dv::GEMM_MAX_SRC; ++i) {
+    const dv_gemm_src& s = srcs[i < nsrc ? i : 0];
+    if (s.C % 64) return fail(DV_ERR_INVALID, "source channels must be a multiple of 64");
+    if (!dv::make_tmap_3d(&p.mapA[i], s.ptr, s.C, s.ld, s.L, B, static_cast<size_t>(s.L) * s.ld, err))
+      return fail(DV_ERR_CUDA, err);
+    rs[i] = dv::GemmRefSrc{s.ptr, s.L, s.C, s.ld};
+  }
+  if (!dv::make_tmap_2d(&p.mapW, w, k_tot, n_pad, 128, err)) return fail(DV_ERR_CUDA, err);
+  int ksum = 0;
+  for (int i = 0; i < nseg; ++i) {
+    if (segs[i].src < 0 || segs[i].src >= nsrc) return fail(DV_ERR_INVALID, "segment source out of range");
+    p.seg[i].src = static_cast<int16_t>(segs[i].src);
+    p.seg[i].row_off = static_cast<int16_t>(segs[i].row_off);
+    p.seg[i].c0 = static_cast<int16_t>(segs[i].c0);
+    p.seg[i].npanels = static_cast<int16_t>(segs[i].npanels);
+    ksum += segs[i].npanels * 64;
+  }
+  if (ksum != k_tot) return fail(DV_ERR_INVALID, "segments do not add up to k_tot");
+  p.nseg = nseg;
+  p.B = B; p.L = L_out; p.N = n; p.n_pad = n_pad;
+  p.tiles_per_batch = (L_out + 127) / 128;
+  p.out_mode = out_mode;
+  p.bias = bias; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out;
+  if (impl == 1) return ck(dv::launch_gemm_ref(p, rs, w, k_tot, S(stream)), "gemm_ref");
+  return ck(dv::launch_gemm_tc(p, S(stream)), "gemm_tc");
+}
+
+int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
+                 long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,
+                 float scale, const int32_t* kv_len, void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  dv::AttnParams p;
+  p.q = q; p.k = k; p.v = v; p.o = o;
+  p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ld_o = ld_o;
+  p.bs_q = bs_q; p.bs_k = bs_k; p.bs_v = bs_v; p.bs_o = bs_o;
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.D = D; p.scale = scale; p.kv_len = kv_len;
+  return ck(dv::launch_attention(p, S(stream)), "attention");
+}
+
+int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, double* stats,
+                 const float* gamma, const float* beta, const float* scale_shift, int ss_ld, float eps, int silu,
+                 void* out, void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  dv::GnParams p;
+  memset(&p, 0, sizeof p);
+  p.x0 = x0; p.c0 = c0; p.x1 = x1; p.c1 = x1 ? c1 : 0;
+  p.B = B; p.L = L; p.G = G; p.stats = stats; p.gamma = gamma; p.beta = beta;
+  p.scale_shift = scale_shift; p.ss_ld = ss_ld; p.eps = eps; p.silu = silu; p.out = out;
+  rc = ck(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * G * 2 * sizeof(double), S(stream)), "memset stats");
+  if (rc != DV_OK) return rc;
+  rc = ck(dv::launch_gn_stats(p, S(stream)), "gn_stats");
+  if (rc != DV_OK) return rc;
+  return ck(dv::launch_gn_apply(p, S(stream)), "gn_apply");
+}
+
+int dv_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C, float eps,
+                 void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  return ck(dv::launch_layernorm(x, out, gamma, beta, rows, C, eps, S(stream)), "layernorm");
+}
+
+int dv_dpmpp_update(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
+                    int roundtrip, float alpha_prev, float sigma_prev, size_t n, void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  return ck(dv::launch_axpbypcz(x_out, x, m1, m0, a, b, c, roundtrip, alpha_prev, sigma_prev, n, S(stream)), "dpmpp_update");
+}
+int dv_unipc_predict(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a, float b,
+                     float cp, float cc, int has_prev, size_t n, void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  return ck(dv::launch_unipc_pred(xpred, base, x, m1, m0, a, b, cp, cc, has_prev, n, S(stream)), "unipc_predict");
+}
+int dv_unipc_correct(float* x, const float* base, const float* mt, const float* m1, float d, size_t n, void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  return ck(dv::launch_unipc_corr(x, base, mt, m1, d, n, S(stream)), "unipc_correct");
+}
+int dv_nct_to_ntc(const float* src, void* dst, int B, int C, int T, int ld, int col0, void* stream) {
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  return ck(dv::launch_nct_to_ntc(src, dst, B, C, T, ld, col0, 1 << 30, 0, S(stream)), "nct_to_ntc");
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// Fused flash-style attention for the UNet's 8-head self- and prompt cross-attention
+// (reference: unet1d/attention_processor.py:980-1052, F.scaled_dot_product_attention at :1032).
+//
+// Head dims on this path are 16/32/48/64 (C/8 per level). At d=16 one S tile costs 64 FLOP per exp, so the
+// kernel is bound by the MUFU/FMA pipes (exp2, max, scale), not by the tensor pipe; S and P therefore stay in
+// registers (mma.sync m16n8k16 bf16, fp32 accumulate) instead of a TMEM round trip, and the softmax is done on
+// the accumulator fragments directly. K/V tiles are staged with cp.async (16-byte, zero-fill for tail rows),
+// double buffered; rows are padded by 16 bytes so the 32-bit fragment loads and ldmatrix.trans are conflict free.
+//
+// Masking: self-attention has no mask (attention_mask=None in the reference, padded frames participate).
+// Cross-attention uses the reference's additive bias: keys >= kv_len[b] get -10000 added to the scaled score
+// (unet_1d_condition.py:816-818), reproduced literally so a fully masked row degrades the same way.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace dv {
+namespace {
+
+constexpr int BQ = 64;    // queries per CTA (4 warps x 16 rows)
+constexpr int BKV = 64;   // keys per tile
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_ptr)));
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams p) {
+  constexpr int PITCH = D + 8;          // elements; +16 bytes
+  constexpr int CHUNKS = D / 8;         // 16-byte chunks per row
+  __shared__ __align__(16) __nv_bfloat16 sQ[BQ * PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sK[2][BKV * PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sV[2][BKV * PITCH];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+
+  const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(p.q) + b * p.bs_q + h * D;
+  const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(p.k) + b * p.bs_k + h * D;
+  const __nv_bfloat16* V = reinterpret_cast<const __nv_bfloat16*>(p.v) + b * p.bs_v + h * D;
+
+  // ---- stage Q (group 0 together with the first K/V tile)
+  for (int i = tid; i < BQ * CHUNKS; i += ATT_THREADS) {
+    const int r = i / CHUNKS, c = i % CHUNKS;
+    const int row = q0 + r;
+    const bool ok = row < p.Lq;
+    cp_async16(&sQ[r * PITCH + c * 8], Q + static_cast<size_t>(ok ? row : 0) * p.ld_q + c * 8, ok ? 16 : 0);
+  }
+  auto load_kv = [&](int tile, int buf) {
+    const int k0 = tile * BKV;
+    for (int i = tid; i < BKV * CHUNKS; i += ATT_THREADS) {
+      const int r = i / CHUNKS, c = i % CHUNKS;
+      const int row = k0 + r;
+      const bool ok = row < p.Lk;
+      const size_t rr = static_cast<size_t>(ok ? row : 0);
+      cp_async16(&sK[buf][r * PITCH + c * 8], K + rr * p.ld_k + c * 8, ok ? 16 : 0);
+      cp_async16(&sV[buf][r * PITCH + c * 8], V + rr * p.ld_v + c * 8, ok ? 16 : 0);
+    }
+  };
+  const int ntiles = (p.Lk + BKV - 1) / BKV;
+  load_kv(0, 0);
+  cp_async_commit();
+
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float sl2 = p.scale * LOG2E;
+  const float mask_bias = -10000.0f * LOG2E;
+  const int kvlen = p.kv_len ? p.kv_len[b] : p.Lk;
+
+  uint32_t qf[D / 16][4];
+  float o[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) {
+      load_kv(tile + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    if (tile == 0) {
+      const __nv_bfloat16* qb = &sQ[(warp * 16) * PITCH];
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        qf[kk][0] = *reinterpret_cast<const uint32_t*>(&qb[g * PITCH + kk * 16 + 2 * t]);
+        qf[kk][1] = *reinterpret_cast<const uint32_t*>(&qb[(g + 8) * PITCH + kk * 16 + 2 * t]);
+        qf[kk][2] = *reinterpret_cast<const uint32_t*>(&qb[g * PITCH + kk * 16 + 2 * t + 8]);
+        qf[kk][3] = *reinterpret_cast<const uint32_t*>(&qb[(g + 8) * PITCH + kk * 16 + 2 * t + 8]);
+      }
+    }
+
+    // ---- S = Q K^T  (16 x 64 per warp)
+    float s[BKV / 8][4];
+#pragma unroll
+    for (int j = 0; j < BKV / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const __nv_bfloat16* kb = &sK[buf][(j * 8 + g) * PITCH + 2 * t];
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kb + kk * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kb + kk * 16 + 8);
+        mma_bf16_16816(s[j], qf[kk], b0, b1);
+      }
+    }
+
+    // ---- scale, mask, online softmax (rows g and g+8 of this warp's 16)
+    const int kbase = tile * BKV + 2 * t;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < BKV / 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = kbase + j * 8 + e;
+        float add = 0.f;
+        if (key >= p.Lk) add = -INFINITY;
+        else if (key >= kvlen) add = mask_bias;
+        s[j][e] = s[j][e] * sl2 + add;
+        s[j][2 + e] = s[j][2 + e] * sl2 + add;
+        mx0 = fmaxf(mx0, s[j][e]);
+        mx1 = fmaxf(mx1, s[j][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 key < Lk
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+
+    uint32_t pf[BKV / 16][4];
+#pragma unroll
+    for (int j = 0; j < BKV / 8; ++j) {
+      const float p0 = exp2f(s[j][0] - mn0), p1 = exp2f(s[j][1] - mn0);
+      const float p2 = exp2f(s[j][2] - mn1), p3 = exp2f(s[j][3] - mn1);
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+
+    // ---- O += P V   (V fragments through ldmatrix.trans)
+#pragma unroll
+    for (int kk = 0; kk < BKV / 16; ++kk) {
+      const int krow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int jd = 0; jd < D / 8; jd += 2) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, &sV[buf][krow * PITCH + (jd + (lane >> 4)) * 8]);
+        mma_bf16_16816(o[jd], pf[kk], vf[0], vf[1]);
+        mma_bf16_16816(o[jd + 1], pf[kk], vf[2], vf[3]);
+      }
+    }
+    __syncthreads();
+  }
+
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* O = reinterpret_cast<__nv_bfloat16*>(p.o) + b * p.bs_o + h * D;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) {
+    if (r0 < p.Lq)
+      *reinterpret_cast<uint32_t*>(&O[static_cast<size_t>(r0) * p.ld_o + j * 8 + 2 * t]) =
+          pack_bf16(o[j][0] * i0, o[j][1] * i0);
+    if (r1 < p.Lq)
+      *reinterpret_cast<uint32_t*>(&O[static_cast<size_t>(r1) * p.ld_o + j * 8 + 2 * t]) =
+          pack_bf16(o[j][2] * i1, o[j][3] * i1);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
+  if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
+  dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
+  switch (p.D) {
+    case 16: attention_kernel<16><<<grid, ATT_THREADS, 0, st>>>(p); break;
+    case 32: attention_kernel<32><<<grid, ATT_THREADS, 0, st>>>(p); break;
+    case 48: attention_kernel<48><<<grid, ATT_THREADS, 0, st>>>(p); break;
+    case 64: attention_kernel<64><<<grid, ATT_THREADS, 0, st>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace dv

@@ -1,0 +1,237 @@
+// Small / HBM-bound kernels of the denoising loop:
+//  * layout change at the API boundary ([B, C, T] fp32 -> channel-last bf16 GEMM operand),
+//  * timestep embedding (sinusoid -> MLP -> + text embedding -> SiLU -> all 22 time_emb_proj at once)
+//    (reference: unet1d/embeddings.py:24-64,157-201; unet_1d_condition.py:841-918; resnet.py:614-617),
+//  * the samplers' per-step multistep updates as single coalesced float4 passes
+//    (reference: sampler/dpm_solver.py:547-580, 796-852; sampler/uni_pc.py:471-588).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace dv {
+namespace {
+
+// ------------------------------------------------------------------ layout
+__global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         int Csrc, int T, int ld_dst, int col0, int split, int shift) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, t = t0 + tx;
+    tile[k][tx] = (c < Csrc && t < T) ? src[(static_cast<size_t>(b) * Csrc + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int t = t0 + k, c = c0 + tx;
+    if (t < T && c < Csrc) {
+      const int col = col0 + c + (c >= split ? shift : 0);
+      dst[(static_cast<size_t>(b) * T + t) * ld_dst + col] = __float2bfloat16_rn(tile[tx][k]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          size_t n) {
+  const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i4);
+    uint2 w;
+    w.x = pack_bf16(v.x, v.y);
+    w.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i4) = w;
+  } else {
+    for (size_t i = i4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// ------------------------------------------------------------------ time embedding
+// One CTA per batch item: e = [cos(t f), sin(t f)] ; h = SiLU(W1 e + b1) ; emb = W2 h + b2 + aug ; out SiLU(emb).
+// w1/w2 are stored transposed ([in][out]) so consecutive threads read consecutive addresses.
+__global__ void __launch_bounds__(512) temb_mlp_kernel(const TembParams p) {
+  __shared__ float e[256];
+  __shared__ float h[512];
+  const int b = blockIdx.x;
+  const int j = threadIdx.x;
+  const float t = p.t[static_cast<size_t>(b) * p.t_stride];
+  const int half = p.sin_dim / 2;
+  if (j < half) {
+    const float a = t * p.freqs[j];
+    e[j] = cosf(a);          // flip_sin_to_cos=True: cos half first
+    e[half + j] = sinf(a);
+  }
+  __syncthreads();
+  float acc = p.b1[j];
+  for (int k = 0; k < p.sin_dim; ++k) acc += p.w1[k * p.emb_dim + j] * e[k];
+  h[j] = silu_f(acc);
+  __syncthreads();
+  float acc2 = p.b2[j];
+  for (int k = 0; k < p.emb_dim; ++k) acc2 += p.w2[k * p.emb_dim + j] * h[k];
+  if (p.aug) acc2 += p.aug[static_cast<size_t>(b) * p.emb_dim + j];
+  p.emb_act[static_cast<size_t>(b) * p.emb_dim + j] = silu_f(acc2);
+}
+
+// ss_all[b, j] = b_all[j] + w_all[j, :] . emb_act[b, :]   (emb_dim = 512)
+constexpr int TP_BCHUNK = 16;
+constexpr int TP_ROWS_PER_WARP = 4;
+__global__ void __launch_bounds__(256) temb_proj_kernel(const TembParams p) {
+  __shared__ float es[TP_BCHUNK][512];
+  const int b0 = blockIdx.y * TP_BCHUNK;
+  const int nb = min(TP_BCHUNK, p.B - b0);
+  for (int i = threadIdx.x; i < nb * 512; i += 256) es[i / 512][i % 512] = p.emb_act[static_cast<size_t>(b0) * 512 + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = 0; rr < TP_ROWS_PER_WARP; ++rr) {
+    const int j = (blockIdx.x * 8 + warp) * TP_ROWS_PER_WARP + rr;
+    if (j >= p.n_all) break;
+    float w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __ldg(p.w_all + static_cast<size_t>(j) * 512 + lane + 32 * i);
+    const float bias = __ldg(p.b_all + j);
+    for (int bb = 0; bb < nb; ++bb) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc += w[i] * es[bb][lane + 32 * i];
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+      if (lane == 0) p.ss_all[static_cast<size_t>(b0 + bb) * p.n_all + j] = acc + bias;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sampler updates (fp32, float4)
+__device__ __forceinline__ float4 ld4(const float* p, size_t i) { return *reinterpret_cast<const float4*>(p + i); }
+__device__ __forceinline__ void st4(float* p, size_t i, float4 v) { *reinterpret_cast<float4*>(p + i) = v; }
+
+__device__ __forceinline__ float roundtrip(float x, float m, float alp, float sig) {
+  // sampler/dpm_solver.py:290-292 then :437-439 : x0 -> eps -> x0, evaluated in the reference's order
+  const float eps = __fdiv_rn(__fsub_rn(x, __fmul_rn(alp, m)), sig);
+  return __fdiv_rn(__fsub_rn(x, __fmul_rn(sig, eps)), alp);
+}
+
+__global__ void __launch_bounds__(256) axpbypcz_kernel(float* xo, const float* x, float* m1,
+                                                       const float* __restrict__ m0, float a, float b, float c,
+                                                       int rt, float alp, float sig, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 xv = ld4(x, i);
+      float4 mv = ld4(m1, i);
+      if (rt) {
+        mv.x = roundtrip(xv.x, mv.x, alp, sig); mv.y = roundtrip(xv.y, mv.y, alp, sig);
+        mv.z = roundtrip(xv.z, mv.z, alp, sig); mv.w = roundtrip(xv.w, mv.w, alp, sig);
+        st4(m1, i, mv);
+      }
+      float4 r;
+      // reference order: (sigma_t/sigma_s) * x - alpha_t*phi * m1 - 0.5*alpha_t*phi/r0 * (m1 - m0)
+      r.x = a * xv.x + b * mv.x; r.y = a * xv.y + b * mv.y; r.z = a * xv.z + b * mv.z; r.w = a * xv.w + b * mv.w;
+      if (m0) {
+        const float4 pv = ld4(m0, i);
+        r.x += c * pv.x; r.y += c * pv.y; r.z += c * pv.z; r.w += c * pv.w;
+      }
+      st4(xo, i, r);
+    } else {
+      for (size_t k = i; k < n; ++k) {
+        float mv = m1[k];
+        if (rt) { mv = roundtrip(x[k], mv, alp, sig); m1[k] = mv; }
+        float r = a * x[k] + b * mv;
+        if (m0) r += c * m0[k];
+        xo[k] = r;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unipc_pred_kernel(float* xp, float* __restrict__ base,
+                                                         const float* x, const float* __restrict__ m1,
+                                                         const float* __restrict__ m0, float a, float b, float cp,
+                                                         float cc, int has_m0, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 xv = ld4(x, i), mv = ld4(m1, i);
+      float4 xb;
+      xb.x = a * xv.x + b * mv.x; xb.y = a * xv.y + b * mv.y; xb.z = a * xv.z + b * mv.z; xb.w = a * xv.w + b * mv.w;
+      float4 p = xb, q = xb;
+      if (has_m0) {
+        const float4 pv = ld4(m0, i);
+        const float dx = pv.x - mv.x, dy = pv.y - mv.y, dz = pv.z - mv.z, dw = pv.w - mv.w;
+        p.x += cp * dx; p.y += cp * dy; p.z += cp * dz; p.w += cp * dw;
+        q.x += cc * dx; q.y += cc * dy; q.z += cc * dz; q.w += cc * dw;
+      }
+      st4(xp, i, p);
+      if (base) st4(base, i, q);
+    } else {
+      for (size_t k = i; k < n; ++k) {
+        const float xb = a * x[k] + b * m1[k];
+        const float d = has_m0 ? (m0[k] - m1[k]) : 0.f;
+        xp[k] = xb + cp * d;
+        if (base) base[k] = xb + cc * d;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unipc_corr_kernel(float* __restrict__ x, const float* __restrict__ base,
+                                                         const float* __restrict__ mt, const float* __restrict__ m1,
+                                                         float d, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 bv = ld4(base, i), tv = ld4(mt, i), mv = ld4(m1, i);
+      float4 r;
+      r.x = bv.x + d * (tv.x - mv.x); r.y = bv.y + d * (tv.y - mv.y);
+      r.z = bv.z + d * (tv.z - mv.z); r.w = bv.w + d * (tv.w - mv.w);
+      st4(x, i, r);
+    } else {
+      for (size_t k = i; k < n; ++k) x[k] = base[k] + d * (mt[k] - m1[k]);
+    }
+  }
+}
+
+inline int ew_grid(size_t n) {
+  const size_t blocks = (n / 4 + 255) / 256;
+  const size_t cap = 148 * 8;  // 8 resident CTAs of 256 threads per SM
+  return static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_nct_to_ntc(const float* src, void* dst, int B, int Csrc, int T, int ld_dst, int col0, int split,
+                              int shift, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (Csrc + 31) / 32, B);
+  nct_to_ntc_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), Csrc, T, ld_dst, col0, split, shift);
+  return cudaGetLastError();
+}
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
+  const size_t blocks = (n / 4 + 256) / 256;
+  f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return cudaGetLastError();
+}
+cudaError_t launch_temb(const TembParams& p, cudaStream_t st) {
+  if (p.emb_dim != 512 || p.sin_dim > 256 || p.sin_dim % 2) return cudaErrorInvalidValue;
+  temb_mlp_kernel<<<p.B, 512, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  dim3 grid((p.n_all + 8 * TP_ROWS_PER_WARP - 1) / (8 * TP_ROWS_PER_WARP), (p.B + TP_BCHUNK - 1) / TP_BCHUNK);
+  temb_proj_kernel<<<grid, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_axpbypcz(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
+                            int roundtrip_flag, float alp, float sig, size_t n, cudaStream_t st) {
+  axpbypcz_kernel<<<ew_grid(n), 256, 0, st>>>(x_out, x, m1, m0, a, b, c, roundtrip_flag, alp, sig, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_unipc_pred(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a,
+                              float b, float cp, float cc, int has_m0, size_t n, cudaStream_t st) {
+  unipc_pred_kernel<<<ew_grid(n), 256, 0, st>>>(xpred, base, x, m1, m0, a, b, cp, cc, has_m0, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_unipc_corr(float* x, const float* base, const float* mt, const float* m1, float d, size_t n,
+                              cudaStream_t st) {
+  unipc_corr_kernel<<<ew_grid(n), 256, 0, st>>>(x, base, mt, m1, d, n);
+  return cudaGetLastError();
+}
+
+}  // namespace dv

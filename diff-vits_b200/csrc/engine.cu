@@ -1,0 +1,761 @@
+// Plan builder + executor for the Diff-VITS denoiser (see engine.h).
+#include "engine.h"
+
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include <cudaTypedefs.h>
+
+namespace dv {
+
+// --------------------------------------------------------------------------------------------- TMA descriptors
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn(std::string& err) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    err = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
+                  std::string& err) {
+  auto fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(view_c), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(batch_stride_elems) * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(3d c=%d ld=%d L=%d B=%d) failed: %d", view_c, ld, L, B, (int)r);
+    err = buf;
+    return false;
+  }
+  return true;
+}
+
+bool make_tmap_2d(CUtensorMap* m, const void* base, int k_tot, int rows, int box_rows, std::string& err) {
+  auto fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_tot), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_tot) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(2d k=%d rows=%d) failed: %d", k_tot, rows, (int)r);
+    err = buf;
+    return false;
+  }
+  return true;
+}
+
+// --------------------------------------------------------------------------------------------- builder
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct Builder {
+  Plan& P;
+  size_t ws_cur = 0, scratch_cur = 0, scratch_max = 0;
+  std::vector<std::pair<size_t*, int>> scratch_fix;  // offsets that live in the scratch arena (patched at the end)
+  std::vector<std::string> wall_keys, ball_keys;
+  int ss_cur = 0;
+  int cross_layers = 0;
+  std::vector<TRef> kv_bufs;
+  TRef ehs_bf16;
+  std::string err;
+
+  explicit Builder(Plan& p) : P(p) {}
+
+  size_t ws_alloc(size_t bytes) {
+    size_t o = align_up(ws_cur, 1024);
+    ws_cur = o + bytes;
+    return o;
+  }
+  TRef act(int L, int C) {
+    TRef t;
+    t.L = L; t.C = C;
+    t.off = ws_alloc(static_cast<size_t>(P.B) * L * C * 2);
+    return t;
+  }
+  // scratch tensors: lifetime = one block; offsets are relative to the scratch arena until finalize()
+  static constexpr size_t SCRATCH_TAG = size_t(1) << 62;
+  TRef tmp(int L, int C) {
+    TRef t;
+    t.L = L; t.C = C;
+    size_t o = align_up(scratch_cur, 1024);
+    scratch_cur = o + static_cast<size_t>(P.B) * L * C * 2;
+    if (scratch_cur > scratch_max) scratch_max = scratch_cur;
+    t.off = SCRATCH_TAG | o;
+    return t;
+  }
+  void scratch_reset() { scratch_cur = 0; }
+
+  long long slot(const std::string& name, const std::string& recipe, std::vector<std::string> keys,
+                 const std::string& dtype, std::vector<int> shape) {
+    ParamSlot s;
+    s.name = name; s.recipe = recipe; s.keys = std::move(keys); s.dtype = dtype; s.shape = std::move(shape);
+    size_t n = 1;
+    for (int d : s.shape) n *= static_cast<size_t>(d);
+    s.bytes = n * (dtype == "bf16" ? 2 : 4);
+    s.off = align_up(P.param_bytes, 256);
+    P.param_bytes = s.off + s.bytes;
+    P.slots.push_back(s);
+    return static_cast<long long>(s.off);
+  }
+  long long vec(const std::string& key, int n) { return slot(key, "vec", {key}, "f32", {n}); }
+
+  size_t stats_alloc() {
+    size_t o = P.stats_bytes;
+    P.stats_bytes += static_cast<size_t>(P.B) * P.cfg.norm_num_groups * 2 * sizeof(double);
+    return o;  // relative to off_stats
+  }
+
+  // ---- op emitters
+  void emit_gn(std::vector<Op>& list, const std::string& tag, TRef x0, TRef x1, const std::string& norm_key, float eps,
+               bool silu, long long ss_off, TRef out) {
+    const int C = x0.C + (x1.valid() ? x1.C : 0);
+    Op st;
+    st.kind = OP_GN_STATS; st.tag = tag + ".stats";
+    memset(&st.gn, 0, sizeof st.gn);
+    st.gn.c0 = x0.C; st.gn.c1 = x1.valid() ? x1.C : 0;
+    st.gn.B = P.B; st.gn.L = x0.L; st.gn.G = P.cfg.norm_num_groups;
+    st.gn.eps = eps; st.gn.silu = silu ? 1 : 0; st.gn.ss_ld = P.n_all;  // n_all patched at finalize
+    st.gno.x0 = x0.off; st.gno.x1 = x1.valid() ? x1.off : 0; st.gno.out = out.off; st.gno.stats = stats_alloc();
+    st.gno.gamma = vec(norm_key + ".weight", C);
+    st.gno.beta = vec(norm_key + ".bias", C);
+    st.gno.ss = ss_off;
+    Op ap = st;
+    ap.kind = OP_GN_APPLY; ap.tag = tag + ".apply";
+    list.push_back(st);
+    list.push_back(ap);
+  }
+  void emit_ln(std::vector<Op>& list, const std::string& tag, TRef x, const std::string& key, TRef out) {
+    Op o;
+    o.kind = OP_LN; o.tag = tag;
+    o.lno.x = x.off; o.lno.out = out.off;
+    o.lno.gamma = vec(key + ".weight", x.C);
+    o.lno.beta = vec(key + ".bias", x.C);
+    o.ln.rows = P.B * x.L; o.ln.C = x.C; o.ln.eps = 1e-5f;
+    list.push_back(o);
+  }
+  Op& emit_gemm(std::vector<Op>& list, const std::string& tag) {
+    Op o;
+    o.kind = OP_GEMM; o.tag = tag;
+    for (int i = 0; i < GEMM_MAX_SRC; ++i) { o.g.view_l[i] = 0; o.g.view_c[i] = 0; }
+    list.push_back(o);
+    return list.back();
+  }
+  static void add_src(GemmDesc& g, TRef t) {
+    g.src[g.nsrc] = t; g.view_l[g.nsrc] = t.L; g.view_c[g.nsrc] = t.C; g.nsrc++;
+  }
+  static void add_seg(GemmDesc& g, int src, int row_off, int c0, int channels) {
+    GemmSeg s;
+    s.src = static_cast<int16_t>(src); s.row_off = static_cast<int16_t>(row_off);
+    s.c0 = static_cast<int16_t>(c0); s.npanels = static_cast<int16_t>(channels / 64);
+    g.seg[g.nseg++] = s;
+    g.k_tot += channels;
+  }
+
+  // Linear / 1x1 conv: out[L, N] = a[L, K] W^T (+bias) (+res)
+  void linear(std::vector<Op>& list, const std::string& tag, TRef a, const std::string& recipe,
+              std::vector<std::string> wkeys, const std::string& bias_key, int N, TRef res, TRef out, int out_mode) {
+    Op& o = emit_gemm(list, tag);
+    GemmDesc& g = o.g;
+    add_src(g, a);
+    add_seg(g, 0, 0, 0, a.C);
+    g.n = N; g.n_pad = round_up(N, 128);
+    g.w_off = slot(tag + ".W", recipe, std::move(wkeys), "bf16", {g.n_pad, g.k_tot});
+    if (!bias_key.empty())
+      g.bias_off = slot(tag + ".b", recipe == "geglu" ? "geglu_vec" : "vec", {bias_key}, "f32", {g.n_pad});
+    g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C;
+  }
+
+  // conv k3 s1 p1 over `a` (+ optional 1x1 shortcut over xs fused as extra K panels) (+ optional identity residual)
+  void conv3(std::vector<Op>& list, const std::string& tag, TRef a, int cin_real, const std::string& wkey,
+             const std::string& bkey, int N, const TRef* sc_src, int n_sc, const std::string& sc_key, TRef res,
+             TRef out, int out_mode, bool dynamic_out) {
+    Op& o = emit_gemm(list, tag);
+    GemmDesc& g = o.g;
+    add_src(g, a);
+    for (int tap = 0; tap < 3; ++tap) add_seg(g, 0, tap - 1, 0, a.C);
+    std::vector<std::string> wk = {wkey};
+    std::vector<std::string> bk = {bkey};
+    for (int i = 0; i < n_sc; ++i) {
+      add_src(g, sc_src[i]);
+      add_seg(g, g.nsrc - 1, 0, 0, sc_src[i].C);
+    }
+    if (n_sc) { wk.push_back(sc_key + ".weight"); bk.push_back(sc_key + ".bias"); }
+    g.n = N; g.n_pad = round_up(N, 128);
+    long long wo = slot(tag + ".W", "conv3", wk, "bf16", {g.n_pad, g.k_tot});
+    P.slots.back().shape.push_back(cin_real);  // [n_pad, k_tot, cin_real]: packer pads each tap from cin_real to a.C
+    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2;
+    g.w_off = wo;
+    g.bias_off = slot(tag + ".b", "vec_sum", bk, "f32", {g.n_pad});
+    g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
+  }
+
+  TRef resnet(const std::string& pfx, TRef x0, TRef x1, int cout) {
+    scratch_reset();
+    const int L = x0.L;
+    const int cin = x0.C + (x1.valid() ? x1.C : 0);
+    const float eps = P.cfg.norm_eps;
+    TRef a = tmp(L, cin);
+    emit_gn(P.ops, pfx + ".norm1", x0, x1, pfx + ".norm1", eps, true, -1, a);
+    TRef u = tmp(L, cout);
+    conv3(P.ops, pfx + ".conv1", a, cin, pfx + ".conv1.weight", pfx + ".conv1.bias", cout, nullptr, 0, "", TRef(), u,
+          GEMM_OUT_BF16, false);
+    // time scale/shift: rows [ss_cur, ss_cur + 2*cout) of the stacked time_emb_proj
+    wall_keys.push_back(pfx + ".time_emb_proj.weight");
+    ball_keys.push_back(pfx + ".time_emb_proj.bias");
+    const long long ss_off = ss_cur;
+    ss_cur += 2 * cout;
+    TRef v = tmp(L, cout);
+    emit_gn(P.ops, pfx + ".norm2", u, TRef(), pfx + ".norm2", eps, true, ss_off, v);
+    TRef y = act(L, cout);
+    if (cin != cout) {
+      TRef sc[2] = {x0, x1};
+      conv3(P.ops, pfx + ".conv2", v, cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, sc, x1.valid() ? 2 : 1,
+            pfx + ".conv_shortcut", TRef(), y, GEMM_OUT_BF16, false);
+    } else {
+      if (x1.valid()) { err = "identity shortcut over a channel concat is not supported"; return y; }
+      conv3(P.ops, pfx + ".conv2", v, cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, nullptr, 0, "", x0, y,
+            GEMM_OUT_BF16, false);
+    }
+    return y;
+  }
+
+  TRef transformer(const std::string& pfx, TRef y) {
+    scratch_reset();
+    const int L = y.L, C = y.C, H = P.cfg.num_heads, D = C / H;
+    const std::string tb = pfx + ".transformer_blocks.0";
+    TRef g = tmp(L, C);
+    emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
+    TRef z = tmp(L, C);
+    linear(P.ops, pfx + ".proj_in", g, "linear", {pfx + ".proj_in.weight"}, pfx + ".proj_in.bias", C, TRef(), z,
+           GEMM_OUT_BF16);
+    TRef nrm = tmp(L, C);
+    TRef qkv = tmp(L, 3 * C);
+    TRef ao = tmp(L, C);
+    // --- self attention
+    emit_ln(P.ops, tb + ".norm1", z, tb + ".norm1", nrm);
+    linear(P.ops, tb + ".attn1.qkv", nrm, "linear",
+           {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, "", 3 * C, TRef(), qkv,
+           GEMM_OUT_BF16);
+    {
+      Op o;
+      o.kind = OP_ATTN; o.tag = tb + ".attn1";
+      memset(&o.at, 0, sizeof o.at);
+      o.ato.q = qkv.off; o.ato.k = qkv.off + static_cast<size_t>(C) * 2; o.ato.v = qkv.off + static_cast<size_t>(C) * 4;
+      o.ato.o = ao.off; o.ato.cross = false;
+      o.at.ld_q = o.at.ld_k = o.at.ld_v = 3 * C; o.at.ld_o = C;
+      o.at.bs_q = o.at.bs_k = o.at.bs_v = static_cast<long long>(L) * 3 * C; o.at.bs_o = static_cast<long long>(L) * C;
+      o.at.B = P.B; o.at.H = H; o.at.Lq = L; o.at.Lk = L; o.at.D = D;
+      o.at.scale = 1.0f / sqrtf(static_cast<float>(D));
+      P.ops.push_back(o);
+    }
+    linear(P.ops, tb + ".attn1.to_out", ao, "linear", {tb + ".attn1.to_out.0.weight"}, tb + ".attn1.to_out.0.bias", C, z,
+           z, GEMM_OUT_BF16);
+    // --- cross attention to the prompt (K/V hoisted into prep_ops)
+    TRef kv;
+    kv.L = P.Tp; kv.C = 2 * C;
+    kv.off = ws_alloc(static_cast<size_t>(P.B) * P.Tp * 2 * C * 2);
+    linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
+           2 * C, TRef(), kv, GEMM_OUT_BF16);
+    emit_ln(P.ops, tb + ".norm2", z, tb + ".norm2", nrm);
+    TRef q = qkv;  // reuse the first C columns' storage as a dense [L, C] tensor
+    q.C = C;
+    linear(P.ops, tb + ".attn2.to_q", nrm, "linear", {tb + ".attn2.to_q.weight"}, "", C, TRef(), q, GEMM_OUT_BF16);
+    {
+      Op o;
+      o.kind = OP_ATTN; o.tag = tb + ".attn2";
+      memset(&o.at, 0, sizeof o.at);
+      o.ato.q = q.off; o.ato.k = kv.off; o.ato.v = kv.off + static_cast<size_t>(C) * 2; o.ato.o = ao.off;
+      o.ato.cross = true;
+      o.at.ld_q = C; o.at.ld_k = o.at.ld_v = 2 * C; o.at.ld_o = C;
+      o.at.bs_q = static_cast<long long>(L) * C; o.at.bs_k = o.at.bs_v = static_cast<long long>(P.Tp) * 2 * C;
+      o.at.bs_o = static_cast<long long>(L) * C;
+      o.at.B = P.B; o.at.H = H; o.at.Lq = L; o.at.Lk = P.Tp; o.at.D = D;
+      o.at.scale = 1.0f / sqrtf(static_cast<float>(D));
+      P.ops.push_back(o);
+    }
+    linear(P.ops, tb + ".attn2.to_out", ao, "linear", {tb + ".attn2.to_out.0.weight"}, tb + ".attn2.to_out.0.bias", C, z,
+           z, GEMM_OUT_BF16);
+    // --- GEGLU feed-forward
+    emit_ln(P.ops, tb + ".norm3", z, tb + ".norm3", nrm);
+    TRef gg = tmp(L, 4 * C);
+    linear(P.ops, tb + ".ff.geglu", nrm, "geglu", {tb + ".ff.net.0.proj.weight"}, tb + ".ff.net.0.proj.bias", 8 * C,
+           TRef(), gg, GEMM_OUT_GEGLU);
+    linear(P.ops, tb + ".ff.out", gg, "linear", {tb + ".ff.net.2.weight"}, tb + ".ff.net.2.bias", C, z, z, GEMM_OUT_BF16);
+    // --- proj_out + residual
+    TRef yo = act(L, C);
+    linear(P.ops, pfx + ".proj_out", z, "linear", {pfx + ".proj_out.weight"}, pfx + ".proj_out.bias", C, y, yo,
+           GEMM_OUT_BF16);
+    return yo;
+  }
+
+  TRef downsample(const std::string& key, TRef x) {  // conv k3 s2 p1 through the [L/2, 2C] view
+    const int C = x.C, Lo = x.L / 2;
+    TRef out = act(Lo, C);
+    Op& o = emit_gemm(P.ops, key);
+    GemmDesc& g = o.g;
+    add_src(g, x);
+    g.view_l[0] = Lo; g.view_c[0] = 2 * C;
+    add_seg(g, 0, -1, C, C);  // tap 0: x[2l-1] = second half of view row l-1
+    add_seg(g, 0, 0, 0, C);   // tap 1: x[2l]
+    add_seg(g, 0, 0, C, C);   // tap 2: x[2l+1]
+    g.n = C; g.n_pad = round_up(C, 128);
+    g.w_off = slot(key + ".W", "conv3", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
+    P.slots.back().shape.push_back(C);
+    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2;
+    g.bias_off = slot(key + ".b", "vec_sum", {key + ".bias"}, "f32", {g.n_pad});
+    g.out = out; g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
+    return out;
+  }
+
+  TRef upsample(const std::string& key, TRef x) {  // nearest 2x + conv k3 p1, folded: N = 2C over the low-res rows
+    const int C = x.C;
+    TRef out2 = act(x.L, 2 * C);
+    Op& o = emit_gemm(P.ops, key);
+    GemmDesc& g = o.g;
+    add_src(g, x);
+    for (int tap = 0; tap < 3; ++tap) add_seg(g, 0, tap - 1, 0, C);
+    g.n = 2 * C; g.n_pad = round_up(2 * C, 128);
+    g.w_off = slot(key + ".W", "conv3_up2", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
+    g.bias_off = slot(key + ".b", "vec_dup2", {key + ".bias"}, "f32", {g.n_pad});
+    g.out = out2; g.l_out = x.L; g.out_mode = GEMM_OUT_BF16; g.ld_out = 2 * C;
+    TRef out = out2;
+    out.L = 2 * x.L; out.C = C;  // same bytes viewed as [2L, C]
+    return out;
+  }
+};
+
+std::string json_escape(const std::string& s) { return s; }  // keys are [A-Za-z0-9_.] only
+
+}  // namespace
+
+int Plan::build(std::string& err) {
+  const dv_unet_cfg& c = cfg;
+  n_levels = c.n_levels;
+  if (n_levels < 2 || n_levels > 8) { err = "n_levels must be in [2, 8]"; return DV_ERR_INVALID; }
+  if (c.layers_per_block < 1 || c.layers_per_block > 4) { err = "layers_per_block must be in [1, 4]"; return DV_ERR_INVALID; }
+  if (B < 1 || T < 1 || Tp < 1) { err = "B, T, Tp must be positive"; return DV_ERR_INVALID; }
+  if (T % (1 << (n_levels - 1)) != 0) {
+    err = "T must be a multiple of 2^(n_levels-1) on the accelerated path (nearest-resize to odd lengths not built yet)";
+    return DV_ERR_UNSUPPORTED;
+  }
+  for (int i = 0; i < n_levels; ++i) {
+    const int ch = c.block_out_channels[i];
+    if (ch % 64 != 0 || ch > 1024) { err = "block_out_channels must be multiples of 64 (<= 1024)"; return DV_ERR_UNSUPPORTED; }
+    if (ch % c.num_heads != 0) { err = "channels not divisible by heads"; return DV_ERR_INVALID; }
+    const int d = ch / c.num_heads;
+    if (i < n_levels - 1 || true) {
+      if (d != 16 && d != 32 && d != 48 && d != 64) { err = "head dim must be 16/32/48/64"; return DV_ERR_UNSUPPORTED; }
+    }
+    if (ch % (8 * c.norm_num_groups) != 0) { err = "channels/groups must be a multiple of 8"; return DV_ERR_UNSUPPORTED; }
+  }
+  if (c.cross_attention_dim % 64 != 0) { err = "cross_attention_dim must be a multiple of 64"; return DV_ERR_UNSUPPORTED; }
+  if (c.x_channels < 1 || c.x_channels > c.in_channels) { err = "x_channels out of range"; return DV_ERR_INVALID; }
+  if (c.out_channels > 128) { err = "out_channels > 128 not supported"; return DV_ERR_UNSUPPORTED; }
+  emb_dim = 4 * c.block_out_channels[0];
+  if (emb_dim != 512) { err = "time_embed_dim must be 512 (block_out_channels[0] == 128)"; return DV_ERR_UNSUPPORTED; }
+  cin_pad = round_up(c.in_channels, 64);
+
+  Builder b(*this);
+  const int C0 = c.block_out_channels[0];
+
+  // ---- persistent regions
+  off_xin = b.ws_alloc(static_cast<size_t>(B) * T * cin_pad * 2);
+  b.ehs_bf16.L = Tp; b.ehs_bf16.C = c.cross_attention_dim;
+  b.ehs_bf16.off = b.ws_alloc(static_cast<size_t>(B) * Tp * c.cross_attention_dim * 2);
+  off_ehs = b.ehs_bf16.off;
+  off_aug = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4);
+  off_embact = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4);
+  off_kvlen = b.ws_alloc(static_cast<size_t>(B) * 4);
+  const size_t xbytes = static_cast<size_t>(B) * c.x_channels * T * 4;
+  const size_t obytes = static_cast<size_t>(B) * c.out_channels * T * 4;
+  off_x = b.ws_alloc(xbytes);
+  off_xp = b.ws_alloc(xbytes);
+  off_base = b.ws_alloc(xbytes);
+  off_h0 = b.ws_alloc(obytes);
+  off_h1 = b.ws_alloc(obytes);
+  off_ttab = b.ws_alloc(4096 * 4);
+
+  // ---- time embedding parameters (fp32; tiny GEMVs on CUDA cores)
+  p_freqs = b.slot("time.freqs", "time_freqs", {}, "f32", {C0 / 2});
+  p_w1 = b.slot("time.w1t", "mat_t", {"time_embedding.linear_1.weight"}, "f32", {C0, emb_dim});
+  p_b1 = b.vec("time_embedding.linear_1.bias", emb_dim);
+  p_w2 = b.slot("time.w2t", "mat_t", {"time_embedding.linear_2.weight"}, "f32", {emb_dim, emb_dim});
+  p_b2 = b.vec("time_embedding.linear_2.bias", emb_dim);
+
+  // ---- the network (unet_1d_condition.py:943-1032)
+  TRef xin;
+  xin.off = off_xin; xin.L = T; xin.C = cin_pad;
+  std::vector<TRef> skips;
+  TRef h = b.act(T, C0);
+  b.conv3(ops, "conv_in", xin, c.in_channels, "conv_in.weight", "conv_in.bias", C0, nullptr, 0, "", TRef(), h,
+          GEMM_OUT_BF16, false);
+  skips.push_back(h);
+  int ch = C0;
+  for (int i = 0; i < n_levels; ++i) {
+    const int co = c.block_out_channels[i];
+    const bool last = (i == n_levels - 1);
+    const std::string bp = "down_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      h = b.resnet(bp + ".resnets." + std::to_string(j), h, TRef(), co);
+      if (!last) h = b.transformer(bp + ".attentions." + std::to_string(j), h);
+      skips.push_back(h);
+      ch = co;
+    }
+    if (!last) {
+      h = b.downsample(bp + ".downsamplers.0.conv", h);
+      skips.push_back(h);
+    }
+  }
+  h = b.resnet("mid_block.resnets.0", h, TRef(), ch);
+  h = b.transformer("mid_block.attentions.0", h);
+  h = b.resnet("mid_block.resnets.1", h, TRef(), ch);
+  for (int i = 0; i < n_levels; ++i) {
+    const int co = c.block_out_channels[n_levels - 1 - i];
+    const bool final_block = (i == n_levels - 1);
+    const std::string bp = "up_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block + 1; ++j) {
+      TRef skip = skips.back();
+      skips.pop_back();
+      if (skip.L != h.L) { err = "internal: skip length mismatch"; return DV_ERR_INVALID; }
+      h = b.resnet(bp + ".resnets." + std::to_string(j), h, skip, co);
+      if (i > 0) h = b.transformer(bp + ".attentions." + std::to_string(j), h);
+    }
+    if (!final_block) h = b.upsample(bp + ".upsamplers.0.conv", h);
+  }
+  if (!b.err.empty()) { err = b.err; return DV_ERR_UNSUPPORTED; }
+  {
+    b.scratch_reset();
+    TRef a = b.tmp(T, C0);
+    b.emit_gn(ops, "conv_norm_out", h, TRef(), "conv_norm_out", c.norm_eps, true, -1, a);
+    TRef dummy;
+    dummy.L = T; dummy.C = c.out_channels;
+    b.conv3(ops, "conv_out", a, C0, "conv_out.weight", "conv_out.bias", c.out_channels, nullptr, 0, "", TRef(), dummy,
+            GEMM_OUT_F32_NCL, true);
+  }
+
+  // ---- stacked time_emb_proj
+  n_all = b.ss_cur;
+  p_wall = b.slot("time.w_all", "rows", b.wall_keys, "f32", {n_all, emb_dim});
+  p_ball = b.slot("time.b_all", "rows", b.ball_keys, "f32", {n_all});
+  off_ss = b.ws_alloc(static_cast<size_t>(B) * n_all * 4);
+  off_stats = b.ws_alloc(stats_bytes);
+  const size_t scratch_base = b.ws_alloc(b.scratch_max);
+  ws_bytes = align_up(b.ws_cur, 1024);
+
+  // ---- resolve scratch-relative offsets and n_all
+  auto fix = [&](size_t& o) { if (o & Builder::SCRATCH_TAG) o = (o & ~Builder::SCRATCH_TAG) + scratch_base; };
+  auto fix_list = [&](std::vector<Op>& list) {
+    for (Op& o : list) {
+      switch (o.kind) {
+        case OP_GEMM:
+          for (int i = 0; i < o.g.nsrc; ++i) fix(o.g.src[i].off);
+          if (o.g.res.valid()) fix(o.g.res.off);
+          fix(o.g.out.off);
+          break;
+        case OP_GN_STATS: case OP_GN_APPLY:
+          fix(o.gno.x0); fix(o.gno.x1); fix(o.gno.out);
+          o.gn.ss_ld = n_all;
+          break;
+        case OP_LN: fix(o.lno.x); fix(o.lno.out); break;
+        case OP_ATTN: {
+          // q/k/v offsets may carry an added column offset: fix preserves low bits
+          fix(o.ato.q); fix(o.ato.k); fix(o.ato.v); fix(o.ato.o);
+          break;
+        }
+      }
+    }
+  };
+  fix_list(ops);
+  fix_list(prep_ops);
+
+  // ---- manifest
+  std::ostringstream js;
+  js << "[";
+  for (size_t i = 0; i < slots.size(); ++i) {
+    const ParamSlot& s = slots[i];
+    if (i) js << ",";
+    js << "{\"name\":\"" << json_escape(s.name) << "\",\"recipe\":\"" << s.recipe << "\",\"dtype\":\"" << s.dtype
+       << "\",\"offset\":" << s.off << ",\"nbytes\":" << s.bytes << ",\"shape\":[";
+    for (size_t k = 0; k < s.shape.size(); ++k) js << (k ? "," : "") << s.shape[k];
+    js << "],\"keys\":[";
+    for (size_t k = 0; k < s.keys.size(); ++k) js << (k ? "," : "") << "\"" << json_escape(s.keys[k]) << "\"";
+    js << "]}";
+  }
+  js << "]";
+  manifest = js.str();
+  param_bytes = align_up(param_bytes, 256);
+  return DV_OK;
+}
+
+// --------------------------------------------------------------------------------------------- bind
+int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& err) {
+  if (!workspace || !prm) { err = "null workspace/params"; return DV_ERR_INVALID; }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(prm) & 255)) {
+    err = "workspace and params must be 256-byte aligned";
+    return DV_ERR_INVALID;
+  }
+  ws = static_cast<uint8_t*>(workspace);
+  params = static_cast<const uint8_t*>(prm);
+  cudaError_t ce = cudaMemsetAsync(ws, 0, ws_bytes, st);
+  if (ce != cudaSuccess) { err = cudaGetErrorString(ce); return DV_ERR_CUDA; }
+
+  auto pf = [&](long long off) -> const float* {
+    return off < 0 ? nullptr : reinterpret_cast<const float*>(params + off);
+  };
+  auto bind_list = [&](std::vector<Op>& list) -> bool {
+    for (Op& o : list) {
+      if (o.kind == OP_GEMM) {
+        GemmDesc& g = o.g;
+        GemmParams& p = o.gp;
+        memset(&p, 0, sizeof p);
+        for (int i = 0; i < GEMM_MAX_SRC; ++i) {
+          const int s = i < g.nsrc ? i : 0;  // unused maps alias source 0 so prefetch.tensormap stays valid
+          const TRef& t = g.src[s];
+          if (!make_tmap_3d(&p.mapA[i], ws + t.off, g.view_c[s], g.view_c[s], g.view_l[s], B,
+                            static_cast<size_t>(t.L) * t.C, err))
+            return false;
+        }
+        if (!make_tmap_2d(&p.mapW, params + g.w_off, g.k_tot, g.n_pad, 128, err)) return false;
+        for (int i = 0; i < g.nseg; ++i) p.seg[i] = g.seg[i];
+        p.nseg = g.nseg;
+        p.B = B; p.L = g.l_out; p.N = g.n; p.n_pad = g.n_pad;
+        p.tiles_per_batch = (g.l_out + 127) / 128;
+        p.out_mode = g.out_mode;
+        p.bias = pf(g.bias_off);
+        p.res = g.res.valid() ? ws + g.res.off : nullptr;
+        p.ld_res = g.res.valid() ? g.res.C : 0;
+        p.out = g.out_dynamic ? nullptr : ws + g.out.off;
+        p.ld_out = g.ld_out;
+      } else if (o.kind == OP_GN_STATS || o.kind == OP_GN_APPLY) {
+        o.gn.x0 = ws + o.gno.x0;
+        o.gn.x1 = o.gn.c1 ? ws + o.gno.x1 : nullptr;
+        o.gn.out = ws + o.gno.out;
+        o.gn.stats = reinterpret_cast<double*>(ws + off_stats + o.gno.stats);
+        o.gn.gamma = pf(o.gno.gamma);
+        o.gn.beta = pf(o.gno.beta);
+        o.gn.scale_shift = o.gno.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + o.gno.ss;
+      } else if (o.kind == OP_LN) {
+        o.ln.x = ws + o.lno.x; o.ln.out = ws + o.lno.out;
+        o.ln.gamma = pf(o.lno.gamma); o.ln.beta = pf(o.lno.beta);
+      } else if (o.kind == OP_ATTN) {
+        o.at.q = ws + o.ato.q; o.at.k = ws + o.ato.k; o.at.v = ws + o.ato.v; o.at.o = ws + o.ato.o;
+        o.at.kv_len = nullptr;  // set in prompt_prepare
+      }
+    }
+    return true;
+  };
+  if (!bind_list(ops) || !bind_list(prep_ops)) return DV_ERR_CUDA;
+  bound = true;
+  prompt_ready = false;
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key = 0; }
+  return DV_OK;
+}
+
+// --------------------------------------------------------------------------------------------- execution
+#define DV_CK(call)                                                                     \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+      return DV_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches) {
+  for (Op& o : list) {
+    cudaError_t e = cudaSuccess;
+    switch (o.kind) {
+      case OP_GEMM:
+        if (o.g.out_dynamic) {
+          GemmParams p = o.gp;
+          p.out = dyn_out;
+          e = launch_gemm_tc(p, st);
+        } else {
+          e = launch_gemm_tc(o.gp, st);
+        }
+        break;
+      case OP_GN_STATS: e = launch_gn_stats(o.gn, st); break;
+      case OP_GN_APPLY: e = launch_gn_apply(o.gn, st); break;
+      case OP_LN: e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st); break;
+      case OP_ATTN: {
+        AttnParams a = o.at;
+        if (o.ato.cross && has_kvlen) a.kv_len = reinterpret_cast<const int*>(ws + off_kvlen);
+        e = launch_attention(a, st);
+        break;
+      }
+    }
+    if (e != cudaSuccess) {
+      err = "launch " + o.tag + ": " + cudaGetErrorString(e);
+      return DV_ERR_CUDA;
+    }
+    if (launches) ++*launches;
+  }
+  return DV_OK;
+}
+
+int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_len, cudaStream_t st, std::string& err) {
+  if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
+  if (!ehs) { err = "ehs is null"; return DV_ERR_INVALID; }
+  const size_t n = static_cast<size_t>(B) * Tp * cfg.cross_attention_dim;
+  DV_CK(launch_f32_to_bf16(ehs, ws + off_ehs, n, st));
+  has_aug = aug != nullptr;
+  if (aug) DV_CK(cudaMemcpyAsync(ws + off_aug, aug, static_cast<size_t>(B) * emb_dim * 4, cudaMemcpyDeviceToDevice, st));
+  has_kvlen = kv_len != nullptr;
+  if (kv_len) DV_CK(cudaMemcpyAsync(ws + off_kvlen, kv_len, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  int rc = enqueue_ops(prep_ops, nullptr, st, err, nullptr);
+  if (rc != DV_OK) return rc;
+  prompt_ready = true;
+  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key = 0; }
+  return DV_OK;
+}
+
+int Plan::set_cond(const float* cond, cudaStream_t st, std::string& err) {
+  if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
+  const int cc = cfg.in_channels - cfg.x_channels;
+  if (cc <= 0) return DV_OK;
+  DV_CK(launch_nct_to_ntc(cond, ws + off_xin, B, cc, T, cin_pad, cfg.x_channels, 1 << 30, 0, st));
+  return DV_OK;
+}
+
+int Plan::forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
+                  std::string& err, int* launches) {
+  if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
+  if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
+  DV_CK(cudaMemsetAsync(ws + off_stats, 0, stats_bytes, st));
+  DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st));
+  TembParams tp;
+  tp.t = t; tp.t_stride = t_stride;
+  tp.freqs = reinterpret_cast<const float*>(params + p_freqs);
+  tp.w1 = reinterpret_cast<const float*>(params + p_w1); tp.b1 = reinterpret_cast<const float*>(params + p_b1);
+  tp.w2 = reinterpret_cast<const float*>(params + p_w2); tp.b2 = reinterpret_cast<const float*>(params + p_b2);
+  tp.aug = has_aug ? reinterpret_cast<const float*>(ws + off_aug) : nullptr;
+  tp.emb_act = reinterpret_cast<float*>(ws + off_embact);
+  tp.w_all = reinterpret_cast<const float*>(params + p_wall); tp.b_all = reinterpret_cast<const float*>(params + p_ball);
+  tp.ss_all = reinterpret_cast<float*>(ws + off_ss);
+  tp.B = B; tp.n_all = n_all; tp.sin_dim = cfg.block_out_channels[0]; tp.emb_dim = emb_dim;
+  DV_CK(launch_temb(tp, st));
+  if (launches) *launches += 3;
+  return enqueue_ops(ops, out, st, err, launches);
+}
+
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+int Plan::sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
+                 std::string& err) {
+  if (!bound || !prompt_ready) { err = "plan not bound / prompt not prepared"; return DV_ERR_STATE; }
+  if (nsteps < 1 || nsteps > 4096) { err = "nsteps out of range"; return DV_ERR_INVALID; }
+  if (sampler != DV_SAMPLER_DPMPP_2M && sampler != DV_SAMPLER_UNIPC_BH2) { err = "unknown sampler"; return DV_ERR_INVALID; }
+  if (cfg.x_channels != cfg.out_channels) { err = "sampler needs x_channels == out_channels"; return DV_ERR_INVALID; }
+  if (!t_in || !coef || !x) { err = "null argument"; return DV_ERR_INVALID; }
+  const size_t n = static_cast<size_t>(B) * cfg.x_channels * T;
+  float* X = reinterpret_cast<float*>(ws + off_x);
+  float* XP = reinterpret_cast<float*>(ws + off_xp);
+  float* BASE = reinterpret_cast<float*>(ws + off_base);
+  float* H[2] = {reinterpret_cast<float*>(ws + off_h0), reinterpret_cast<float*>(ws + off_h1)};
+  const float* ttab = reinterpret_cast<const float*>(ws + off_ttab);
+  const bool rt = (flags & DV_SAMPLE_ROUNDTRIP) != 0;
+
+  // One model evaluation per step (NFE == nsteps); history slots rotate by pointer at enqueue time.
+  auto body = [&](cudaStream_t s, int* launches) -> int {
+    int cur = 0;  // H[cur] = newest model output m_{-1}, H[cur^1] = m_{-2}
+    int rc = forward(X, 1, ttab, 0, H[cur], s, err, launches);
+    if (rc != DV_OK) return rc;
+    for (int i = 0; i < nsteps; ++i) {
+      const float* c = coef + static_cast<size_t>(i) * 8;
+      const bool last = (i == nsteps - 1);
+      if (sampler == DV_SAMPLER_DPMPP_2M) {
+        const bool has_prev = c[3] != 0.f;
+        DV_CK(launch_axpbypcz(X, X, H[cur], has_prev ? H[cur ^ 1] : nullptr, c[0], c[1], c[2], rt ? 1 : 0, c[4], c[5], n, s));
+        ++*launches;
+        if (!last) {
+          cur ^= 1;
+          rc = forward(X, 1, ttab + i + 1, 0, H[cur], s, err, launches);
+          if (rc != DV_OK) return rc;
+        }
+      } else {
+        const bool has_prev = c[5] != 0.f, use_corr = c[6] != 0.f;
+        if (use_corr) {
+          if (last) { err = "UniPC table: corrector on the last step"; return DV_ERR_INVALID; }
+          DV_CK(launch_unipc_pred(XP, BASE, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
+          ++*launches;
+          rc = forward(XP, 1, ttab + i + 1, 0, H[cur ^ 1], s, err, launches);  // m_t overwrites the consumed m_{-2}
+          if (rc != DV_OK) return rc;
+          DV_CK(launch_unipc_corr(X, BASE, H[cur ^ 1], H[cur], c[4], n, s));
+          ++*launches;
+          cur ^= 1;
+        } else {
+          DV_CK(launch_unipc_pred(X, nullptr, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
+          ++*launches;
+        }
+      }
+    }
+    return DV_OK;
+  };
+
+  DV_CK(cudaMemcpyAsync(ws + off_ttab, t_in, static_cast<size_t>(nsteps) * 4, cudaMemcpyHostToDevice, st));
+  DV_CK(cudaMemcpyAsync(X, x, n * 4, cudaMemcpyDeviceToDevice, st));
+  if (flags & DV_SAMPLE_NO_GRAPH) {
+    int launches = 0;
+    int rc = body(st, &launches);
+    if (rc != DV_OK) return rc;
+    last_sample_launches = launches;
+  } else {
+    uint64_t key = 1469598103934665603ull;
+    key = fnv1a(key, &sampler, sizeof sampler);
+    key = fnv1a(key, &nsteps, sizeof nsteps);
+    key = fnv1a(key, &rt, sizeof rt);
+    key = fnv1a(key, coef, static_cast<size_t>(nsteps) * 8 * 4);
+    if (!graph_exec || key != graph_key) {
+      if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+      if (!cap_stream) DV_CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+      DV_CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+      int launches = 0;
+      int rc = body(cap_stream, &launches);
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+      if (rc != DV_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) { err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return DV_ERR_CUDA; }
+      ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { graph_exec = nullptr; err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return DV_ERR_CUDA; }
+      graph_key = key;
+      graph_launches = launches;
+    }
+    DV_CK(cudaGraphLaunch(graph_exec, st));
+    last_sample_launches = graph_launches;
+  }
+  DV_CK(cudaMemcpyAsync(x, X, n * 4, cudaMemcpyDeviceToDevice, st));
+  return DV_OK;
+}
+
+Plan::~Plan() {
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (cap_stream) cudaStreamDestroy(cap_stream);
+}
+
+}  // namespace dv

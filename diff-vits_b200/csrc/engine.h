@@ -1,0 +1,101 @@
+// Plan: the UNet1DConditionModel forward pass at a fixed (B, T, Tp), flattened at build time into a linear
+// program of kernel launches over one caller-owned workspace. Mirrors the module order of
+// unet1d/unet_1d_condition.py:743-1037 with step-invariant work hoisted.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/diffvits_b200.h"
+#include "kernels.h"
+
+namespace dv {
+
+struct TRef {  // bf16 channel-last tensor [B, L, C] at byte offset `off` of the workspace
+  size_t off = 0;
+  int L = 0, C = 0;
+  bool valid() const { return C > 0; }
+};
+
+struct ParamSlot {
+  std::string name;               // engine-side slot name
+  std::string recipe;             // packing recipe implemented by the host packer
+  std::vector<std::string> keys;  // reference state_dict keys consumed
+  std::string dtype;              // "bf16" | "f32"
+  std::vector<int> shape;
+  size_t off = 0, bytes = 0;
+};
+
+enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_LN, OP_ATTN };
+
+struct GemmDesc {
+  int nsrc = 0;
+  TRef src[GEMM_MAX_SRC];
+  int view_l[GEMM_MAX_SRC], view_c[GEMM_MAX_SRC];  // TMA view (stride-2 conv reads [L/2, 2C])
+  int nseg = 0;
+  GemmSeg seg[GEMM_MAX_SEG];
+  size_t w_off = 0; int k_tot = 0, n = 0, n_pad = 0;
+  long long bias_off = -1;
+  TRef res; TRef out;
+  int l_out = 0, out_mode = GEMM_OUT_BF16, ld_out = 0;
+  bool out_dynamic = false;  // conv_out: destination supplied per call
+};
+
+struct Op {
+  OpKind kind;
+  std::string tag;
+  GemmDesc g; GemmParams gp;
+  GnParams gn;
+  struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; } ln;
+  AttnParams at;
+  // deferred (offset-based) descriptions resolved in bind()
+  struct { size_t x0, x1, out, stats; long long gamma, beta, ss; } gno;
+  struct { size_t x, out; long long gamma, beta; } lno;
+  struct { size_t q, k, v, o; bool cross; } ato;
+};
+
+struct Plan {
+  dv_unet_cfg cfg;
+  int B, T, Tp;
+  int n_levels, emb_dim, cin_pad;
+  std::vector<ParamSlot> slots;
+  size_t param_bytes = 0, ws_bytes = 0;
+  std::vector<Op> ops;       // one denoiser call
+  std::vector<Op> prep_ops;  // prompt-side hoisted projections
+  std::string manifest;
+
+  // workspace regions (byte offsets)
+  size_t off_xin = 0, off_ehs = 0, off_aug = 0, off_embact = 0, off_ss = 0, off_stats = 0, off_kvlen = 0;
+  size_t off_x = 0, off_xp = 0, off_base = 0, off_h0 = 0, off_h1 = 0, off_ttab = 0;
+  size_t stats_bytes = 0;
+  int n_all = 0;  // total time_emb_proj outputs
+  long long p_freqs = -1, p_w1 = -1, p_b1 = -1, p_w2 = -1, p_b2 = -1, p_wall = -1, p_ball = -1;
+
+  // bound state
+  uint8_t* ws = nullptr;
+  const uint8_t* params = nullptr;
+  bool bound = false, prompt_ready = false, has_aug = false, has_kvlen = false;
+  int last_sample_launches = 0;
+
+  // graph cache for dv_sample
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  uint64_t graph_key = 0;
+  int graph_launches = 0;
+
+  int build(std::string& err);
+  int bind(void* workspace, const void* params, cudaStream_t st, std::string& err);
+  int enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches);
+  int forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
+              std::string& err, int* launches);
+  int prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_len, cudaStream_t st, std::string& err);
+  int set_cond(const float* cond, cudaStream_t st, std::string& err);
+  int sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
+             std::string& err);
+  ~Plan();
+};
+
+bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
+                  std::string& err);
+bool make_tmap_2d(CUtensorMap* m, const void* base, int k_tot, int rows, int box_rows, std::string& err);
+
+}  // namespace dv

@@ -1,0 +1,112 @@
+// Launch-level interface of the sm_100a kernels (host side). All launches are stream-ordered, never
+// synchronise, never allocate: safe inside CUDA-graph capture.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace dv {
+
+// ------------------------------------------------------------------ tap-GEMM (conv1d k3 / 1x1 / linear)
+// out[b, l, n] = epi( sum over K panels  A_seg[b, l + row_off, c0 + 64*p : +64] . W[n, k_run : +64] )
+// A sources are channel-last bf16 tensors [B, L, C] behind 3-D TMA maps (zero fill outside [0, L) gives the
+// conv padding); W is bf16 [N_pad, K_tot] K-major behind a 2-D TMA map.
+constexpr int GEMM_MAX_SRC = 3;
+constexpr int GEMM_MAX_SEG = 6;
+
+enum GemmOut : int {
+  GEMM_OUT_BF16 = 0,     // out bf16 [B, L, ld_out], columns [0, N)
+  GEMM_OUT_F32_NCL = 1,  // out fp32 [B, N, L]  (transposed store, used by conv_out)
+  GEMM_OUT_GEGLU = 2,    // tile columns [0,64) = u, [64,128) = gate: out bf16 [B, L, ld_out], N/2 columns
+};
+
+struct GemmSeg {
+  int16_t src;      // index into mapA
+  int16_t row_off;  // row offset added to the tile's first row (-1, 0, +1 for the three conv taps)
+  int16_t c0;       // first channel of the segment in the source tensor
+  int16_t npanels;  // number of 64-channel panels
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap mapA[GEMM_MAX_SRC];
+  CUtensorMap mapW;
+  GemmSeg seg[GEMM_MAX_SEG];
+  int nseg;
+  int B, L, N;          // L = output rows per batch item, N = real output columns
+  int n_pad;            // N rounded up to the N tile
+  int tiles_per_batch;  // ceil(L / 128)
+  int out_mode;
+  const float* bias;    // [n_pad] or nullptr
+  const void* res;      // bf16 [B, L, ld_res] residual added before the store, or nullptr
+  int ld_res;
+  void* out;
+  int ld_out;
+};
+
+cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st);
+// Debug/reference implementation of exactly the same contract on CUDA cores (plain loads, fp32 FMA).
+// Used by tests to cross-check the tcgen05 kernel; never used by the engine.
+struct GemmRefSrc { const void* ptr; int L, C, ld; };
+cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const void* W, int k_tot, cudaStream_t st);
+
+// ------------------------------------------------------------------ attention (flash style, bf16 in, fp32 softmax)
+struct AttnParams {
+  const void* q; const void* k; const void* v; void* o;   // bf16
+  int ld_q, ld_k, ld_v, ld_o;                              // row strides in elements
+  long long bs_q, bs_k, bs_v, bs_o;                        // batch strides in elements
+  int B, H, Lq, Lk, D;
+  float scale;                                             // D^-0.5
+  const int* kv_len;   // per-batch number of un-masked keys (keys >= kv_len[b] get the -10000 bias), or nullptr
+};
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);
+
+// ------------------------------------------------------------------ norms
+struct GnParams {
+  const void* x0; int c0;      // first source  bf16 [B, L, c0]
+  const void* x1; int c1;      // optional second source (channel concat), bf16 [B, L, c1]
+  int B, L, G;
+  double* stats;               // [B, G, 2] sum / sum of squares (must be zero before gn_stats)
+  const float* gamma; const float* beta;   // [c0 + c1]
+  const float* scale_shift; int ss_ld;     // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + C + c]
+  float eps; int silu;
+  void* out;                   // bf16 [B, L, c0 + c1]
+};
+cudaError_t launch_gn_stats(const GnParams& p, cudaStream_t st);
+cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st);
+cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
+                             float eps, cudaStream_t st);
+
+// ------------------------------------------------------------------ elementwise / small
+// [B, Csrc, T] fp32 -> channel-last bf16 [B, T, ld_dst]; channel c goes to column c + (c >= split ? shift : 0).
+cudaError_t launch_nct_to_ntc(const float* src, void* dst, int B, int Csrc, int T, int ld_dst, int col0, int split,
+                              int shift, cudaStream_t st);
+// [B, T, C] fp32 -> bf16 (same layout)
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
+
+struct TembParams {
+  const float* t; int t_stride;          // model time per batch item (t_stride 0 = broadcast)
+  const float* freqs;                    // [sin_dim/2] sinusoid frequencies exp(-ln(1e4) j / half)
+  const float* w1; const float* b1;      // [128,512] (transposed: [in][out]), [512]
+  const float* w2; const float* b2;      // [512,512] (transposed), [512]
+  const float* aug;                      // [B,512] addition embedding (or nullptr)
+  float* emb_act;                        // out [B,512] = SiLU(emb)
+  const float* w_all; const float* b_all;  // [n_all, 512], [n_all]  all time_emb_proj stacked
+  float* ss_all;                         // out [B, n_all]
+  int B, n_all, sin_dim, emb_dim;
+};
+cudaError_t launch_temb(const TembParams& p, cudaStream_t st);
+
+// sampler updates (fp32, [n] elements)
+// x_out = a*x + b*m1 + c*m0 ; if roundtrip: m1 is first replaced by the reference's x0->eps->x0 round trip
+// m1' = (x - sig*((x - alp*m1)/sig))/alp  and written back.
+cudaError_t launch_axpbypcz(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
+                            int roundtrip, float alp, float sig, size_t n, cudaStream_t st);
+// UniPC predictor: xpred = a*x + b*m1 + cp*(m0 - m1) ; base = a*x + b*m1 + cc*(m0 - m1)
+cudaError_t launch_unipc_pred(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a,
+                              float b, float cp, float cc, int has_m0, size_t n, cudaStream_t st);
+// UniPC corrector: x = base + d*(mt - m1)
+cudaError_t launch_unipc_corr(float* x, const float* base, const float* mt, const float* m1, float d, size_t n,
+                              cudaStream_t st);
+
+}  // namespace dv

@@ -1,0 +1,186 @@
+// GroupNorm (+SiLU, + time scale/shift) and LayerNorm on channel-last bf16 activations. HBM/L2-bound kernels:
+// 16-byte vector loads along the contiguous channel axis, fp32 math, statistics accumulated in fp64.
+//
+// GroupNorm is split in two fully parallel launches so it scales from B=1 to B=256:
+//   gn_stats : per-(b, group) sum / sum-of-squares over [L, C/G]; supports a channel concat of two sources
+//              (torch.cat([h, skip], 1) in the up blocks is never materialised - groups may straddle the seam).
+//   gn_apply : y = SiLU?( ((x-mean)*rstd*gamma+beta) * (1+scale[b,c]) + shift[b,c] ) -> bf16 GEMM operand.
+// Reference: unet1d/resnet.py:591-631 (norm1/norm2 + scale_shift), transformer_1d.py:256 (eps 1e-6),
+// unet_1d_condition.py:1029-1031 (conv_norm_out + SiLU).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace dv {
+namespace {
+
+constexpr int NT = 256;
+constexpr int GN_ROWS_PER_CTA = 32;
+
+__device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, int c) {
+  if (c < p.c0)
+    return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x0) +
+                                          (static_cast<size_t>(b) * p.L + l) * p.c0 + c);
+  return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x1) +
+                                        (static_cast<size_t>(b) * p.L + l) * p.c1 + (c - p.c0));
+}
+
+__global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p) {
+  __shared__ float acc[64][2];
+  const int C = p.c0 + p.c1;
+  const int octs = C >> 3;
+  const int R = NT / octs;
+  const int b = blockIdx.y;
+  const int lbeg = blockIdx.x * GN_ROWS_PER_CTA;
+  const int lend = min(lbeg + GN_ROWS_PER_CTA, p.L);
+  if (threadIdx.x < 2 * p.G) (&acc[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int r = threadIdx.x / octs, o = threadIdx.x % octs;
+  if (r < R) {
+    float s = 0.f, ss = 0.f;
+    for (int l = lbeg + r; l < lend; l += R) {
+      const uint4 v = __ldg(gn_src(p, b, l, o * 8));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+        s += a + c;
+        ss += a * a + c * c;
+      }
+    }
+    const int grp = (o * 8) / (C / p.G);
+    atomicAdd(&acc[grp][0], s);
+    atomicAdd(&acc[grp][1], ss);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * p.G)
+    atomicAdd(&p.stats[static_cast<size_t>(b) * p.G * 2 + threadIdx.x], static_cast<double>((&acc[0][0])[threadIdx.x]));
+}
+
+__global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p) {
+  const int C = p.c0 + p.c1;
+  const int octs = C >> 3;
+  const int R = NT / octs;
+  const int b = blockIdx.y;
+  const int lbeg = blockIdx.x * GN_ROWS_PER_CTA;
+  const int lend = min(lbeg + GN_ROWS_PER_CTA, p.L);
+  const int r = threadIdx.x / octs, o = threadIdx.x % octs;
+  if (r >= R) return;
+  const int cbase = o * 8;
+  const int cpg = C / p.G;
+  const int grp = cbase / cpg;
+  const double n = static_cast<double>(p.L) * cpg;
+  const double mean_d = p.stats[(static_cast<size_t>(b) * p.G + grp) * 2] / n;
+  double var_d = p.stats[(static_cast<size_t>(b) * p.G + grp) * 2 + 1] / n - mean_d * mean_d;
+  if (var_d < 0.0) var_d = 0.0;
+  const float mean = static_cast<float>(mean_d);
+  const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(p.eps)));
+  float ca[8], cb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cbase + j;
+    float a = rstd * __ldg(p.gamma + c);
+    float bb = __ldg(p.beta + c) - mean * a;
+    if (p.scale_shift) {
+      const float sc = 1.0f + __ldg(p.scale_shift + static_cast<size_t>(b) * p.ss_ld + c);
+      const float sh = __ldg(p.scale_shift + static_cast<size_t>(b) * p.ss_ld + C + c);
+      a *= sc;
+      bb = bb * sc + sh;
+    }
+    ca[j] = a;
+    cb[j] = bb;
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  for (int l = lbeg + r; l < lend; l += R) {
+    const uint4 v = __ldg(gn_src(p, b, l, cbase));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = bf16_lo(w[j]) * ca[2 * j] + cb[2 * j];
+      float c = bf16_hi(w[j]) * ca[2 * j + 1] + cb[2 * j + 1];
+      if (p.silu) { a = silu_f(a); c = silu_f(c); }
+      y[j] = pack_bf16(a, c);
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * p.L + l) * C + cbase) = make_uint4(y[0], y[1], y[2], y[3]);
+  }
+}
+
+// One warp per row, row kept in registers (C <= 1024, multiple of 128): exact two-pass mean / variance.
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int rows, float eps) {
+  constexpr int C = CHUNKS * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint2* xr = reinterpret_cast<const uint2*>(x + static_cast<size_t>(row) * C);
+  float v[CHUNKS][4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const uint2 w = __ldg(xr + lane + 32 * i);
+    v[i][0] = bf16_lo(w.x); v[i][1] = bf16_hi(w.x); v[i][2] = bf16_lo(w.y); v[i][3] = bf16_hi(w.y);
+    s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  const float mean = s * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float d = v[i][j] - mean; q += d * d; }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) q += __shfl_xor_sync(0xffffffffu, q, m);
+  const float rstd = rsqrtf(q * (1.0f / C) + eps);
+  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C);
+#pragma unroll
+  for (int i = 0; i < CHUNKS; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+    uint2 w;
+    w.x = pack_bf16((v[i][0] - mean) * rstd * gm.x + bt.x, (v[i][1] - mean) * rstd * gm.y + bt.y);
+    w.y = pack_bf16((v[i][2] - mean) * rstd * gm.z + bt.z, (v[i][3] - mean) * rstd * gm.w + bt.w);
+    orow[lane + 32 * i] = w;
+  }
+}
+
+}  // namespace
+
+static bool gn_ok(const GnParams& p) {
+  const int C = p.c0 + p.c1;
+  return p.G > 0 && p.G <= 32 && C % (8 * p.G) == 0 && p.c0 % 8 == 0 && p.c1 % 8 == 0 && C / 8 <= NT;
+}
+cudaError_t launch_gn_stats(const GnParams& p, cudaStream_t st) {
+  if (!gn_ok(p)) return cudaErrorInvalidValue;
+  dim3 grid((p.L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, p.B);
+  gn_stats_kernel<<<grid, NT, 0, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
+  if (!gn_ok(p)) return cudaErrorInvalidValue;
+  dim3 grid((p.L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, p.B);
+  gn_apply_kernel<<<grid, NT, 0, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
+                             float eps, cudaStream_t st) {
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+  dim3 grid((rows + 7) / 8);
+  switch (C) {
+    case 128: layernorm_kernel<1><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 256: layernorm_kernel<2><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 384: layernorm_kernel<3><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 512: layernorm_kernel<4><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 640: layernorm_kernel<5><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 768: layernorm_kernel<6><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 1024: layernorm_kernel<8><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace dv

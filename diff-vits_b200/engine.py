@@ -1,0 +1,264 @@
+"""Host side of the B200-native denoiser: weight packing and the ctypes calls into libdiffvits_b200.
+
+`DenoiserEngine` owns one plan (fixed B, T, Tp on one device), its workspace and a handle on the packed parameter
+blob. PyTorch is used for device memory (`torch.empty`), streams and the two hoisted, step-invariant prompt ops
+(`TextTimeEmbedding`); all per-step compute is enqueued by the C library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DVError, UnetCfg, check
+
+SAMPLER_DPMPP_2M = 0
+SAMPLER_UNIPC_BH2 = 1
+SAMPLE_NO_GRAPH = 1
+SAMPLE_ROUNDTRIP = 2
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(
+            f"diffvits_b200 runs on CUDA sm_100a devices only (got {device}); there is no CPU fallback path")
+    if not torch.cuda.is_available():
+        raise RuntimeError("diffvits_b200: no CUDA device is available and there is no CPU fallback path")
+    return device
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+def _interleave64(t: torch.Tensor) -> torch.Tensor:
+    """[2H, ...] (value rows then gate rows) -> 64-row value / 64-row gate blocks alternating (GEGLU tiles)."""
+    half = t.shape[0] // 2
+    u, g = t[:half], t[half:]
+    ub = u.reshape(half // 64, 64, *t.shape[1:])
+    gb = g.reshape(half // 64, 64, *t.shape[1:])
+    return torch.stack([ub, gb], dim=1).reshape(t.shape)
+
+
+def _pad_rows(t: torch.Tensor, rows: int) -> torch.Tensor:
+    if t.shape[0] == rows:
+        return t
+    out = t.new_zeros((rows,) + tuple(t.shape[1:]))
+    out[: t.shape[0]] = t
+    return out
+
+
+def pack_slot(slot: dict, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Build one slot of the parameter blob from reference-layout tensors. Returns a flat CPU tensor of the slot's
+    dtype. Recipes are defined by the plan builder (csrc/engine.cu)."""
+    rec, shape = slot["recipe"], slot["shape"]
+    w = [sd[k].detach().to("cpu", torch.float32) for k in slot["keys"]]
+    if rec == "time_freqs":
+        from .dropin.unet1d.embeddings import time_frequencies  # same fp32 op sequence as the reference
+        out = time_frequencies(shape[0], 0, 10000)
+    elif rec == "vec":
+        out = _pad_rows(torch.cat([v.reshape(-1) for v in w]), shape[0])
+    elif rec == "vec_sum":
+        out = _pad_rows(sum(v.reshape(-1) for v in w), shape[0])
+    elif rec == "vec_dup2":
+        out = _pad_rows(torch.cat([w[0].reshape(-1)] * 2), shape[0])
+    elif rec == "geglu_vec":
+        out = _pad_rows(_interleave64(w[0].reshape(-1)), shape[0])
+    elif rec == "linear":
+        mats = [v.reshape(v.shape[0], -1) for v in w]          # Linear [N, K] or 1x1 conv [N, K, 1]
+        out = _pad_rows(torch.cat(mats, dim=0), shape[0])
+    elif rec == "geglu":
+        out = _pad_rows(_interleave64(w[0]), shape[0])
+    elif rec == "conv3":
+        n_pad, k_tot, cin = shape
+        cpad = (cin + 63) // 64 * 64
+        cw = w[0]                                              # [Cout, Cin, 3]
+        assert cw.shape[1] == cin and cw.shape[2] == 3, (slot["name"], cw.shape)
+        taps = cw.new_zeros(cw.shape[0], 3, cpad)
+        taps[:, :, :cin] = cw.permute(0, 2, 1)                 # tap-major K: k = tap * cpad + c
+        parts = [taps.reshape(cw.shape[0], 3 * cpad)]
+        if len(w) > 1:                                         # 1x1 shortcut fused as extra K panels
+            parts.append(w[1].reshape(w[1].shape[0], -1))
+        out = _pad_rows(torch.cat(parts, dim=1), n_pad)
+        assert out.shape[1] == k_tot, (slot["name"], out.shape, k_tot)
+    elif rec == "conv3_up2":
+        # nearest-2x upsample folded into the conv: even output rows see taps (x[p-1], x[p], x[p]) and odd rows
+        # (x[p], x[p], x[p+1]) of the low-resolution input, so over low-res rows the weights are
+        #   even: [W0 | W1+W2 | 0]      odd: [0 | W0+W1 | W2]            (resnet.py:157-170)
+        cw = w[0]
+        w0, w1, w2 = cw[:, :, 0], cw[:, :, 1], cw[:, :, 2]
+        z = torch.zeros_like(w0)
+        even = torch.cat([w0, w1 + w2, z], dim=1)
+        odd = torch.cat([z, w0 + w1, w2], dim=1)
+        out = _pad_rows(torch.cat([even, odd], dim=0), shape[0])
+    elif rec == "mat_t":
+        out = w[0].t().contiguous()
+    elif rec == "rows":
+        out = torch.cat([v.reshape(v.shape[0], -1) for v in w], dim=0)
+    else:
+        raise ValueError(f"unknown packing recipe {rec!r}")
+    out = out.contiguous()
+    n_expected = 1
+    for d in (shape[:2] if rec == "conv3" else shape):
+        n_expected *= d
+    if out.numel() != n_expected:
+        raise ValueError(f"slot {slot['name']}: packed {tuple(out.shape)} does not match manifest shape {shape}")
+    return out.to(torch.bfloat16 if slot["dtype"] == "bf16" else torch.float32).reshape(-1)
+
+
+def pack_params(manifest: List[dict], sd: Dict[str, torch.Tensor], nbytes: int) -> torch.Tensor:
+    """Pack a reference-layout state_dict into the flat parameter blob (CPU uint8 tensor)."""
+    blob = torch.zeros(nbytes, dtype=torch.uint8)
+    for slot in manifest:
+        flat = pack_slot(slot, sd)
+        raw = flat.view(torch.uint8)
+        assert raw.numel() == slot["nbytes"], (slot["name"], raw.numel(), slot["nbytes"])
+        blob[slot["offset"]: slot["offset"] + slot["nbytes"]] = raw
+    return blob
+
+
+def unet_cfg_from_config(config: dict, x_channels: Optional[int] = None) -> UnetCfg:
+    """Translate the reference UNet's config dict (unet_1d_condition.py:560-607) into the C struct; raises
+    ValueError for configurations outside the accelerated path."""
+    boc = tuple(config["block_out_channels"])
+    n = len(boc)
+    want_down = tuple(["CrossAttnDownBlock2D"] * (n - 1) + ["DownBlock2D"])
+    want_up = tuple(["UpBlock2D"] + ["CrossAttnUpBlock2D"] * (n - 1))
+    if tuple(config["down_block_types"]) != want_down or tuple(config["up_block_types"]) != want_up:
+        raise ValueError("accelerated path supports the default CrossAttnDown*(n-1)+Down / Up+CrossAttnUp*(n-1) layout")
+    lpb = config["layers_per_block"]
+    if not isinstance(lpb, int):
+        if len(set(lpb)) != 1:
+            raise ValueError("layers_per_block must be uniform")
+        lpb = lpb[0]
+    heads = config["attention_head_dim"]
+    if not isinstance(heads, int):
+        if len(set(heads)) != 1:
+            raise ValueError("attention_head_dim must be uniform")
+        heads = heads[0]
+    xdim = config["cross_attention_dim"]
+    if not isinstance(xdim, int):
+        if len(set(xdim)) != 1:
+            raise ValueError("cross_attention_dim must be uniform")
+        xdim = xdim[0]
+    if config.get("addition_embed_type") not in ("text", None):
+        raise ValueError("addition_embed_type must be 'text' or None")
+    if config.get("resnet_time_scale_shift") != "scale_shift":
+        raise ValueError("resnet_time_scale_shift must be 'scale_shift'")
+    cfg = UnetCfg()
+    cfg.in_channels = config["in_channels"]
+    cfg.out_channels = config["out_channels"]
+    cfg.n_levels = n
+    for i, c in enumerate(boc):
+        cfg.block_out_channels[i] = c
+    cfg.layers_per_block = lpb
+    cfg.norm_num_groups = config["norm_num_groups"]
+    cfg.cross_attention_dim = xdim
+    cfg.num_heads = heads
+    cfg.norm_eps = config["norm_eps"]
+    cfg.x_channels = x_channels if x_channels is not None else min(config["out_channels"], config["in_channels"])
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ engine
+class DenoiserEngine:
+    """One plan of the native UNet forward / sampling loop at fixed (B, T, Tp) on one CUDA device."""
+
+    def __init__(self, unet: torch.nn.Module, B: int, T: int, Tp: int, device, x_channels: Optional[int] = None,
+                 params: Optional[torch.Tensor] = None):
+        self.device = require_cuda(device)
+        self.lib = _lib.load()
+        self.unet = unet
+        self.B, self.T, self.Tp = int(B), int(T), int(Tp)
+        self.cfg = unet_cfg_from_config(unet.config, x_channels)
+        self.x_channels = self.cfg.x_channels
+        self.in_channels, self.out_channels = self.cfg.in_channels, self.cfg.out_channels
+        self._plan = C.c_void_p()
+        check(self.lib.dv_plan_create(C.byref(self.cfg), self.B, self.T, self.Tp, C.byref(self._plan)))
+        self.manifest = json.loads(self.lib.dv_plan_manifest_json(self._plan).decode())
+        self.param_bytes = self.lib.dv_plan_param_bytes(self._plan)
+        self.ws_bytes = self.lib.dv_plan_workspace_bytes(self._plan)
+        self.launches_per_forward = self.lib.dv_plan_launches_per_forward(self._plan)
+        with torch.cuda.device(self.device):
+            if params is None:
+                params = pack_params(self.manifest, unet.state_dict(), self.param_bytes).to(self.device)
+            assert params.numel() == self.param_bytes and params.device == self.device
+            self.params = params
+            self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+            check(self.lib.dv_plan_bind(self._plan, _ptr(self.workspace), _ptr(self.params), _stream(self.device)))
+        self._keep: list = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) is not None and self._plan.value:
+                if self.device.type == "cuda":
+                    torch.cuda.synchronize(self.device)
+                self.lib.dv_plan_destroy(self._plan)
+                self._plan = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- step-invariant inputs
+    def prepare_prompt(self, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None) -> None:
+        """ehs: encoder_hidden_states [B, Tp, D]; kv_len: [B] valid prompt rows (None = no mask)."""
+        assert ehs.shape == (self.B, self.Tp, self.cfg.cross_attention_dim), ehs.shape
+        ehs = ehs.to(self.device, torch.float32).contiguous()
+        aug = None
+        add = getattr(self.unet, "add_embedding", None)
+        if add is not None:
+            with torch.no_grad():
+                aug = add(ehs).to(torch.float32).contiguous()      # hoisted: prompt-only (unet_1d_condition.py:869)
+        if kv_len is not None:
+            kv_len = kv_len.to(self.device, torch.int32).contiguous()
+        check(self.lib.dv_prompt_prepare(self._plan, _ptr(ehs), _ptr(aug), _ptr(kv_len), _stream(self.device)))
+        self._keep = [ehs, aug, kv_len]
+
+    def set_cond(self, cond: torch.Tensor) -> None:
+        """cond: NCT [B, in_channels - x_channels, T] (model3.py:908)."""
+        assert cond.shape == (self.B, self.in_channels - self.x_channels, self.T), cond.shape
+        cond = cond.to(self.device, torch.float32).contiguous()
+        check(self.lib.dv_set_cond(self._plan, _ptr(cond), _stream(self.device)))
+        self._keep_cond = cond
+
+    # ---- one denoiser call
+    def forward(self, sample: torch.Tensor, t: torch.Tensor, x_only: bool = False,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        cin = self.x_channels if x_only else self.in_channels
+        assert sample.shape == (self.B, cin, self.T), (sample.shape, (self.B, cin, self.T))
+        sample = sample.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device, torch.float32).reshape(-1).contiguous()
+        assert t.numel() in (1, self.B)
+        if out is None:
+            out = torch.empty(self.B, self.out_channels, self.T, dtype=torch.float32, device=self.device)
+        check(self.lib.dv_unet_forward(self._plan, _ptr(sample), 1 if x_only else 0, _ptr(t),
+                                       1 if t.numel() == self.B else 0, _ptr(out), _stream(self.device)))
+        return out
+
+    # ---- whole sampling loop
+    def sample(self, sampler: int, t_in: torch.Tensor, coef: torch.Tensor, x: torch.Tensor, graph: bool = True,
+               roundtrip: bool = False) -> torch.Tensor:
+        """x: NCT [B, x_channels, T] fp32 on the device, updated in place and returned."""
+        assert x.shape == (self.B, self.x_channels, self.T) and x.dtype == torch.float32 and x.is_contiguous()
+        assert x.device == self.device
+        t_host = t_in.detach().to("cpu", torch.float32).contiguous()
+        c_host = coef.detach().to("cpu", torch.float32).contiguous()
+        nsteps = t_host.numel()
+        assert c_host.shape == (nsteps, 8)
+        flags = (0 if graph else SAMPLE_NO_GRAPH) | (SAMPLE_ROUNDTRIP if roundtrip else 0)
+        fp = C.POINTER(C.c_float)
+        check(self.lib.dv_sample(self._plan, sampler, nsteps, C.cast(t_host.data_ptr(), fp),
+                                 C.cast(c_host.data_ptr(), fp), _ptr(x), flags, _stream(self.device)))
+        return x
+
+    @property
+    def last_sample_launches(self) -> int:
+        return self.lib.dv_plan_last_sample_launches(self._plan)

@@ -1,0 +1,142 @@
+/*
+ * diffvits_b200 - C ABI of the B200-native Diff-VITS denoising loop (libdiffvits_b200.so).
+ *
+ * The reference (adelacvg/diff-vits) is pure PyTorch and has no FFI layer; its boundary for this path is the
+ * Python class API. Each entry point below names the reference interface it replaces (file:line relative to the
+ * reference tree). The Python shims in diff-vits_b200/dropin/{unet1d,sampler} bind these with ctypes and keep
+ * the reference's class names, constructor kwargs, state_dict layout and call signatures.
+ *
+ * Conventions
+ *  - return 0 on success, negative dv_status on failure; dv_last_error() gives a thread-local message.
+ *  - the caller owns every device buffer (workspace, parameter blob, inputs, outputs); the library never
+ *    allocates device memory, never synchronises the device and never calls back. All work is enqueued on the
+ *    given CUDA stream (cudaStream_t passed as void*) and is CUDA-graph-capture safe.
+ *  - one plan per (device, B, T, Tp); a plan is not thread safe, distinct plans are independent.
+ *  - there is no CPU path: every compute entry point requires a CUDA device of compute capability 10.x.
+ *  - tensors: "NCT" = [B, C, T] fp32 contiguous (the reference's layout), "NTC" = channel-last.
+ */
+#ifndef DIFFVITS_B200_H
+#define DIFFVITS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DV_VERSION 100
+
+#if defined(__GNUC__)
+#define DV_API __attribute__((visibility("default")))
+#else
+#define DV_API
+#endif
+
+typedef enum dv_status {
+  DV_OK = 0,
+  DV_ERR_INVALID = -1,     /* bad argument / unsupported configuration (reference: ValueError, unet_1d_condition.py:208-255) */
+  DV_ERR_CUDA = -2,        /* CUDA runtime / driver error, message has the cudaError string */
+  DV_ERR_STATE = -3,       /* call order violated (e.g. forward before bind / prompt_prepare) */
+  DV_ERR_UNSUPPORTED = -4  /* valid for the reference but outside the accelerated path */
+} dv_status;
+
+/* UNet1DConditionModel constructor arguments that shape the network
+ * (reference: unet1d/unet_1d_condition.py:151-203; call site model3.py:887-896). */
+typedef struct dv_unet_cfg {
+  int in_channels;            /* 228 = 100 latent + 128 cond on the diffusion path */
+  int out_channels;           /* 100 */
+  int n_levels;               /* len(block_out_channels), 2..8 */
+  int block_out_channels[8];  /* (128, 256, 384, 512) */
+  int layers_per_block;       /* 2 */
+  int norm_num_groups;        /* 8 */
+  int cross_attention_dim;    /* 128 */
+  int num_heads;              /* `attention_head_dim` in the reference ctor (it is the head COUNT): 8 */
+  float norm_eps;             /* 1e-5 */
+  int x_channels;             /* leading input channels that change every step (the noisy latent): 100 */
+} dv_unet_cfg;
+
+typedef struct dv_plan dv_plan;
+
+DV_API int dv_version(void);
+DV_API const char* dv_last_error(void);
+
+/* Build the per-call kernel program for UNet1DConditionModel.forward at a fixed (B, T, Tp).
+ * Replaces: nn.Module construction + eager dispatch of unet_1d_condition.py:743-1037. Requires T % 2^(n_levels-1) == 0. */
+DV_API int dv_plan_create(const dv_unet_cfg* cfg, int B, int T, int Tp, dv_plan** out);
+DV_API void dv_plan_destroy(dv_plan* plan);
+
+DV_API size_t dv_plan_workspace_bytes(const dv_plan* plan);
+DV_API size_t dv_plan_param_bytes(const dv_plan* plan);
+/* JSON list describing every slot of the packed parameter blob: which state_dict tensors
+ * (reference key names, e.g. "down_blocks.0.resnets.0.conv1.weight") go where and in which packed layout. */
+DV_API const char* dv_plan_manifest_json(const dv_plan* plan);
+/* Number of kernels one dv_unet_forward enqueues (used for the bench's gpu_launches claim). */
+DV_API int dv_plan_launches_per_forward(const dv_plan* plan);
+
+/* Attach caller-owned device memory (256-byte aligned): workspace (zeroed by this call) and the packed parameters. */
+DV_API int dv_plan_bind(dv_plan* plan, void* workspace, const void* params, void* stream);
+
+/* Step-invariant prompt work, hoisted out of the loop: bf16 copy of encoder_hidden_states, the 16 cross-attention
+ * K/V projections (attention_processor.py:1014-1015), the key-padding lengths and the text-time embedding `aug`
+ * (unet_1d_condition.py:869-870; computed by the caller).   ehs: [B, Tp, cross_attention_dim] fp32,
+ * aug: [B, 4*C0] fp32 or NULL, kv_len: [B] int32 or NULL (= no mask). */
+DV_API int dv_prompt_prepare(dv_plan* plan, const float* ehs, const float* aug, const int32_t* kv_len, void* stream);
+
+/* Step-invariant conditioning channels of the UNet input (model3.py:908 torch.cat([x, cond])): cond NCT [B, in-x, T]. */
+DV_API int dv_set_cond(dv_plan* plan, const float* cond, void* stream);
+
+/* UNet1DConditionModel.forward (unet_1d_condition.py:743-1037) for one denoiser call.
+ * sample: NCT [B, in_channels, T] (full concat) if x_only == 0, else NCT [B, x_channels, T] with dv_set_cond done.
+ * t: device fp32 model times, t[b * t_stride] (t_stride 0 broadcasts one value).  out: NCT [B, out_channels, T]. */
+DV_API int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride, float* out,
+                    void* stream);
+
+/* Whole multistep sampling loop (DPM_Solver.sample dpm_solver.py:1171-1213 / UniPC.sample uni_pc.py:606-658) with
+ * the denoiser, captured in one CUDA graph and replayed. Coefficients are computed on the host by the caller with
+ * the reference's own NoiseScheduleVP formulas.  t_in: host [nsteps] model times. coef: host [nsteps * 8]:
+ *   DV_SAMPLER_DPMPP_2M  row i (update to t_{i+1}): {A, B, C, has_prev, alpha_prev, sigma_prev, 0, 0}
+ *   DV_SAMPLER_UNIPC_BH2 row i: {a, b, cp, cc, d, has_prev, use_corrector, 0}
+ * x: device NCT [B, x_channels, T] fp32, noise in, latent out. flags: DV_SAMPLE_* */
+#define DV_SAMPLER_DPMPP_2M 0
+#define DV_SAMPLER_UNIPC_BH2 1
+#define DV_SAMPLE_NO_GRAPH 1     /* enqueue directly instead of capturing/replaying a graph */
+#define DV_SAMPLE_ROUNDTRIP 2    /* DPM++ only: reproduce the reference's x0->eps->x0 round trip bit for bit */
+DV_API int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags,
+              void* stream);
+/* Kernel launches enqueued by the most recent dv_sample on this plan. */
+DV_API int dv_plan_last_sample_launches(const dv_plan* plan);
+
+/* ---- single-kernel entry points (used by the parity tests and micro-benchmarks) ------------------------------- */
+typedef struct dv_gemm_src { const void* ptr; int L; int C; int ld; } dv_gemm_src;   /* bf16 [B, L, ld], C used */
+typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; } dv_gemm_seg;
+/* out_mode: 0 bf16 NTC, 1 fp32 NCT, 2 GEGLU bf16. impl: 0 = tcgen05 kernel, 1 = CUDA-core reference (writes raw
+ * fp32 [B, L, n_pad] accumulators + bias into `out`). Replaces F.conv1d (unet1d/lora.py:102) / nn.Linear. */
+DV_API int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
+            int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
+            int L_out, int impl, void* stream);
+/* F.scaled_dot_product_attention (attention_processor.py:1032); bf16 q/k/v/o with element strides. */
+DV_API int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
+                 long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,
+                 float scale, const int32_t* kv_len, void* stream);
+/* nn.GroupNorm (+SiLU, + (1+scale)*x+shift) on channel-last bf16 (resnet.py:591-631). stats: [B, G, 2] fp64 scratch. */
+DV_API int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, double* stats,
+                 const float* gamma, const float* beta, const float* scale_shift, int ss_ld, float eps, int silu,
+                 void* out, void* stream);
+/* nn.LayerNorm over the last dim of bf16 [rows, C] (attention.py:83,102,118). */
+DV_API int dv_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C, float eps,
+                 void* stream);
+/* DPM-Solver++ multistep update x_out = a*x + b*m1 + c*m0 (dpm_solver.py:547-580, 796-852). m0 may be NULL. */
+DV_API int dv_dpmpp_update(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
+                    int roundtrip, float alpha_prev, float sigma_prev, size_t n, void* stream);
+/* UniPC bh predictor / corrector (uni_pc.py:471-588). */
+DV_API int dv_unipc_predict(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a, float b,
+                     float cp, float cc, int has_prev, size_t n, void* stream);
+DV_API int dv_unipc_correct(float* x, const float* base, const float* mt, const float* m1, float d, size_t n, void* stream);
+/* [B, C, T] fp32 -> channel-last bf16 [B, T, ld] at column col0. */
+DV_API int dv_nct_to_ntc(const float* src, void* dst, int B, int C, int T, int ld, int col0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFVITS_B200_H */
