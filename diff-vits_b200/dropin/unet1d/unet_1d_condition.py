@@ -162,9 +162,11 @@ class UNet1DConditionModel(nn.Module):
     def _weights_version(self) -> Tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def native_engine(self, B: int, T: int, Tp: int, x_channels: Optional[int] = None):
+    def native_engine(self, B: int, T: int, Tp: int, x_channels: Optional[int] = None, private: bool = False):
         """The (cached) native plan for this shape on the module's device. Weights are packed once per module and
-        shared by all of its plans; they are re-packed when any parameter changed (load_state_dict, .to(...))."""
+        shared by all of its plans; they are re-packed when any parameter changed (load_state_dict, .to(...)).
+        `private=True` returns a fresh plan (own workspace, prompt and cond state) that is not shared with
+        `forward()` or other callers."""
         from diffvits_b200.engine import DenoiserEngine, require_cuda
         device = require_cuda(self.device)
         if self.dtype != torch.float32:
@@ -174,13 +176,14 @@ class UNet1DConditionModel(nn.Module):
             self._params_cache = None
             self._engines.clear()          # plans hold pointers into the old blob
         key = (B, T, Tp, x_channels)
-        eng = self._engines.get(key)
+        eng = None if private else self._engines.get(key)
         if eng is None:
             blob = None if self._params_cache is None else self._params_cache[1]
             eng = DenoiserEngine(self, B, T, Tp, device, x_channels=x_channels, params=blob)
             if self._params_cache is None:
                 self._params_cache = (ver, eng.params)
-            self._engines[key] = eng
+            if not private:
+                self._engines[key] = eng
         return eng
 
     # ------------------------------------------------------------------------------------------ forward

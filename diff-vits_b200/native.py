@@ -28,7 +28,7 @@ class NativeDenoiser:
         Tp = ehs.shape[1]
         self.unet = unet
         self.x_channels = unet.config["in_channels"] - Cc
-        self.engine: DenoiserEngine = unet.native_engine(B, T, Tp, x_channels=self.x_channels)
+        self.engine: DenoiserEngine = unet.native_engine(B, T, Tp, x_channels=self.x_channels, private=True)
         self.engine.prepare_prompt(ehs, kv_len)
         self.engine.set_cond(cond)
         self.calls = 0

@@ -1,0 +1,236 @@
+"""Per-kernel parity on the B200 (through the C ABI) against plain fp32 torch math on the same BF16-rounded inputs.
+Tolerances: a BF16 result is one rounding (2^-9 relative) away from the fp32 value, so rel-L2 <= 4e-3 and max-abs
+<= 2^-7 * max|ref|; fp32 kernels (sampler updates) <= 1e-6."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def U():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gpu_util
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return gpu_util
+
+
+def _check_bf16(U, got, ref, rel=4e-3):
+    assert torch.isfinite(got.float()).all()
+    assert U.rel_l2(got.float(), ref) < rel, U.rel_l2(got.float(), ref)
+    assert U.max_abs(got.float(), ref) <= 2 ** -7 * float(ref.abs().max()) + 1e-3
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,L,K,N", [(2, 300, 128, 128), (1, 125, 512, 256), (3, 1000, 64, 384), (1, 25, 1024, 512)])
+def test_gemm_linear(U, B, L, K, N):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = _rand((B, L, K), g)
+    w = _rand((N, K), g, K ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = _rand((B, L, N), g)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    got = U.gemm([a], [(0, 0, 0, K)], w, N, bias=bias, res=res)
+    _check_bf16(U, got, ref)
+    raw = U.gemm([a], [(0, 0, 0, K)], w, N, bias=bias, impl=1)      # CUDA-core reference kernel, raw fp32
+    assert U.rel_l2(raw[:, :, :N], a.float() @ w.float().t() + bias) < 1e-5
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout", [(2, 257, 128, 128), (1, 200, 256, 384), (2, 1000, 384, 128), (2, 26, 512, 512)])
+def test_gemm_conv3(U, B, L, Cin, Cout):
+    """conv1d k3 s1 p1: three row-shifted K segments, zero fill outside [0, L)."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = _rand((B, L, Cin), g)
+    w = (torch.randn(Cout, Cin, 3, generator=g, device="cuda") * (3 * Cin) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g, device="cuda")
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=1).transpose(1, 2)
+    wp = w.permute(0, 2, 1).reshape(Cout, 3 * Cin).contiguous()
+    got = U.gemm([x], [(0, -1, 0, Cin), (0, 0, 0, Cin), (0, 1, 0, Cin)], wp, Cout, bias=bias)
+    _check_bf16(U, got, ref)
+
+
+def test_gemm_conv3_with_fused_shortcut_two_sources(U):
+    """conv2 + 1x1 shortcut over torch.cat([h, skip]) as extra K panels from two tensors (resnet.py:634-639)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, L, C, C1, C2 = 2, 250, 256, 256, 128
+    v, h, s = _rand((B, L, C), g), _rand((B, L, C1), g), _rand((B, L, C2), g)
+    w2 = (torch.randn(C, C, 3, generator=g, device="cuda") * (3 * C) ** -0.5).to(torch.bfloat16)
+    wsc = (torch.randn(C, C1 + C2, 1, generator=g, device="cuda") * (C1 + C2) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(C, generator=g, device="cuda")
+    ref = (F.conv1d(v.float().transpose(1, 2), w2.float(), None, padding=1)
+           + F.conv1d(torch.cat([h, s], 2).float().transpose(1, 2), wsc.float(), b)).transpose(1, 2)
+    wp = torch.cat([w2.permute(0, 2, 1).reshape(C, 3 * C), wsc[:, :, 0]], dim=1).contiguous()
+    segs = [(0, -1, 0, C), (0, 0, 0, C), (0, 1, 0, C), (1, 0, 0, C1), (2, 0, 0, C2)]
+    got = U.gemm([v, h, s], segs, wp, C, bias=b)
+    _check_bf16(U, got, ref)
+
+
+def test_gemm_conv3_stride2_view(U):
+    """Downsample2D conv k3 s2 p1 through the [L/2, 2C] view (resnet.py:200)."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, L, C = 2, 500, 128
+    x = _rand((B, L, C), g)
+    w = (torch.randn(C, C, 3, generator=g, device="cuda") * (3 * C) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(C, generator=g, device="cuda")
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=2, padding=1).transpose(1, 2)
+    wp = w.permute(0, 2, 1).reshape(C, 3 * C).contiguous()
+    got = U.gemm([x], [(0, -1, C, C), (0, 0, 0, C), (0, 0, C, C)], wp, C, bias=b, l_out=L // 2,
+                 views=[(L // 2, 2 * C)])
+    _check_bf16(U, got, ref)
+
+
+def test_gemm_upsample_folded(U):
+    """nearest-2x + conv k3 p1 folded into [2C, 3C] weights over the low-res rows (resnet.py:157-170)."""
+    from diffvits_b200.engine import pack_slot
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, L, C = 2, 125, 256
+    x = _rand((B, L, C), g)
+    w = (torch.randn(C, C, 3, generator=g, device="cuda") * (3 * C) ** -0.5).to(torch.bfloat16).float()
+    b = torch.randn(C, generator=g, device="cuda")
+    up = F.interpolate(x.float().transpose(1, 2), size=2 * L, mode="nearest")
+    ref = F.conv1d(up, w, b, padding=1).transpose(1, 2)                       # [B, 2L, C]
+    slot = dict(recipe="conv3_up2", shape=[2 * C, 3 * C], keys=["w"], dtype="bf16", name="t")
+    wp = pack_slot(slot, {"w": w.cpu()}).reshape(2 * C, 3 * C).cuda()
+    got = U.gemm([x], [(0, -1, 0, C), (0, 0, 0, C), (0, 1, 0, C)], wp, 2 * C, bias=torch.cat([b, b]))
+    _check_bf16(U, got.reshape(B, 2 * L, C), ref, rel=6e-3)                  # W1+W2 is rounded once more
+
+
+def test_gemm_geglu_and_ncl(U):
+    from diffvits_b200.engine import pack_slot
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, L, C = 2, 300, 128
+    a = _rand((B, L, C), g)
+    w = (torch.randn(8 * C, C, generator=g, device="cuda") * C ** -0.5).to(torch.bfloat16).float()
+    b = torch.randn(8 * C, generator=g, device="cuda")
+    proj = a.float() @ w.t() + b
+    u, gate = proj.chunk(2, dim=-1)
+    ref = u * F.gelu(gate)
+    wp = pack_slot(dict(recipe="geglu", shape=[8 * C, C], keys=["w"], dtype="bf16", name="t"), {"w": w.cpu()})
+    bp = pack_slot(dict(recipe="geglu_vec", shape=[8 * C], keys=["b"], dtype="f32", name="t"), {"b": b.cpu()})
+    got = U.gemm([a], [(0, 0, 0, C)], wp.reshape(8 * C, C).cuda(), 8 * C, bias=bp.cuda(), out_mode=2)
+    _check_bf16(U, got, ref)
+    # conv_out style: N=100 padded to 128, fp32 [B, N, L] store
+    w3 = (torch.randn(100, C, 3, generator=g, device="cuda") * (3 * C) ** -0.5).to(torch.bfloat16)
+    b3 = torch.randn(100, generator=g, device="cuda")
+    ref3 = F.conv1d(a.float().transpose(1, 2), w3.float(), b3, padding=1)
+    wp3 = torch.zeros(128, 3 * C, dtype=torch.bfloat16, device="cuda")
+    wp3[:100] = w3.permute(0, 2, 1).reshape(100, 3 * C)
+    bp3 = torch.zeros(128, device="cuda")
+    bp3[:100] = b3
+    got3 = U.gemm([a], [(0, -1, 0, C), (0, 0, 0, C), (0, 1, 0, C)], wp3, 100, bias=bp3, out_mode=1)
+    assert U.rel_l2(got3, ref3) < 1e-5
+
+
+@pytest.mark.parametrize("D,Lq,Lk", [(16, 200, 200), (32, 500, 500), (48, 250, 250), (64, 125, 125), (16, 1000, 1000)])
+def test_attention_self(U, D, Lq, Lk):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H = 2, 8
+    C = H * D
+    qkv = _rand((B, Lq, 3 * C), g)
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    ref = F.scaled_dot_product_attention(*(t.float().reshape(B, Lq, H, D).transpose(1, 2) for t in (q, k, v)))
+    ref = ref.transpose(1, 2).reshape(B, Lq, C)
+    got = U.attention(q, k, v, H)
+    _check_bf16(U, got, ref, rel=8e-3)        # + bf16 rounding of P
+
+
+@pytest.mark.parametrize("D,Lq", [(16, 1000), (32, 500), (48, 250), (64, 125)])
+def test_attention_cross_masked(U, D, Lq):
+    g = torch.Generator(device="cuda").manual_seed(8)
+    B, H, Lk = 3, 8, 282
+    C = H * D
+    q = _rand((B, Lq, C), g)
+    kv = _rand((B, Lk, 2 * C), g)
+    k, v = kv[:, :, :C], kv[:, :, C:]
+    lens = torch.tensor([282, 182, 1], dtype=torch.int32, device="cuda")
+    bias = ((torch.arange(Lk, device="cuda")[None, :] >= lens[:, None]).float() * -10000.0)[:, None, None, :]
+    ref = F.scaled_dot_product_attention(q.float().reshape(B, Lq, H, D).transpose(1, 2),
+                                         k.float().reshape(B, Lk, H, D).transpose(1, 2),
+                                         v.float().reshape(B, Lk, H, D).transpose(1, 2), attn_mask=bias)
+    ref = ref.transpose(1, 2).reshape(B, Lq, C)
+    got = U.attention(q, k, v, H, kv_len=lens)
+    _check_bf16(U, got, ref, rel=8e-3)
+
+
+@pytest.mark.parametrize("C0,C1,L", [(128, 0, 1000), (512, 384, 125), (384, 0, 250), (256, 128, 77)])
+def test_groupnorm(U, C0, C1, L):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, G = 3, 8
+    x0 = _rand((B, L, C0), g, 2.0) + 0.5
+    x1 = (_rand((B, L, C1), g) - 0.25) if C1 else None
+    C = C0 + C1
+    gamma = torch.randn(C, generator=g, device="cuda")
+    beta = torch.randn(C, generator=g, device="cuda")
+    ss = torch.randn(B, 2 * C + 64, generator=g, device="cuda") * 0.3
+    x = torch.cat([x0, x1], 2) if C1 else x0
+    gn = F.group_norm(x.float().transpose(1, 2), G, gamma, beta, 1e-5)
+    ref = F.silu(gn * (1 + ss[:, :C, None]) + ss[:, C:2 * C, None]).transpose(1, 2)
+    got = U.groupnorm(x0, x1, G, gamma, beta, 1e-5, True, ss)
+    _check_bf16(U, got, ref)
+    ref2 = F.group_norm(x.float().transpose(1, 2), G, gamma, beta, 1e-6).transpose(1, 2)
+    _check_bf16(U, U.groupnorm(x0, x1, G, gamma, beta, 1e-6, False), ref2)
+
+
+@pytest.mark.parametrize("C", [128, 256, 384, 512])
+def test_layernorm(U, C):
+    g = torch.Generator(device="cuda").manual_seed(10)
+    x = _rand((2, 333, C), g, 1.5) + 0.3
+    gamma = torch.randn(C, generator=g, device="cuda")
+    beta = torch.randn(C, generator=g, device="cuda")
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    _check_bf16(U, U.layernorm(x, gamma, beta), ref)
+
+
+def test_sampler_update_kernels(U):
+    import ctypes as C
+    from diffvits_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n = 3 * 100 * 203                      # not a multiple of 4: exercises the scalar tail
+    x, m1, m0, mt = (torch.randn(n, generator=g, device="cuda") for _ in range(4))
+    a, b, c = 0.93, -0.21, 0.07
+    out = torch.empty_like(x)
+    _lib.check(lib.dv_dpmpp_update(U.vp(out), U.vp(x), U.vp(m1), U.vp(m0), a, b, c, 0, 1.0, 1.0, n, U.stream()))
+    assert U.rel_l2(out, a * x + b * m1 + c * m0) < 1e-6
+    _lib.check(lib.dv_dpmpp_update(U.vp(out), U.vp(x), U.vp(m1), None, a, b, c, 0, 1.0, 1.0, n, U.stream()))
+    assert U.rel_l2(out, a * x + b * m1) < 1e-6
+    # round trip: m1 <- (x - sig*((x - alp*m1)/sig))/alp, bit-exact vs torch fp32 evaluated in the same order
+    alp, sig = 0.0063, 0.99998
+    m1c = m1.clone()
+    ta, tsg = torch.tensor(alp, device="cuda"), torch.tensor(sig, device="cuda")
+    rt = (x - tsg * ((x - ta * m1) / tsg)) / ta
+    _lib.check(lib.dv_dpmpp_update(U.vp(out), U.vp(x), U.vp(m1c), U.vp(m0), a, b, c, 1, alp, sig, n, U.stream()))
+    assert torch.equal(m1c, rt)
+    assert U.rel_l2(out, a * x + b * rt + c * m0) < 1e-6
+    # UniPC predictor / corrector
+    xp, base = torch.empty_like(x), torch.empty_like(x)
+    cp, cc, d = 0.11, -0.05, 0.4
+    _lib.check(lib.dv_unipc_predict(U.vp(xp), U.vp(base), U.vp(x), U.vp(m1), U.vp(m0), a, b, cp, cc, 1, n, U.stream()))
+    xbar = a * x + b * m1
+    assert U.rel_l2(xp, xbar + cp * (m0 - m1)) < 1e-6 and U.rel_l2(base, xbar + cc * (m0 - m1)) < 1e-6
+    _lib.check(lib.dv_unipc_correct(U.vp(out), U.vp(base), U.vp(mt), U.vp(m1), d, n, U.stream()))
+    assert U.rel_l2(out, base + d * (mt - m1)) < 1e-6
+    # in-place predictor without history (last UniPC step)
+    xin = x.clone()
+    _lib.check(lib.dv_unipc_predict(U.vp(xin), None, U.vp(xin), U.vp(m1), U.vp(m0), a, b, cp, cc, 0, n, U.stream()))
+    assert U.rel_l2(xin, xbar) < 1e-6
+
+
+def test_nct_to_ntc(U):
+    from diffvits_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, Cc, T, ld = 2, 100, 203, 256
+    src = torch.randn(B, Cc, T, generator=g, device="cuda")
+    dst = torch.zeros(B, T, ld, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.dv_nct_to_ntc(U.vp(src), U.vp(dst), B, Cc, T, ld, 100, U.stream()))
+    assert torch.equal(dst[:, :, 100:200], src.transpose(1, 2).to(torch.bfloat16))
+    assert float(dst[:, :, :100].abs().max()) == 0 and float(dst[:, :, 200:].abs().max()) == 0
