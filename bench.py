@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the Diff-VITS denoising loop (BASELINE.json metric: denoised latent frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5|c1] [--impl native|reference]
+
+One "step" = one complete sampling loop (all denoiser calls + sampler updates) over one batch of synthetic
+utterances. N > 1: launched under torchrun, one rank per GPU, independent utterances batch-sharded (weak scaling,
+32 per GPU), one NCCL all-gather of the output latents per step, max-over-ranks device timing.
+Rank 0 prints ONE JSON line. See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, T, Tp, sampler, steps, description)
+    "c1": (1, 200, 282, "dpmsolver++", 50, "C1: 1 utterance x 200 frames, Tp=282, 50-step DPM-Solver++ 2M"),
+    "c2": (32, 1000, 282, "dpmsolver++", 50, "C2: batch 32 x 1000 frames, Tp=282, 50-step DPM-Solver++ 2M"),
+    "c3": (32, 1000, 282, "unipc", 10, "C3: batch 32 x 1000 frames, Tp=282, 10-step UniPC bh2 with prompt cross-attention"),
+    "c5": (8, 4000, 282, "unipc", 25, "C5: long-form batch 8 x 4000 frames, Tp=282, 25-step UniPC bh2"),
+}
+KIND_NAMES = {0: "gemm_tc", 1: "gn_stats", 2: "gn_apply", 3: "layernorm", 4: "attention"}
+
+
+def denoiser_flops(T: int, Tp: int) -> float:
+    """Algorithmic FLOPs of one reference denoiser call per utterance."""
+    return 31.705e6 * T + 2.35e6 * Tp + 4352.0 * T * T + 7296.0 * T * Tp
+
+
+def load_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "_source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                for n, v in zip(names, parts[3:7]):
+                    if v == "Active":
+                        reasons.add(n)
+        except Exception:
+            pass
+        finally:
+            if self.path and os.path.exists(self.path):
+                os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_sample_run(B: int, T: int, Tp: int, sampler: str, steps_total: int, steps_run: int, threads: int):
+    """Oracle port (oracle/unet_oracle.py + oracle/sampler_oracle.py: the reference's algorithm in the reference's own
+    torch CPU ops) on a bounded sample: B utterances, the first `steps_run` solver steps of a `steps_run`-step loop.
+    Returns (seconds, extrapolated frames/s for the full `steps_total`-step loop)."""
+    import torch
+    from oracle import inputs, sampler_oracle, unet_oracle
+    from oracle.ref_import import UNET_KW
+    import diffvits_b200
+    diffvits_b200.install_dropin()
+    from unet1d.unet_1d_condition import UNet1DConditionModel
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    sd = UNet1DConditionModel(**UNET_KW).eval().state_dict()     # parameter container only; compute is the oracle's
+    x_T, cond, ehs = inputs.make_inputs(B, T, Tp)
+    betas = inputs.betas_linear()
+    calls = [0]
+
+    def model(x, t_in):
+        calls[0] += 1
+        return unet_oracle.unet_forward(sd, torch.cat([x, cond], 1), t_in, ehs)
+
+    fn = sampler_oracle.dpmpp_2m if sampler == "dpmsolver++" else sampler_oracle.unipc_bh2
+    t0 = time.perf_counter()
+    fn(model, betas, x_T.clone(), steps_run)
+    dt = time.perf_counter() - t0
+    per_call = dt / max(1, calls[0])
+    return dt, (B * T) / (per_call * steps_total)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, timed on this host's cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bg, T, Tp, sampler, nfe, desc = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    Bs, steps_run = min(Bg, 4), 2
+    for _ in range(args.warmup):
+        cpu_sample_run(Bs, T, Tp, sampler, nfe, steps_run, threads)
+    secs, fps = [], []
+    for _ in range(args.steps):
+        dt, f = cpu_sample_run(Bs, T, Tp, sampler, nfe, steps_run, threads)
+        secs.append(dt)
+        fps.append(f)
+    value = sum(fps) / len(fps)
+    sample = (f"{Bs} of {Bg} utterances x {T} frames, {steps_run}-step loop ({steps_run} denoiser calls) of the {nfe}-step "
+              f"{sampler} loop, extrapolated linearly in NFE and batch; oracle port of the reference (same torch CPU ops; the "
+              f"reference's per-step PromptEncoder is NOT included, which favours the CPU arm)")
+    line = {
+        "impl": "reference", "metric": "denoised latent frames/sec", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "B": Bg, "T": T, "Tp": Tp, "sampler": sampler, "nfe": nfe},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import diffvits_b200
+    from oracle import inputs
+    from oracle.ref_import import UNET_KW
+    diffvits_b200.install_dropin()
+    import sampler.dpm_solver as dpm
+    import sampler.uni_pc as uni
+    from unet1d.unet_1d_condition import UNet1DConditionModel
+
+    Bg, T, Tp, sampler, nfe, desc = WORKLOADS[args.workload]
+    torch.manual_seed(1234)
+    unet = UNet1DConditionModel(**UNET_KW).eval().to(dev)
+    # noise / conditioning are drawn for the GLOBAL batch with one seed, then sharded (bit-identical to 1 GPU)
+    x_all, cond_all, ehs_all = inputs.make_inputs(Bg * world, T, Tp)
+    sl = slice(rank * Bg, (rank + 1) * Bg)
+    x_h, cond_h, ehs_h = (t[sl].contiguous().pin_memory() for t in (x_all, cond_all, ehs_all))
+    del x_all, cond_all, ehs_all
+    betas = inputs.betas_linear()
+    x_d, cond_d, ehs_d = x_h.to(dev), cond_h.to(dev), ehs_h.to(dev)
+    native = diffvits_b200.NativeDenoiser(unet, cond_d, ehs_d)
+    eng = native.engine
+    gathered = torch.empty(world * Bg, 100, T, device=dev) if world > 1 else None
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, iters):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / iters
+
+    # ---- device-resident loop: inputs already in HBM, whole loop = one CUDA-graph replay
+    def step_resident():
+        lat = diffvits_b200.sample_native(unet, x_d, cond_d, ehs_d, sampler=sampler, steps=nfe, betas=betas,
+                                          native=native)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lat)
+        return lat
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    with ClockSampler(local) as cs:
+        ms_res = timed(step_resident, args.steps)
+    clocks = cs.summary()
+    launches_per_step = eng.last_sample_launches + (1 if world > 1 else 0)
+
+    # ---- end to end through the reference-facing API (drop-in model_wrapper + solver), host buffers in and out
+    if sampler == "dpmsolver++":
+        ns = dpm.NoiseScheduleVP("discrete", betas=betas)
+        solver = dpm.DPM_Solver(dpm.model_wrapper(native, ns, model_type="x_start", model_kwargs={}), ns,
+                                algorithm_type="dpmsolver++")
+    else:
+        ns = uni.NoiseScheduleVP("discrete", betas=betas)
+        solver = uni.UniPC(uni.model_wrapper(native, ns, model_type="x_start", model_kwargs={}), ns, variant="bh2")
+    out_h = torch.empty(Bg, 100, T).pin_memory()
+
+    def step_e2e():
+        xd = x_h.to(dev, non_blocking=True)
+        cd = cond_h.to(dev, non_blocking=True)
+        ed = ehs_h.to(dev, non_blocking=True)
+        native.rebind(cd, ed)                                     # hoisted prompt work is part of the job
+        lat = solver.sample(xd, steps=nfe, order=2, skip_type="time_uniform", method="multistep")
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lat)
+        out_h.copy_(lat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                 # the caller holds the latent on the host
+        assert solver.last_run_native
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    h2d = x_h.numel() * 4 + cond_h.numel() * 4 + ehs_h.numel() * 4
+    d2h = out_h.numel() * 4
+
+    frames = Bg * world * T
+    value = frames / (ms_res * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        # ---- roofline of the dominant kernel (the tcgen05 tap-GEMM), CUDA events around every launch of an eager call
+        ops = eng.op_table()
+        t_probe = torch.tensor([500.0], device=dev)
+        eng.profile_forward(x_d, t_probe)                         # warm
+        acc = [0.0] * (len(ops) + 1)
+        reps = 3
+        for _ in range(reps):
+            for i, v in enumerate(eng.profile_forward(x_d, t_probe)):
+                acc[i] += v / reps
+        by_kind = {}
+        for o, ms in zip(ops, acc[:-1]):
+            k = by_kind.setdefault(KIND_NAMES[o["kind"]], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            k["ms"] += ms
+            k["flops"] += o["flops"]
+            k["bytes"] += o["bytes"]
+            k["launches"] += 1
+        call_ms_eager = sum(acc)
+        g = by_kind["gemm_tc"]
+        gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12
+        peak_tf = peaks["bf16_tflops"]
+        kernels = {}
+        for name, k in by_kind.items():
+            ent = {"launches_per_call": k["launches"], "ms_per_call": round(k["ms"], 4),
+                   "share_of_call": round(k["ms"] / call_ms_eager, 4)}
+            if k["flops"] > 0:
+                ent["tflops"] = round(k["flops"] / (k["ms"] * 1e-3) / 1e12, 2)
+                ent["frac_of_bf16_peak"] = round(ent["tflops"] / peak_tf, 4)
+            if name in ("gn_stats", "gn_apply", "layernorm"):
+                ent["gbs"] = round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1)
+                ent["frac_of_hbm_peak"] = round(ent["gbs"] / peaks["hbm_gbs"], 4)
+            kernels[name] = ent
+        kernels["prologue(layout+time_mlp)"] = {"ms_per_call": round(acc[-1], 4)}
+        total_flops = denoiser_flops(T, Tp) * Bg * nfe           # per GPU per step
+        step_tflops = total_flops / (ms_res * 1e-3) / 1e12
+        roofline = {
+            "kernel": "gemm_tc_kernel<128> (tcgen05 tap-GEMM: conv1d k3 / 1x1 / linear)",
+            "bound": "tensor", "achieved": round(gemm_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": round(gemm_tflops / peak_tf, 4), "traffic": None,
+            "peak_source": peaks["_source"] + ", burst figure (kernel timed launch by launch)",
+            "how": f"sum of algorithmic FLOPs of the {g['launches']} GEMM launches of one denoiser call / sum of their "
+                   f"CUDA-event durations (eager, events on the launching stream, mean of {reps} calls)",
+            "whole_step": {"algorithmic_tflop_per_step_per_gpu": round(total_flops / 1e12, 2),
+                           "achieved_tflops": round(step_tflops, 2),
+                           "frac_of_sustained_peak": round(step_tflops / peaks["bf16_tflops_sustained"], 4)},
+            "kernels": kernels,
+        }
+        line = {
+            "metric": "denoised latent frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_res, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "rtf": (ms_res * 1e-3) / (frames * 256 / 24000.0),
+            "config": {"workload": desc + ", BF16 operands / FP32 accumulate, FP32 sampler state",
+                       "B_per_gpu": Bg, "T": T, "Tp": Tp, "sampler": sampler, "nfe": nfe, "order": 2,
+                       "weights": "random init seed 1234 (64.7 M params)", "inputs": "N(0,1) seed 0",
+                       "l2": "no flush: per-step working set (workspace %.2f GB + weights 0.15 GB) >> 126 MB L2" %
+                             (eng.ws_bytes / 1e9),
+                       "graph": "whole loop = one CUDA graph (%d kernel nodes)" % eng.last_sample_launches},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "path": "pinned host x_T/cond/prompt -> H2D -> NativeDenoiser.rebind (prompt K/V, text-time emb) -> "
+                            "drop-in model_wrapper + solver.sample (native graph) -> D2H latent"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            Bs, steps_run = min(Bg, 4), 2
+            cpu_sample_run(1, min(T, 200), Tp, sampler, nfe, 1, threads)     # warm the CPU libraries
+            dt, fps = cpu_sample_run(Bs, T, Tp, sampler, nfe, steps_run, threads)
+            line["cpu_baseline"] = {
+                "value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                "sample": f"{Bs} of {Bg} utterances x {T} frames, {steps_run} denoiser calls + updates of the {nfe}-step "
+                          f"loop ({dt:.1f} s of CPU work), extrapolated linearly in NFE and batch; oracle port of the "
+                          f"reference (same torch CPU ops, FP32, without the reference's per-step PromptEncoder)"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,10 +59,16 @@ SIGNATURES = {
     "dv_set_cond": (_i, [_vp, _vp, _vp]),
     "dv_unet_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dv_sample": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp]),
+    "dv_plan_tensor_count": (_i, [_vp]),
+    "dv_plan_tensor_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),
+    "dv_plan_op_count": (_i, [_vp]),
+    "dv_plan_op_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "dv_plan_profile_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp, C.POINTER(_f), _i, _vp]),
     "dv_gemm": (_i, [C.POINTER(GemmSrc), _i, C.POINTER(GemmSeg), _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i,
                      _i, _i, _vp]),
     "dv_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "dv_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    "dv_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
     "dv_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "dv_dpmpp_update": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _i, _f, _f, _sz, _vp]),
     "dv_unipc_predict": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _sz, _vp]),

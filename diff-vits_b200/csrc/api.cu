@@ -98,6 +98,40 @@ int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const f
   return rc == DV_OK ? rc : fail(rc, err);
 }
 
+int dv_plan_tensor_count(const dv_plan* plan) { return plan ? static_cast<int>(plan->impl.named.size()) : 0; }
+int dv_plan_tensor_info(const dv_plan* plan, int i, char* name, int name_cap, size_t* offset, int* L, int* C) {
+  if (!plan || i < 0 || i >= static_cast<int>(plan->impl.named.size())) return fail(DV_ERR_INVALID, "tensor index out of range");
+  const auto& t = plan->impl.named[i];
+  if (name && name_cap > 0) {
+    strncpy(name, t.first.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (offset) *offset = t.second.off;
+  if (L) *L = t.second.L;
+  if (C) *C = t.second.C;
+  return DV_OK;
+}
+int dv_plan_op_count(const dv_plan* plan) { return plan ? static_cast<int>(plan->impl.ops.size()) : 0; }
+int dv_plan_op_info(const dv_plan* plan, int i, char* tag, int tag_cap, int* kind, double* flops, double* bytes) {
+  if (!plan || i < 0 || i >= static_cast<int>(plan->impl.ops.size())) return fail(DV_ERR_INVALID, "op index out of range");
+  const dv::Op& o = plan->impl.ops[i];
+  if (tag && tag_cap > 0) {
+    strncpy(tag, o.tag.c_str(), tag_cap - 1);
+    tag[tag_cap - 1] = 0;
+  }
+  if (kind) *kind = static_cast<int>(o.kind);
+  if (flops) *flops = o.flops;
+  if (bytes) *bytes = o.bytes;
+  return DV_OK;
+}
+int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride, float* out,
+                            float* ms, int cap, void* stream) {
+  if (!plan || !sample || !t || !out || !ms) return fail(DV_ERR_INVALID, "null argument");
+  std::string err;
+  int rc = plan->impl.profile_forward(sample, x_only, t, t_stride, out, S(stream), ms, cap, err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+
 // ------------------------------------------------------------------------------------------ single kernels
 int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
             int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
@@ -151,7 +185,7 @@ int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q,
   return ck(dv::launch_attention(p, S(stream)), "attention");
 }
 
-int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, double* stats,
+int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, float* scratch,
                  const float* gamma, const float* beta, const float* scale_shift, int ss_ld, float eps, int silu,
                  void* out, void* stream) {
   int rc = require_device();
@@ -159,14 +193,14 @@ int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, i
   dv::GnParams p;
   memset(&p, 0, sizeof p);
   p.x0 = x0; p.c0 = c0; p.x1 = x1; p.c1 = x1 ? c1 : 0;
-  p.B = B; p.L = L; p.G = G; p.stats = stats; p.gamma = gamma; p.beta = beta;
+  p.B = B; p.L = L; p.G = G; p.stats = scratch; p.gamma = gamma; p.beta = beta;
   p.scale_shift = scale_shift; p.ss_ld = ss_ld; p.eps = eps; p.silu = silu; p.out = out;
-  rc = ck(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * G * 2 * sizeof(double), S(stream)), "memset stats");
-  if (rc != DV_OK) return rc;
   rc = ck(dv::launch_gn_stats(p, S(stream)), "gn_stats");
   if (rc != DV_OK) return rc;
   return ck(dv::launch_gn_apply(p, S(stream)), "gn_apply");
 }
+
+size_t dv_groupnorm_scratch_floats(int B, int L, int G) { return dv::gn_scratch_floats(B, L, G); }
 
 int dv_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C, float eps,
                  void* stream) {

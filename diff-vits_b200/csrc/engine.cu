@@ -120,9 +120,9 @@ struct Builder {
   }
   long long vec(const std::string& key, int n) { return slot(key, "vec", {key}, "f32", {n}); }
 
-  size_t stats_alloc() {
+  size_t stats_alloc(int L) {
     size_t o = P.stats_bytes;
-    P.stats_bytes += static_cast<size_t>(P.B) * P.cfg.norm_num_groups * 2 * sizeof(double);
+    P.stats_bytes += align_up(gn_scratch_floats(P.B, L, P.cfg.norm_num_groups) * sizeof(float), 256);
     return o;  // relative to off_stats
   }
 
@@ -136,7 +136,7 @@ struct Builder {
     st.gn.c0 = x0.C; st.gn.c1 = x1.valid() ? x1.C : 0;
     st.gn.B = P.B; st.gn.L = x0.L; st.gn.G = P.cfg.norm_num_groups;
     st.gn.eps = eps; st.gn.silu = silu ? 1 : 0; st.gn.ss_ld = P.n_all;  // n_all patched at finalize
-    st.gno.x0 = x0.off; st.gno.x1 = x1.valid() ? x1.off : 0; st.gno.out = out.off; st.gno.stats = stats_alloc();
+    st.gno.x0 = x0.off; st.gno.x1 = x1.valid() ? x1.off : 0; st.gno.out = out.off; st.gno.stats = stats_alloc(x0.L);
     st.gno.gamma = vec(norm_key + ".weight", C);
     st.gno.beta = vec(norm_key + ".bias", C);
     st.gno.ss = ss_off;
@@ -232,10 +232,12 @@ struct Builder {
       TRef sc[2] = {x0, x1};
       conv3(P.ops, pfx + ".conv2", v, cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, sc, x1.valid() ? 2 : 1,
             pfx + ".conv_shortcut", TRef(), y, GEMM_OUT_BF16, false);
+      P.named.emplace_back(pfx, y);
     } else {
       if (x1.valid()) { err = "identity shortcut over a channel concat is not supported"; return y; }
       conv3(P.ops, pfx + ".conv2", v, cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, nullptr, 0, "", x0, y,
             GEMM_OUT_BF16, false);
+      P.named.emplace_back(pfx, y);
     }
     return y;
   }
@@ -306,6 +308,7 @@ struct Builder {
     TRef yo = act(L, C);
     linear(P.ops, pfx + ".proj_out", z, "linear", {pfx + ".proj_out.weight"}, pfx + ".proj_out.bias", C, y, yo,
            GEMM_OUT_BF16);
+    P.named.emplace_back(pfx, yo);
     return yo;
   }
 
@@ -325,6 +328,7 @@ struct Builder {
     P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2;
     g.bias_off = slot(key + ".b", "vec_sum", {key + ".bias"}, "f32", {g.n_pad});
     g.out = out; g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
+    P.named.emplace_back(key, out);
     return out;
   }
 
@@ -341,6 +345,7 @@ struct Builder {
     g.out = out2; g.l_out = x.L; g.out_mode = GEMM_OUT_BF16; g.ld_out = 2 * C;
     TRef out = out2;
     out.L = 2 * x.L; out.C = C;  // same bytes viewed as [2L, C]
+    P.named.emplace_back(key, out);
     return out;
   }
 };
@@ -410,6 +415,7 @@ int Plan::build(std::string& err) {
   TRef h = b.act(T, C0);
   b.conv3(ops, "conv_in", xin, c.in_channels, "conv_in.weight", "conv_in.bias", C0, nullptr, 0, "", TRef(), h,
           GEMM_OUT_BF16, false);
+  named.emplace_back("conv_in", h);
   skips.push_back(h);
   int ch = C0;
   for (int i = 0; i < n_levels; ++i) {
@@ -489,6 +495,29 @@ int Plan::build(std::string& err) {
   fix_list(ops);
   fix_list(prep_ops);
 
+  // ---- algorithmic work per launch (roofline accounting in bench.py)
+  for (Op& o : ops) {
+    const double Bd = B;
+    switch (o.kind) {
+      case OP_GEMM: {
+        double abytes = 0;
+        for (int i = 0; i < o.g.nsrc; ++i) abytes += Bd * o.g.src[i].L * o.g.src[i].C * 2;
+        o.flops = 2.0 * Bd * o.g.l_out * o.g.n * o.g.k_tot;
+        const double outw = o.g.out_mode == GEMM_OUT_F32_NCL ? 4.0 * o.g.n : (o.g.out_mode == GEMM_OUT_GEGLU ? o.g.n : 2.0 * o.g.n);
+        o.bytes = abytes + 2.0 * o.g.n_pad * o.g.k_tot + Bd * o.g.l_out * outw +
+                  (o.g.res.valid() ? Bd * o.g.l_out * o.g.n * 2.0 : 0.0);
+        break;
+      }
+      case OP_ATTN:
+        o.flops = 4.0 * Bd * o.at.H * o.at.Lq * static_cast<double>(o.at.Lk) * o.at.D;
+        o.bytes = 2.0 * Bd * o.at.H * o.at.D * (2.0 * o.at.Lq + 2.0 * o.at.Lk);
+        break;
+      case OP_GN_STATS: o.bytes = 2.0 * Bd * o.gn.L * (o.gn.c0 + o.gn.c1); break;
+      case OP_GN_APPLY: o.bytes = 4.0 * Bd * o.gn.L * (o.gn.c0 + o.gn.c1); break;
+      case OP_LN: o.bytes = 4.0 * o.ln.rows * static_cast<double>(o.ln.C); break;
+    }
+  }
+
   // ---- manifest
   std::ostringstream js;
   js << "[";
@@ -551,7 +580,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         o.gn.x0 = ws + o.gno.x0;
         o.gn.x1 = o.gn.c1 ? ws + o.gno.x1 : nullptr;
         o.gn.out = ws + o.gno.out;
-        o.gn.stats = reinterpret_cast<double*>(ws + off_stats + o.gno.stats);
+        o.gn.stats = reinterpret_cast<float*>(ws + off_stats + o.gno.stats);
         o.gn.gamma = pf(o.gno.gamma);
         o.gn.beta = pf(o.gno.beta);
         o.gn.scale_shift = o.gno.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + o.gno.ss;
@@ -582,8 +611,11 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
     }                                                                                   \
   } while (0)
 
-int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches) {
+int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches,
+                      cudaEvent_t* events) {
+  int idx = 0;
   for (Op& o : list) {
+    if (events) cudaEventRecord(events[idx++], st);
     cudaError_t e = cudaSuccess;
     switch (o.kind) {
       case OP_GEMM:
@@ -623,7 +655,7 @@ int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_l
   if (aug) DV_CK(cudaMemcpyAsync(ws + off_aug, aug, static_cast<size_t>(B) * emb_dim * 4, cudaMemcpyDeviceToDevice, st));
   has_kvlen = kv_len != nullptr;
   if (kv_len) DV_CK(cudaMemcpyAsync(ws + off_kvlen, kv_len, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
-  int rc = enqueue_ops(prep_ops, nullptr, st, err, nullptr);
+  int rc = enqueue_ops(prep_ops, nullptr, st, err, nullptr, nullptr);
   if (rc != DV_OK) return rc;
   prompt_ready = true;
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key = 0; }
@@ -638,11 +670,29 @@ int Plan::set_cond(const float* cond, cudaStream_t st, std::string& err) {
   return DV_OK;
 }
 
+int Plan::profile_forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
+                          float* ms, int cap, std::string& err) {
+  const int n = static_cast<int>(ops.size());
+  if (cap < n + 1) { err = "ms buffer too small (need ops + 1)"; return DV_ERR_INVALID; }
+  std::vector<cudaEvent_t> ev(n + 2);
+  for (auto& e : ev) DV_CK(cudaEventCreate(&e));
+  int launches = 0;
+  DV_CK(cudaEventRecord(ev[n + 1], st));                 // start of the prologue (layout change + time embedding)
+  int rc = forward(sample, x_only, t, t_stride, out, st, err, &launches, ev.data());
+  if (rc == DV_OK) {
+    DV_CK(cudaEventRecord(ev[n], st));
+    DV_CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    cudaEventElapsedTime(&ms[n], ev[n + 1], ev[0]);      // prologue
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
 int Plan::forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
-                  std::string& err, int* launches) {
+                  std::string& err, int* launches, cudaEvent_t* events) {
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
-  DV_CK(cudaMemsetAsync(ws + off_stats, 0, stats_bytes, st));
   DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st));
   TembParams tp;
   tp.t = t; tp.t_stride = t_stride;
@@ -656,7 +706,7 @@ int Plan::forward(const float* sample, int x_only, const float* t, int t_stride,
   tp.B = B; tp.n_all = n_all; tp.sin_dim = cfg.block_out_channels[0]; tp.emb_dim = emb_dim;
   DV_CK(launch_temb(tp, st));
   if (launches) *launches += 3;
-  return enqueue_ops(ops, out, st, err, launches);
+  return enqueue_ops(ops, out, st, err, launches, events);
 }
 
 static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {

@@ -43,6 +43,7 @@ struct GemmDesc {
 struct Op {
   OpKind kind;
   std::string tag;
+  double flops = 0, bytes = 0;  // algorithmic work of one launch (for roofline accounting)
   GemmDesc g; GemmParams gp;
   GnParams gn;
   struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; } ln;
@@ -62,6 +63,7 @@ struct Plan {
   std::vector<Op> ops;       // one denoiser call
   std::vector<Op> prep_ops;  // prompt-side hoisted projections
   std::string manifest;
+  std::vector<std::pair<std::string, TRef>> named;  // block outputs that stay intact after a call (debug/tests)
 
   // workspace regions (byte offsets)
   size_t off_xin = 0, off_ehs = 0, off_aug = 0, off_embact = 0, off_ss = 0, off_stats = 0, off_kvlen = 0;
@@ -84,11 +86,15 @@ struct Plan {
 
   int build(std::string& err);
   int bind(void* workspace, const void* params, cudaStream_t st, std::string& err);
-  int enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches);
+  int enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches,
+                  cudaEvent_t* events = nullptr);
   int forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
-              std::string& err, int* launches);
+              std::string& err, int* launches, cudaEvent_t* events = nullptr);
   int prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_len, cudaStream_t st, std::string& err);
   int set_cond(const float* cond, cudaStream_t st, std::string& err);
+  // Debug/measurement: one eager forward with a CUDA event between consecutive launches; synchronises.
+  int profile_forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
+                      float* ms, int cap, std::string& err);
   int sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
              std::string& err);
   ~Plan();

@@ -66,12 +66,13 @@ struct GnParams {
   const void* x0; int c0;      // first source  bf16 [B, L, c0]
   const void* x1; int c1;      // optional second source (channel concat), bf16 [B, L, c1]
   int B, L, G;
-  double* stats;               // [B, G, 2] sum / sum of squares (must be zero before gn_stats)
+  float* stats;                // scratch [B, ceil(L/32), G, 2]: per row-chunk sum / sum of squares (gn_scratch_floats)
   const float* gamma; const float* beta;   // [c0 + c1]
   const float* scale_shift; int ss_ld;     // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + C + c]
   float eps; int silu;
   void* out;                   // bf16 [B, L, c0 + c1]
 };
+size_t gn_scratch_floats(int B, int L, int G);
 cudaError_t launch_gn_stats(const GnParams& p, cudaStream_t st);
 cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st);
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,

@@ -2,7 +2,7 @@
 // 16-byte vector loads along the contiguous channel axis, fp32 math, statistics accumulated in fp64.
 //
 // GroupNorm is split in two fully parallel launches so it scales from B=1 to B=256:
-//   gn_stats : per-(b, group) sum / sum-of-squares over [L, C/G]; supports a channel concat of two sources
+//   gn_stats : per-(b, 32-row chunk, group) sum / sum-of-squares; supports a channel concat of two sources
 //              (torch.cat([h, skip], 1) in the up blocks is never materialised - groups may straddle the seam).
 //   gn_apply : y = SiLU?( ((x-mean)*rstd*gamma+beta) * (1+scale[b,c]) + shift[b,c] ) -> bf16 GEMM operand.
 // Reference: unet1d/resnet.py:591-631 (norm1/norm2 + scale_shift), transformer_1d.py:256 (eps 1e-6),
@@ -24,19 +24,20 @@ __device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, 
                                         (static_cast<size_t>(b) * p.L + l) * p.c1 + (c - p.c0));
 }
 
+// Deterministic two-level reduction (no atomics): per-thread partials -> shared -> one fp32 partial per
+// (b, row-chunk, group); gn_apply sums the row-chunk partials in a fixed order in fp64. Bit-reproducible run to run
+// and independent of the batch size, so a sample computes identically alone or inside a batch.
 __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p) {
-  __shared__ float acc[64][2];
+  __shared__ float ps[NT][2];
   const int C = p.c0 + p.c1;
   const int octs = C >> 3;
   const int R = NT / octs;
   const int b = blockIdx.y;
   const int lbeg = blockIdx.x * GN_ROWS_PER_CTA;
   const int lend = min(lbeg + GN_ROWS_PER_CTA, p.L);
-  if (threadIdx.x < 2 * p.G) (&acc[0][0])[threadIdx.x] = 0.f;
-  __syncthreads();
   const int r = threadIdx.x / octs, o = threadIdx.x % octs;
+  float s = 0.f, ss = 0.f;
   if (r < R) {
-    float s = 0.f, ss = 0.f;
     for (int l = lbeg + r; l < lend; l += R) {
       const uint4 v = __ldg(gn_src(p, b, l, o * 8));
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -47,13 +48,25 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p) {
         ss += a * a + c * c;
       }
     }
-    const int grp = (o * 8) / (C / p.G);
-    atomicAdd(&acc[grp][0], s);
-    atomicAdd(&acc[grp][1], ss);
+  }
+  ps[threadIdx.x][0] = s;
+  ps[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (threadIdx.x < octs) {  // fold the R row-slots of this octet
+    float a = ps[threadIdx.x][0], c = ps[threadIdx.x][1];
+    for (int rr = 1; rr < R; ++rr) { a += ps[rr * octs + threadIdx.x][0]; c += ps[rr * octs + threadIdx.x][1]; }
+    ps[threadIdx.x][0] = a;
+    ps[threadIdx.x][1] = c;
   }
   __syncthreads();
-  if (threadIdx.x < 2 * p.G)
-    atomicAdd(&p.stats[static_cast<size_t>(b) * p.G * 2 + threadIdx.x], static_cast<double>((&acc[0][0])[threadIdx.x]));
+  if (threadIdx.x < p.G) {   // fold the octets of this group
+    const int opg = (C / p.G) >> 3;
+    float a = 0.f, c = 0.f;
+    for (int k = 0; k < opg; ++k) { a += ps[threadIdx.x * opg + k][0]; c += ps[threadIdx.x * opg + k][1]; }
+    float* dst = p.stats + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * p.G + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = c;
+  }
 }
 
 __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p) {
@@ -69,8 +82,17 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p) {
   const int cpg = C / p.G;
   const int grp = cbase / cpg;
   const double n = static_cast<double>(p.L) * cpg;
-  const double mean_d = p.stats[(static_cast<size_t>(b) * p.G + grp) * 2] / n;
-  double var_d = p.stats[(static_cast<size_t>(b) * p.G + grp) * 2 + 1] / n - mean_d * mean_d;
+  double sum = 0.0, sumsq = 0.0;
+  {
+    const float* src = p.stats + (static_cast<size_t>(b) * gridDim.x * p.G + grp) * 2;
+    for (unsigned c = 0; c < gridDim.x; ++c) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src + static_cast<size_t>(c) * p.G * 2));
+      sum += static_cast<double>(v.x);
+      sumsq += static_cast<double>(v.y);
+    }
+  }
+  const double mean_d = sum / n;
+  double var_d = sumsq / n - mean_d * mean_d;
   if (var_d < 0.0) var_d = 0.0;
   const float mean = static_cast<float>(mean_d);
   const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(p.eps)));
@@ -164,6 +186,9 @@ cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
   dim3 grid((p.L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, p.B);
   gn_apply_kernel<<<grid, NT, 0, st>>>(p);
   return cudaGetLastError();
+}
+size_t gn_scratch_floats(int B, int L, int G) {
+  return static_cast<size_t>(B) * ((L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA) * G * 2;
 }
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
                              float eps, cudaStream_t st) {

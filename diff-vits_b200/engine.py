@@ -208,13 +208,17 @@ class DenoiserEngine:
             pass
 
     # ---- step-invariant inputs
-    def prepare_prompt(self, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None) -> None:
-        """ehs: encoder_hidden_states [B, Tp, D]; kv_len: [B] valid prompt rows (None = no mask)."""
+    def prepare_prompt(self, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None,
+                       aug: Optional[torch.Tensor] = None) -> None:
+        """ehs: encoder_hidden_states [B, Tp, D]; kv_len: [B] valid prompt rows (None = no mask); aug: optional
+        precomputed text-time embedding [B, 512] (default: computed here with the module's TextTimeEmbedding)."""
         assert ehs.shape == (self.B, self.Tp, self.cfg.cross_attention_dim), ehs.shape
         ehs = ehs.to(self.device, torch.float32).contiguous()
-        aug = None
         add = getattr(self.unet, "add_embedding", None)
-        if add is not None:
+        if aug is not None:
+            aug = aug.to(self.device, torch.float32).contiguous()
+            assert aug.shape == (self.B, 4 * self.cfg.block_out_channels[0])
+        elif add is not None:
             with torch.no_grad():
                 aug = add(ehs).to(torch.float32).contiguous()      # hoisted: prompt-only (unet_1d_condition.py:869)
         if kv_len is not None:
@@ -258,6 +262,45 @@ class DenoiserEngine:
         check(self.lib.dv_sample(self._plan, sampler, nsteps, C.cast(t_host.data_ptr(), fp),
                                  C.cast(c_host.data_ptr(), fp), _ptr(x), flags, _stream(self.device)))
         return x
+
+    # ---- debug: block outputs left in the workspace by the last denoiser call
+    def named_tensors(self) -> Dict[str, torch.Tensor]:
+        """{reference module path: bf16 [B, L, C] view into the workspace}."""
+        out = {}
+        buf = C.create_string_buffer(160)
+        off, L, Cc = C.c_size_t(), C.c_int(), C.c_int()
+        for i in range(self.lib.dv_plan_tensor_count(self._plan)):
+            check(self.lib.dv_plan_tensor_info(self._plan, i, buf, 160, C.byref(off), C.byref(L), C.byref(Cc)))
+            n = self.B * L.value * Cc.value * 2
+            out[buf.value.decode()] = self.workspace[off.value: off.value + n].view(torch.bfloat16).view(
+                self.B, L.value, Cc.value)
+        return out
+
+    # ---- measurement support
+    def op_table(self) -> List[dict]:
+        """[{tag, kind, flops, bytes}] for every launch of one denoiser call (kind: 0 gemm, 1 gn_stats, 2 gn_apply,
+        3 layernorm, 4 attention)."""
+        n = self.lib.dv_plan_op_count(self._plan)
+        out = []
+        buf = C.create_string_buffer(160)
+        kind, fl, by = C.c_int(), C.c_double(), C.c_double()
+        for i in range(n):
+            check(self.lib.dv_plan_op_info(self._plan, i, buf, 160, C.byref(kind), C.byref(fl), C.byref(by)))
+            out.append(dict(tag=buf.value.decode(), kind=kind.value, flops=fl.value, bytes=by.value))
+        return out
+
+    def profile_forward(self, sample: torch.Tensor, t: torch.Tensor, x_only: bool = True) -> List[float]:
+        """Device time (ms) of every launch of one eager denoiser call, CUDA events on the launching stream;
+        last entry = prologue (input layout change + time embedding). Synchronises."""
+        n = self.lib.dv_plan_op_count(self._plan)
+        ms = (C.c_float * (n + 1))()
+        sample = sample.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device, torch.float32).reshape(-1).contiguous()
+        out = torch.empty(self.B, self.out_channels, self.T, dtype=torch.float32, device=self.device)
+        check(self.lib.dv_plan_profile_forward(self._plan, _ptr(sample), 1 if x_only else 0, _ptr(t),
+                                               1 if t.numel() == self.B else 0, _ptr(out), ms, n + 1,
+                                               _stream(self.device)))
+        return list(ms)
 
     @property
     def last_sample_launches(self) -> int:

@@ -23,15 +23,22 @@ class NativeDenoiser:
     transposed PromptEncoder output, model3.py:906,912); kv_len: [B] valid prompt rows or None.
     """
 
-    def __init__(self, unet, cond: torch.Tensor, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None):
+    def __init__(self, unet, cond: torch.Tensor, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None,
+                 aug: Optional[torch.Tensor] = None):
         B, Cc, T = cond.shape
         Tp = ehs.shape[1]
         self.unet = unet
         self.x_channels = unet.config["in_channels"] - Cc
         self.engine: DenoiserEngine = unet.native_engine(B, T, Tp, x_channels=self.x_channels, private=True)
-        self.engine.prepare_prompt(ehs, kv_len)
-        self.engine.set_cond(cond)
         self.calls = 0
+        self.rebind(cond, ehs, kv_len, aug)
+
+    def rebind(self, cond: torch.Tensor, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None,
+               aug: Optional[torch.Tensor] = None) -> "NativeDenoiser":
+        """Bind a new batch of the same shape (re-runs the hoisted prompt work; plan, workspace, weights are kept)."""
+        self.engine.prepare_prompt(ehs, kv_len, aug)
+        self.engine.set_cond(cond)
+        return self
 
     def __call__(self, x: torch.Tensor, t_input: torch.Tensor, **_unused) -> torch.Tensor:
         self.calls += 1

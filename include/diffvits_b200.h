@@ -107,6 +107,20 @@ DV_API int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, 
 /* Kernel launches enqueued by the most recent dv_sample on this plan. */
 DV_API int dv_plan_last_sample_launches(const dv_plan* plan);
 
+/* ---- measurement support ------------------------------------------------------------------------------------- */
+/* Block outputs (bf16 [B, L, C] at byte `offset` of the workspace, named by reference module path) that are still
+ * intact after dv_unet_forward returns: lets tests compare the network block by block with the oracle. */
+DV_API int dv_plan_tensor_count(const dv_plan* plan);
+DV_API int dv_plan_tensor_info(const dv_plan* plan, int i, char* name, int name_cap, size_t* offset, int* L, int* C);
+/* The per-call program: op i has a tag (reference module path + role), a kind (0 GEMM/conv on tcgen05, 1 GroupNorm
+ * statistics, 2 GroupNorm apply, 3 LayerNorm, 4 attention) and its algorithmic FLOPs / HBM bytes per launch. */
+DV_API int dv_plan_op_count(const dv_plan* plan);
+DV_API int dv_plan_op_info(const dv_plan* plan, int i, char* tag, int tag_cap, int* kind, double* flops, double* bytes);
+/* One eager dv_unet_forward with a CUDA event between consecutive launches. SYNCHRONISES the stream (the only entry
+ * point that does). ms[i] = device time of op i (i < op_count), ms[op_count] = prologue (layout change + time MLP). */
+DV_API int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride,
+                                   float* out, float* ms, int cap, void* stream);
+
 /* ---- single-kernel entry points (used by the parity tests and micro-benchmarks) ------------------------------- */
 typedef struct dv_gemm_src { const void* ptr; int L; int C; int ld; } dv_gemm_src;   /* bf16 [B, L, ld], C used */
 typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; } dv_gemm_seg;
@@ -119,8 +133,10 @@ DV_API int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, i
 DV_API int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
                  long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,
                  float scale, const int32_t* kv_len, void* stream);
-/* nn.GroupNorm (+SiLU, + (1+scale)*x+shift) on channel-last bf16 (resnet.py:591-631). stats: [B, G, 2] fp64 scratch. */
-DV_API int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, double* stats,
+/* nn.GroupNorm (+SiLU, + (1+scale)*x+shift) on channel-last bf16 (resnet.py:591-631).
+ * scratch: dv_groupnorm_scratch_floats(B, L, G) floats (per row-chunk partial sums; deterministic reduction). */
+DV_API size_t dv_groupnorm_scratch_floats(int B, int L, int G);
+DV_API int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, float* scratch,
                  const float* gamma, const float* beta, const float* scale_shift, int ss_ld, float eps, int silu,
                  void* out, void* stream);
 /* nn.LayerNorm over the last dim of bf16 [rows, C] (attention.py:83,102,118). */

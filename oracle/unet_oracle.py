@@ -202,35 +202,35 @@ def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, ehs: T
     if "add_embedding.proj.weight" in sd:
         emb = emb + text_time_embedding(c, ehs)                                        # :869-870, 918
     emb_act = F.silu(emb)                                                              # resnet.py:614-616
-    h = c.r(conv(c, c.r(sample), "conv_in"))                                           # :943
+    def tr(name, v):
+        if trace is not None:
+            trace[name] = v
+        return v
+
+    h = tr("conv_in", c.r(conv(c, c.r(sample), "conv_in")))                            # :943
     skips = [h]
     for i in range(n):                                                                 # :950-976
         p = f"down_blocks.{i}"
         for j in range(lpb):
-            h = resnet(c, h, emb_act, f"{p}.resnets.{j}")
+            h = tr(f"{p}.resnets.{j}", resnet(c, h, emb_act, f"{p}.resnets.{j}"))
             if i < n - 1:
-                h = transformer(c, h, ehs, bias, f"{p}.attentions.{j}")
+                h = tr(f"{p}.attentions.{j}", transformer(c, h, ehs, bias, f"{p}.attentions.{j}"))
             skips.append(h)
-            if trace is not None:
-                trace[f"{p}.{j}"] = h
         if i < n - 1:
-            h = c.r(conv(c, h, f"{p}.downsamplers.0.conv", stride=2))                  # resnet.py:214-223
+            h = tr(f"{p}.downsamplers.0.conv", c.r(conv(c, h, f"{p}.downsamplers.0.conv", stride=2)))  # resnet.py:214-223
             skips.append(h)
-    h = resnet(c, h, emb_act, "mid_block.resnets.0")                                   # unet_1d_blocks.py:611-622
-    h = transformer(c, h, ehs, bias, "mid_block.attentions.0")
-    h = resnet(c, h, emb_act, "mid_block.resnets.1")
-    if trace is not None:
-        trace["mid"] = h
+    h = tr("mid_block.resnets.0", resnet(c, h, emb_act, "mid_block.resnets.0"))        # unet_1d_blocks.py:611-622
+    h = tr("mid_block.attentions.0", transformer(c, h, ehs, bias, "mid_block.attentions.0"))
+    h = tr("mid_block.resnets.1", resnet(c, h, emb_act, "mid_block.resnets.1"))
     for i in range(n):                                                                 # :1003-1026
         p = f"up_blocks.{i}"
         for j in range(lpb + 1):
             h = torch.cat([h, skips.pop()], dim=1)                                     # unet_1d_blocks.py:2085, 2187
-            h = resnet(c, h, emb_act, f"{p}.resnets.{j}")
+            h = tr(f"{p}.resnets.{j}", resnet(c, h, emb_act, f"{p}.resnets.{j}"))
             if i > 0:
-                h = transformer(c, h, ehs, bias, f"{p}.attentions.{j}")
+                h = tr(f"{p}.attentions.{j}", transformer(c, h, ehs, bias, f"{p}.attentions.{j}"))
         if i < n - 1:
-            h = upsample(c, h, skips[-1].shape[-1], f"{p}.upsamplers.0.conv")          # :1011-1012 (size forwarded)
-        if trace is not None:
-            trace[p] = h
+            h = tr(f"{p}.upsamplers.0.conv",
+                   upsample(c, h, skips[-1].shape[-1], f"{p}.upsamplers.0.conv"))      # :1011-1012 (size forwarded)
     h = c.r(F.silu(group_norm(c, h, "conv_norm_out", cfg["norm_eps"])))                # :1029-1031
     return conv(c, h, "conv_out")                                                      # :1032

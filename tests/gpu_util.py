@@ -83,7 +83,7 @@ def groupnorm(x0, x1, G, gamma, beta, eps, silu, ss=None) -> torch.Tensor:
     B, L, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[2]
     out = torch.zeros(B, L, c0 + c1, dtype=torch.bfloat16, device=x0.device)
-    stats = torch.empty(B, G, 2, dtype=torch.float64, device=x0.device)
+    stats = torch.empty(lib.dv_groupnorm_scratch_floats(B, L, G), dtype=torch.float32, device=x0.device)
     check(lib.dv_groupnorm(vp(x0), c0, vp(x1), c1, B, L, G, vp(stats), vp(gamma), vp(beta), vp(ss),
                            0 if ss is None else ss.shape[1], eps, 1 if silu else 0, vp(out), stream()))
     return out

@@ -1,6 +1,6 @@
 #!/bin/bash
 # first GPU contact: kernel parity, then the end-to-end parity tests; logs under gpurun_out/
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,driver_version --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "gemm_linear" -x > gpurun_out/t1_gemm.log 2>&1; echo "gemm_linear rc=$?"
