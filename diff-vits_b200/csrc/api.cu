@@ -133,6 +133,11 @@ int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, cons
 }
 
 // ------------------------------------------------------------------------------------------ single kernels
+static thread_local float* g_test_stats = nullptr;
+static thread_local int g_test_bn = 0;
+/* Test hooks for dv_gemm: force the N tile (0 = heuristic) and ask the epilogue for GroupNorm partials. */
+void dv_gemm_test_options(int bn, float* stats) { g_test_bn = bn; g_test_stats = stats; }
+
 int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
             int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
             int L_out, int impl, void* stream) {
@@ -168,6 +173,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   p.tiles_per_batch = (L_out + 127) / 128;
   p.out_mode = out_mode;
   p.bias = bias; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out;
+  p.stats = g_test_stats; p.stats_nblk = n / 16; p.bn = g_test_bn;
   if (impl == 1) return ck(dv::launch_gemm_ref(p, rs, w, k_tot, S(stream)), "gemm_ref");
   return ck(dv::launch_gemm_tc(p, S(stream)), "gemm_tc");
 }
@@ -193,14 +199,17 @@ int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, i
   dv::GnParams p;
   memset(&p, 0, sizeof p);
   p.x0 = x0; p.c0 = c0; p.x1 = x1; p.c1 = x1 ? c1 : 0;
-  p.B = B; p.L = L; p.G = G; p.stats = scratch; p.gamma = gamma; p.beta = beta;
+  p.B = B; p.L = L; p.G = G; p.gamma = gamma; p.beta = beta;
   p.scale_shift = scale_shift; p.ss_ld = ss_ld; p.eps = eps; p.silu = silu; p.out = out;
-  rc = ck(dv::launch_gn_stats(p, S(stream)), "gn_stats");
+  p.nst = 1;
+  p.st[0].ptr = scratch; p.st[0].chunks = (L + 31) / 32; p.st[0].nblk = (p.c0 + p.c1) / 16; p.st[0].fold = 0;
+  p.st[0].cover = p.c0 + p.c1;
+  rc = ck(dv::launch_gn_stats(p, scratch, S(stream)), "gn_stats");
   if (rc != DV_OK) return rc;
   return ck(dv::launch_gn_apply(p, S(stream)), "gn_apply");
 }
 
-size_t dv_groupnorm_scratch_floats(int B, int L, int G) { return dv::gn_scratch_floats(B, L, G); }
+size_t dv_groupnorm_scratch_floats(int B, int L, int C) { return dv::gn_scratch_floats(B, L, C); }
 
 int dv_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C, float eps,
                  void* stream) {

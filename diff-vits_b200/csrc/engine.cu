@@ -120,29 +120,37 @@ struct Builder {
   }
   long long vec(const std::string& key, int n) { return slot(key, "vec", {key}, "f32", {n}); }
 
-  size_t stats_alloc(int L) {
-    size_t o = P.stats_bytes;
-    P.stats_bytes += align_up(gn_scratch_floats(P.B, L, P.cfg.norm_num_groups) * sizeof(float), 256);
-    return o;  // relative to off_stats
+  // GroupNorm partials of a GEMM output: [B][ceil(L/128)*4 row chunks][N/16 blocks][2] floats
+  void attach_stats(GemmDesc& g, TRef& out) {
+    const int chunks = ((g.l_out + 127) / 128) * 4;
+    g.stats_off = static_cast<long long>(P.stats_bytes);
+    g.stats_nblk = g.n / 16;
+    P.stats_bytes += align_up(static_cast<size_t>(P.B) * chunks * g.stats_nblk * 2 * sizeof(float), 256);
+    out.st_off = g.stats_off; out.st_chunks = chunks; out.st_nblk = g.stats_nblk; out.st_fold = 0;
   }
 
   // ---- op emitters
   void emit_gn(std::vector<Op>& list, const std::string& tag, TRef x0, TRef x1, const std::string& norm_key, float eps,
                bool silu, long long ss_off, TRef out) {
     const int C = x0.C + (x1.valid() ? x1.C : 0);
-    Op st;
-    st.kind = OP_GN_STATS; st.tag = tag + ".stats";
-    memset(&st.gn, 0, sizeof st.gn);
-    st.gn.c0 = x0.C; st.gn.c1 = x1.valid() ? x1.C : 0;
-    st.gn.B = P.B; st.gn.L = x0.L; st.gn.G = P.cfg.norm_num_groups;
-    st.gn.eps = eps; st.gn.silu = silu ? 1 : 0; st.gn.ss_ld = P.n_all;  // n_all patched at finalize
-    st.gno.x0 = x0.off; st.gno.x1 = x1.valid() ? x1.off : 0; st.gno.out = out.off; st.gno.stats = stats_alloc(x0.L);
-    st.gno.gamma = vec(norm_key + ".weight", C);
-    st.gno.beta = vec(norm_key + ".bias", C);
-    st.gno.ss = ss_off;
-    Op ap = st;
-    ap.kind = OP_GN_APPLY; ap.tag = tag + ".apply";
-    list.push_back(st);
+    if (x0.st_off < 0 || (x1.valid() && x1.st_off < 0)) { err = "internal: GroupNorm input without statistics: " + tag; return; }
+    Op ap;
+    ap.kind = OP_GN_APPLY; ap.tag = tag;
+    memset(&ap.gn, 0, sizeof ap.gn);
+    ap.gn.c0 = x0.C; ap.gn.c1 = x1.valid() ? x1.C : 0;
+    ap.gn.B = P.B; ap.gn.L = x0.L; ap.gn.G = P.cfg.norm_num_groups;
+    ap.gn.eps = eps; ap.gn.silu = silu ? 1 : 0;
+    ap.gn.nst = x1.valid() ? 2 : 1;
+    const TRef* xs[2] = {&x0, &x1};
+    for (int i = 0; i < ap.gn.nst; ++i) {
+      ap.gn.st[i].chunks = xs[i]->st_chunks; ap.gn.st[i].nblk = xs[i]->st_nblk;
+      ap.gn.st[i].fold = xs[i]->st_fold; ap.gn.st[i].cover = xs[i]->C;
+      ap.gno.st[i] = xs[i]->st_off;
+    }
+    ap.gno.x0 = x0.off; ap.gno.x1 = x1.valid() ? x1.off : 0; ap.gno.out = out.off;
+    ap.gno.gamma = vec(norm_key + ".weight", C);
+    ap.gno.beta = vec(norm_key + ".bias", C);
+    ap.gno.ss = ss_off;
     list.push_back(ap);
   }
   void emit_ln(std::vector<Op>& list, const std::string& tag, TRef x, const std::string& key, TRef out) {
@@ -174,7 +182,8 @@ struct Builder {
 
   // Linear / 1x1 conv: out[L, N] = a[L, K] W^T (+bias) (+res)
   void linear(std::vector<Op>& list, const std::string& tag, TRef a, const std::string& recipe,
-              std::vector<std::string> wkeys, const std::string& bias_key, int N, TRef res, TRef out, int out_mode) {
+              std::vector<std::string> wkeys, const std::string& bias_key, int N, TRef res, TRef& out, int out_mode,
+              bool stats = false) {
     Op& o = emit_gemm(list, tag);
     GemmDesc& g = o.g;
     add_src(g, a);
@@ -184,12 +193,13 @@ struct Builder {
     if (!bias_key.empty())
       g.bias_off = slot(tag + ".b", recipe == "geglu" ? "geglu_vec" : "vec", {bias_key}, "f32", {g.n_pad});
     g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C;
+    if (stats) attach_stats(g, out);
   }
 
   // conv k3 s1 p1 over `a` (+ optional 1x1 shortcut over xs fused as extra K panels) (+ optional identity residual)
   void conv3(std::vector<Op>& list, const std::string& tag, TRef a, int cin_real, const std::string& wkey,
              const std::string& bkey, int N, const TRef* sc_src, int n_sc, const std::string& sc_key, TRef res,
-             TRef out, int out_mode, bool dynamic_out) {
+             TRef& out, int out_mode, bool dynamic_out) {
     Op& o = emit_gemm(list, tag);
     GemmDesc& g = o.g;
     add_src(g, a);
@@ -208,6 +218,7 @@ struct Builder {
     g.w_off = wo;
     g.bias_off = slot(tag + ".b", "vec_sum", bk, "f32", {g.n_pad});
     g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
+    if (out_mode == GEMM_OUT_BF16) attach_stats(g, out);
   }
 
   TRef resnet(const std::string& pfx, TRef x0, TRef x1, int cout) {
@@ -307,7 +318,7 @@ struct Builder {
     // --- proj_out + residual
     TRef yo = act(L, C);
     linear(P.ops, pfx + ".proj_out", z, "linear", {pfx + ".proj_out.weight"}, pfx + ".proj_out.bias", C, y, yo,
-           GEMM_OUT_BF16);
+           GEMM_OUT_BF16, true);
     P.named.emplace_back(pfx, yo);
     return yo;
   }
@@ -328,6 +339,7 @@ struct Builder {
     P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2;
     g.bias_off = slot(key + ".b", "vec_sum", {key + ".bias"}, "f32", {g.n_pad});
     g.out = out; g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
+    attach_stats(g, out);
     P.named.emplace_back(key, out);
     return out;
   }
@@ -343,8 +355,10 @@ struct Builder {
     g.w_off = slot(key + ".W", "conv3_up2", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
     g.bias_off = slot(key + ".b", "vec_dup2", {key + ".bias"}, "f32", {g.n_pad});
     g.out = out2; g.l_out = x.L; g.out_mode = GEMM_OUT_BF16; g.ld_out = 2 * C;
+    attach_stats(g, out2);
     TRef out = out2;
     out.L = 2 * x.L; out.C = C;  // same bytes viewed as [2L, C]
+    out.st_fold = 1;             // partials are indexed by low-res row chunk and 2C/16 blocks: block kb also at kb + C/16
     P.named.emplace_back(key, out);
     return out;
   }
@@ -479,7 +493,7 @@ int Plan::build(std::string& err) {
           if (o.g.res.valid()) fix(o.g.res.off);
           fix(o.g.out.off);
           break;
-        case OP_GN_STATS: case OP_GN_APPLY:
+        case OP_GN_APPLY:
           fix(o.gno.x0); fix(o.gno.x1); fix(o.gno.out);
           o.gn.ss_ld = n_all;
           break;
@@ -512,7 +526,6 @@ int Plan::build(std::string& err) {
         o.flops = 4.0 * Bd * o.at.H * o.at.Lq * static_cast<double>(o.at.Lk) * o.at.D;
         o.bytes = 2.0 * Bd * o.at.H * o.at.D * (2.0 * o.at.Lq + 2.0 * o.at.Lk);
         break;
-      case OP_GN_STATS: o.bytes = 2.0 * Bd * o.gn.L * (o.gn.c0 + o.gn.c1); break;
       case OP_GN_APPLY: o.bytes = 4.0 * Bd * o.gn.L * (o.gn.c0 + o.gn.c1); break;
       case OP_LN: o.bytes = 4.0 * o.ln.rows * static_cast<double>(o.ln.C); break;
     }
@@ -546,6 +559,10 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
   }
   ws = static_cast<uint8_t*>(workspace);
   params = static_cast<const uint8_t*>(prm);
+  {
+    cudaError_t ie = gemm_tc_init();
+    if (ie != cudaSuccess) { err = std::string("gemm_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
+  }
   cudaError_t ce = cudaMemsetAsync(ws, 0, ws_bytes, st);
   if (ce != cudaSuccess) { err = cudaGetErrorString(ce); return DV_ERR_CUDA; }
 
@@ -576,11 +593,14 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.ld_res = g.res.valid() ? g.res.C : 0;
         p.out = g.out_dynamic ? nullptr : ws + g.out.off;
         p.ld_out = g.ld_out;
-      } else if (o.kind == OP_GN_STATS || o.kind == OP_GN_APPLY) {
+        p.stats = g.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + g.stats_off) : nullptr;
+        p.stats_nblk = g.stats_nblk;
+        p.bn = 0;
+      } else if (o.kind == OP_GN_APPLY) {
         o.gn.x0 = ws + o.gno.x0;
         o.gn.x1 = o.gn.c1 ? ws + o.gno.x1 : nullptr;
         o.gn.out = ws + o.gno.out;
-        o.gn.stats = reinterpret_cast<float*>(ws + off_stats + o.gno.stats);
+        for (int i = 0; i < o.gn.nst; ++i) o.gn.st[i].ptr = reinterpret_cast<const float*>(ws + off_stats + o.gno.st[i]);
         o.gn.gamma = pf(o.gno.gamma);
         o.gn.beta = pf(o.gno.beta);
         o.gn.scale_shift = o.gno.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + o.gno.ss;
@@ -627,7 +647,6 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
           e = launch_gemm_tc(o.gp, st);
         }
         break;
-      case OP_GN_STATS: e = launch_gn_stats(o.gn, st); break;
       case OP_GN_APPLY: e = launch_gn_apply(o.gn, st); break;
       case OP_LN: e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st); break;
       case OP_ATTN: {

@@ -13,6 +13,9 @@ namespace dv {
 struct TRef {  // bf16 channel-last tensor [B, L, C] at byte offset `off` of the workspace
   size_t off = 0;
   int L = 0, C = 0;
+  // GroupNorm partial statistics written by the producing GEMM's epilogue (offset inside the stats region)
+  long long st_off = -1;
+  int st_chunks = 0, st_nblk = 0, st_fold = 0;
   bool valid() const { return C > 0; }
 };
 
@@ -25,7 +28,7 @@ struct ParamSlot {
   size_t off = 0, bytes = 0;
 };
 
-enum OpKind { OP_GEMM, OP_GN_STATS, OP_GN_APPLY, OP_LN, OP_ATTN };
+enum OpKind { OP_GEMM = 0, OP_GN_APPLY = 2, OP_LN = 3, OP_ATTN = 4 };
 
 struct GemmDesc {
   int nsrc = 0;
@@ -38,6 +41,8 @@ struct GemmDesc {
   TRef res; TRef out;
   int l_out = 0, out_mode = GEMM_OUT_BF16, ld_out = 0;
   bool out_dynamic = false;  // conv_out: destination supplied per call
+  long long stats_off = -1;  // >= 0: emit GroupNorm partials of the output
+  int stats_nblk = 0;
 };
 
 struct Op {
@@ -49,7 +54,7 @@ struct Op {
   struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; } ln;
   AttnParams at;
   // deferred (offset-based) descriptions resolved in bind()
-  struct { size_t x0, x1, out, stats; long long gamma, beta, ss; } gno;
+  struct { size_t x0, x1, out; long long st[2]; long long gamma, beta, ss; } gno;
   struct { size_t x, out; long long gamma, beta; } lno;
   struct { size_t q, k, v, o; bool cross; } ato;
 };

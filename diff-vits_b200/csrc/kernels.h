@@ -42,8 +42,13 @@ struct alignas(64) GemmParams {
   int ld_res;
   void* out;
   int ld_out;
+  float* stats;         // optional GroupNorm partials of the stored tensor: [B][tiles_per_batch*4][stats_nblk][2]
+  int stats_nblk;       // 16-channel blocks per row chunk (= N / 16)
+  int bn;               // N tile (128 / 256); 0 = choose
 };
 
+cudaError_t gemm_tc_init();                       // query the device, set kernel attributes (call outside graph capture)
+int gemm_pick_bn(int m_tiles, int n_pad);
 cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st);
 // Debug/reference implementation of exactly the same contract on CUDA cores (plain loads, fp32 FMA).
 // Used by tests to cross-check the tcgen05 kernel; never used by the engine.
@@ -62,18 +67,30 @@ struct AttnParams {
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);
 
 // ------------------------------------------------------------------ norms
+// Partial statistics layout (written by the GEMM epilogue or by gn_stats): float [B][chunks][nblk][2] holding the
+// sum / sum of squares of a 32-row x 16-channel block. A GroupNorm group is any union of such blocks, also across
+// the two sources of a channel concat.
+struct GnStatSrc {
+  const float* ptr;   // partials
+  int chunks;         // 32-row chunks per batch item in the producer's row space
+  int nblk;           // 16-channel blocks per chunk in the producer's column space
+  int fold;           // 1: producer wrote [L/2, 2C] (folded nearest-2x upsample): block kb also lives at kb + nblk/2
+  int cover;          // channels of the normalised tensor this source covers (starting where the previous one ended)
+};
 struct GnParams {
   const void* x0; int c0;      // first source  bf16 [B, L, c0]
   const void* x1; int c1;      // optional second source (channel concat), bf16 [B, L, c1]
+  GnStatSrc st[2];
+  int nst;
   int B, L, G;
-  float* stats;                // scratch [B, ceil(L/32), G, 2]: per row-chunk sum / sum of squares (gn_scratch_floats)
   const float* gamma; const float* beta;   // [c0 + c1]
   const float* scale_shift; int ss_ld;     // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + C + c]
   float eps; int silu;
   void* out;                   // bf16 [B, L, c0 + c1]
 };
-size_t gn_scratch_floats(int B, int L, int G);
-cudaError_t launch_gn_stats(const GnParams& p, cudaStream_t st);
+size_t gn_scratch_floats(int B, int L, int C);
+// standalone statistics pass over (x0 | x1) into `scratch` (same partial layout, one source covering all channels)
+cudaError_t launch_gn_stats(const GnParams& p, float* scratch, cudaStream_t st);
 cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st);
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
                              float eps, cudaStream_t st);

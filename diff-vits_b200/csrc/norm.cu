@@ -1,9 +1,12 @@
 // GroupNorm (+SiLU, + time scale/shift) and LayerNorm on channel-last bf16 activations. HBM/L2-bound kernels:
-// 16-byte vector loads along the contiguous channel axis, fp32 math, statistics accumulated in fp64.
+// 16-byte vector loads along the contiguous channel axis, fp32 math, statistics combined in fp64.
 //
-// GroupNorm is split in two fully parallel launches so it scales from B=1 to B=256:
-//   gn_stats : per-(b, 32-row chunk, group) sum / sum-of-squares; supports a channel concat of two sources
-//              (torch.cat([h, skip], 1) in the up blocks is never materialised - groups may straddle the seam).
+// GroupNorm statistics arrive as partial sums per (32-row chunk, 16-channel block), normally written by the epilogue
+// of the GEMM that produced the tensor (csrc/gemm_tc.cu), so the tensor is not re-read; gn_stats below produces the
+// same layout for tensors that do not come from a GEMM (tests, stand-alone use). A group is any union of blocks,
+// also across the two sources of torch.cat([h, skip], 1) in the up blocks (never materialised; groups may straddle
+// the seam, e.g. 896 = 512 + 384 channels in 8 groups of 112). All reductions are fixed-order: bit reproducible and
+// independent of the batch size.
 //   gn_apply : y = SiLU?( ((x-mean)*rstd*gamma+beta) * (1+scale[b,c]) + shift[b,c] ) -> bf16 GEMM operand.
 // Reference: unet1d/resnet.py:591-631 (norm1/norm2 + scale_shift), transformer_1d.py:256 (eps 1e-6),
 // unet_1d_condition.py:1029-1031 (conv_norm_out + SiLU).
@@ -14,7 +17,6 @@ namespace dv {
 namespace {
 
 constexpr int NT = 256;
-constexpr int GN_ROWS_PER_CTA = 32;
 
 __device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, int c) {
   if (c < p.c0)
@@ -24,17 +26,15 @@ __device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, 
                                         (static_cast<size_t>(b) * p.L + l) * p.c1 + (c - p.c0));
 }
 
-// Deterministic two-level reduction (no atomics): per-thread partials -> shared -> one fp32 partial per
-// (b, row-chunk, group); gn_apply sums the row-chunk partials in a fixed order in fp64. Bit-reproducible run to run
-// and independent of the batch size, so a sample computes identically alone or inside a batch.
-__global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p) {
+// One CTA per (32-row chunk, batch item): partial sums per 16-channel block.
+__global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p, float* __restrict__ scratch) {
   __shared__ float ps[NT][2];
   const int C = p.c0 + p.c1;
   const int octs = C >> 3;
   const int R = NT / octs;
   const int b = blockIdx.y;
-  const int lbeg = blockIdx.x * GN_ROWS_PER_CTA;
-  const int lend = min(lbeg + GN_ROWS_PER_CTA, p.L);
+  const int lbeg = blockIdx.x * 32;
+  const int lend = min(lbeg + 32, p.L);
   const int r = threadIdx.x / octs, o = threadIdx.x % octs;
   float s = 0.f, ss = 0.f;
   if (r < R) {
@@ -52,50 +52,67 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p) {
   ps[threadIdx.x][0] = s;
   ps[threadIdx.x][1] = ss;
   __syncthreads();
-  if (threadIdx.x < octs) {  // fold the R row-slots of this octet
-    float a = ps[threadIdx.x][0], c = ps[threadIdx.x][1];
-    for (int rr = 1; rr < R; ++rr) { a += ps[rr * octs + threadIdx.x][0]; c += ps[rr * octs + threadIdx.x][1]; }
-    ps[threadIdx.x][0] = a;
-    ps[threadIdx.x][1] = c;
-  }
-  __syncthreads();
-  if (threadIdx.x < p.G) {   // fold the octets of this group
-    const int opg = (C / p.G) >> 3;
+  if (threadIdx.x < (octs >> 1)) {   // fold the R row slots and the two octets of a 16-channel block, fixed order
     float a = 0.f, c = 0.f;
-    for (int k = 0; k < opg; ++k) { a += ps[threadIdx.x * opg + k][0]; c += ps[threadIdx.x * opg + k][1]; }
-    float* dst = p.stats + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * p.G + threadIdx.x) * 2;
+    for (int rr = 0; rr < R; ++rr)
+      for (int h = 0; h < 2; ++h) {
+        a += ps[rr * octs + threadIdx.x * 2 + h][0];
+        c += ps[rr * octs + threadIdx.x * 2 + h][1];
+      }
+    float* dst = scratch + ((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * (octs >> 1) + threadIdx.x) * 2;
     dst[0] = a;
     dst[1] = c;
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p) {
+__global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows_per_cta) {
+  __shared__ float s_mean[32], s_rstd[32];
   const int C = p.c0 + p.c1;
+  const int cpg = C / p.G;
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- group statistics: one warp per group, lanes stride over the partials, fixed shuffle tree
+  for (int g = warp; g < p.G; g += NT / 32) {
+    double sum = 0.0, sumsq = 0.0;
+    const int kb0 = (g * cpg) >> 4, kb1 = ((g + 1) * cpg) >> 4;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      int cov0 = 0, si = 0;
+      while (si + 1 < p.nst && (kb << 4) >= cov0 + p.st[si].cover) { cov0 += p.st[si].cover; ++si; }
+      const GnStatSrc st = p.st[si];
+      const int kl = kb - (cov0 >> 4);
+      const int nf = st.fold ? 2 : 1;
+      const float* base = st.ptr + static_cast<size_t>(b) * st.chunks * st.nblk * 2;
+      for (int i = lane; i < st.chunks * nf; i += 32) {
+        const int ch = i / nf, f = i % nf;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(ch) * st.nblk + kl + f * (st.nblk >> 1)) * 2));
+        sum += static_cast<double>(v.x);
+        sumsq += static_cast<double>(v.y);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, m);
+      sumsq += __shfl_xor_sync(0xffffffffu, sumsq, m);
+    }
+    if (lane == 0) {
+      const double n = static_cast<double>(p.L) * cpg;
+      const double mean = sum / n;
+      double var = sumsq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+    }
+  }
+  __syncthreads();
   const int octs = C >> 3;
   const int R = NT / octs;
-  const int b = blockIdx.y;
-  const int lbeg = blockIdx.x * GN_ROWS_PER_CTA;
-  const int lend = min(lbeg + GN_ROWS_PER_CTA, p.L);
+  const int lbeg = blockIdx.x * rows_per_cta;
+  const int lend = min(lbeg + rows_per_cta, p.L);
   const int r = threadIdx.x / octs, o = threadIdx.x % octs;
   if (r >= R) return;
   const int cbase = o * 8;
-  const int cpg = C / p.G;
   const int grp = cbase / cpg;
-  const double n = static_cast<double>(p.L) * cpg;
-  double sum = 0.0, sumsq = 0.0;
-  {
-    const float* src = p.stats + (static_cast<size_t>(b) * gridDim.x * p.G + grp) * 2;
-    for (unsigned c = 0; c < gridDim.x; ++c) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(src + static_cast<size_t>(c) * p.G * 2));
-      sum += static_cast<double>(v.x);
-      sumsq += static_cast<double>(v.y);
-    }
-  }
-  const double mean_d = sum / n;
-  double var_d = sumsq / n - mean_d * mean_d;
-  if (var_d < 0.0) var_d = 0.0;
-  const float mean = static_cast<float>(mean_d);
-  const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(p.eps)));
+  const float mean = s_mean[grp], rstd = s_rstd[grp];
   float ca[8], cb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -173,22 +190,26 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 
 static bool gn_ok(const GnParams& p) {
   const int C = p.c0 + p.c1;
-  return p.G > 0 && p.G <= 32 && C % (8 * p.G) == 0 && p.c0 % 8 == 0 && p.c1 % 8 == 0 && C / 8 <= NT;
+  return p.G > 0 && p.G <= 32 && C % (16 * p.G) == 0 && p.c0 % 16 == 0 && p.c1 % 16 == 0 && C / 8 <= NT;
 }
-cudaError_t launch_gn_stats(const GnParams& p, cudaStream_t st) {
+size_t gn_scratch_floats(int B, int L, int C) {
+  return static_cast<size_t>(B) * ((L + 31) / 32) * (C / 16) * 2;
+}
+cudaError_t launch_gn_stats(const GnParams& p, float* scratch, cudaStream_t st) {
   if (!gn_ok(p)) return cudaErrorInvalidValue;
-  dim3 grid((p.L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, p.B);
-  gn_stats_kernel<<<grid, NT, 0, st>>>(p);
+  dim3 grid((p.L + 31) / 32, p.B);
+  gn_stats_kernel<<<grid, NT, 0, st>>>(p, scratch);
   return cudaGetLastError();
 }
 cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
-  if (!gn_ok(p)) return cudaErrorInvalidValue;
-  dim3 grid((p.L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA, p.B);
-  gn_apply_kernel<<<grid, NT, 0, st>>>(p);
+  if (!gn_ok(p) || p.nst < 1 || p.nst > 2) return cudaErrorInvalidValue;
+  // about two waves of CTAs on 148 SMs x 8 resident CTAs would be ideal; never fewer than 32 rows per CTA
+  int per_batch = (2 * 148 + p.B - 1) / p.B;
+  int rows = (p.L + per_batch - 1) / per_batch;
+  if (rows < 32) rows = 32;
+  dim3 grid((p.L + rows - 1) / rows, p.B);
+  gn_apply_kernel<<<grid, NT, 0, st>>>(p, rows);
   return cudaGetLastError();
-}
-size_t gn_scratch_floats(int B, int L, int G) {
-  return static_cast<size_t>(B) * ((L + GN_ROWS_PER_CTA - 1) / GN_ROWS_PER_CTA) * G * 2;
 }
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
                              float eps, cudaStream_t st) {

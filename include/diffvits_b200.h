@@ -129,13 +129,17 @@ typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; } dv_gem
 DV_API int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
             int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
             int L_out, int impl, void* stream);
+/* Test hooks for the next dv_gemm calls of this thread: force the N tile (128 / 256, 0 = heuristic) and let the
+ * epilogue emit GroupNorm partials [B][ceil(L/128)*4][n/16][2] into `stats` (NULL = off). */
+DV_API void dv_gemm_test_options(int bn, float* stats);
 /* F.scaled_dot_product_attention (attention_processor.py:1032); bf16 q/k/v/o with element strides. */
 DV_API int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
                  long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,
                  float scale, const int32_t* kv_len, void* stream);
 /* nn.GroupNorm (+SiLU, + (1+scale)*x+shift) on channel-last bf16 (resnet.py:591-631).
- * scratch: dv_groupnorm_scratch_floats(B, L, G) floats (per row-chunk partial sums; deterministic reduction). */
-DV_API size_t dv_groupnorm_scratch_floats(int B, int L, int G);
+ * scratch: dv_groupnorm_scratch_floats(B, L, c0 + c1) floats: partial sums per (32-row chunk, 16-channel block),
+ * the layout the GEMM epilogue emits inside the engine; deterministic fixed-order reduction. */
+DV_API size_t dv_groupnorm_scratch_floats(int B, int L, int C);
 DV_API int dv_groupnorm(const void* x0, int c0, const void* x1, int c1, int B, int L, int G, float* scratch,
                  const float* gamma, const float* beta, const float* scale_shift, int ss_ld, float eps, int silu,
                  void* out, void* stream);

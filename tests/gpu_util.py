@@ -32,7 +32,8 @@ def bf16r(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, n: int,
          bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, out_mode: int = 0, impl: int = 0,
-         l_out: Optional[int] = None, views: Optional[Sequence[Tuple[int, int]]] = None) -> torch.Tensor:
+         l_out: Optional[int] = None, views: Optional[Sequence[Tuple[int, int]]] = None, bn: int = 0,
+         stats: bool = False):
     """srcs: bf16 [B, L, C] tensors; segs: (src, row_off, c0, channels); w: bf16 [n_pad, k_tot].
     views: optional (L_view, C_view) per source (the stride-2 conv reads [L/2, 2C])."""
     lib = _lib.load()
@@ -60,9 +61,16 @@ def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]]
     else:
         out = torch.zeros(B, L_out, n // 2, dtype=torch.bfloat16, device=dev)
         ld_out = n // 2
-    check(lib.dv_gemm(S, len(srcs), G, len(segs), vp(w), k_tot, n, n_pad, vp(bias), vp(res),
-                      0 if res is None else res.shape[-1], vp(out), ld_out, out_mode, B, L_out, impl, stream()))
-    return out
+    st = None
+    if stats:
+        st = torch.full((B, (L_out + 127) // 128 * 4, n // 16, 2), float("nan"), dtype=torch.float32, device=dev)
+    lib.dv_gemm_test_options(bn, vp(st))
+    try:
+        check(lib.dv_gemm(S, len(srcs), G, len(segs), vp(w), k_tot, n, n_pad, vp(bias), vp(res),
+                          0 if res is None else res.shape[-1], vp(out), ld_out, out_mode, B, L_out, impl, stream()))
+    finally:
+        lib.dv_gemm_test_options(0, None)
+    return (out, st) if stats else out
 
 
 def attention(q, k, v, heads: int, kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -83,7 +91,7 @@ def groupnorm(x0, x1, G, gamma, beta, eps, silu, ss=None) -> torch.Tensor:
     B, L, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[2]
     out = torch.zeros(B, L, c0 + c1, dtype=torch.bfloat16, device=x0.device)
-    stats = torch.empty(lib.dv_groupnorm_scratch_floats(B, L, G), dtype=torch.float32, device=x0.device)
+    stats = torch.empty(lib.dv_groupnorm_scratch_floats(B, L, c0 + c1), dtype=torch.float32, device=x0.device)
     check(lib.dv_groupnorm(vp(x0), c0, vp(x1), c1, B, L, G, vp(stats), vp(gamma), vp(beta), vp(ss),
                            0 if ss is None else ss.shape[1], eps, 1 if silu else 0, vp(out), stream()))
     return out

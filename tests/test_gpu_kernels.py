@@ -44,6 +44,34 @@ def test_gemm_linear(U, B, L, K, N):
     assert U.rel_l2(raw[:, :, :N], a.float() @ w.float().t() + bias) < 1e-5
 
 
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_tile_width_and_groupnorm_partials(U, bn):
+    """Both N-tile instantiations (persistent schedule over many tiles) + the epilogue's GroupNorm partial sums:
+    per (32-row chunk, 16-channel block) sum / sum of squares of the STORED bf16 values."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, L, K, N = 5, 1000, 384, 512            # 5 x 8 row tiles x 2-4 column tiles: several tiles per CTA... on 148 SMs
+    a = _rand((B, L, K), g)
+    w = _rand((N, K), g, K ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = _rand((B, L, N), g)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    got, st = U.gemm([a], [(0, 0, 0, K)], w, N, bias=bias, res=res, bn=bn, stats=True)
+    _check_bf16(U, got, ref)
+    rows = (L + 127) // 128 * 128
+    y = torch.zeros(B, rows, N, device="cuda")
+    y[:, :L] = got.float()
+    blk = y.reshape(B, rows // 32, 32, N // 16, 16)
+    want = torch.stack([blk.sum(dim=(2, 4)), (blk * blk).sum(dim=(2, 4))], dim=-1)
+    assert torch.isfinite(st).all()
+    assert U.rel_l2(st, want) < 1e-5
+    # many more tiles than SMs: every CTA loops (B=40 -> 320 row tiles x N/bn)
+    B2 = 40
+    a2 = _rand((B2, L, 128), g)
+    w2 = _rand((256, 128), g, 128 ** -0.5)
+    got2 = U.gemm([a2], [(0, 0, 0, 128)], w2, 256, bn=bn)
+    _check_bf16(U, got2, a2.float() @ w2.float().t())
+
+
 @pytest.mark.parametrize("B,L,Cin,Cout", [(2, 257, 128, 128), (1, 200, 256, 384), (2, 1000, 384, 128), (2, 26, 512, 512)])
 def test_gemm_conv3(U, B, L, Cin, Cout):
     """conv1d k3 s1 p1: three row-shifted K segments, zero fill outside [0, L)."""
