@@ -135,6 +135,10 @@ int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, cons
 // ------------------------------------------------------------------------------------------ single kernels
 static thread_local float* g_test_stats = nullptr;
 static thread_local int g_test_bn = 0;
+static thread_local unsigned long long* g_test_trace = nullptr;
+static thread_local int g_test_flags = 0;
+void dv_gemm_test_trace(unsigned long long* buf) { g_test_trace = buf; }
+void dv_gemm_test_flags(int flags) { g_test_flags = flags; }
 /* Test hooks for dv_gemm: force the N tile (0 = heuristic) and ask the epilogue for GroupNorm partials. */
 void dv_gemm_test_options(int bn, float* stats) { g_test_bn = bn; g_test_stats = stats; }
 
@@ -173,7 +177,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   p.tiles_per_batch = (L_out + 127) / 128;
   p.out_mode = out_mode;
   p.bias = bias; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out;
-  p.stats = g_test_stats; p.stats_nblk = n / 16; p.bn = g_test_bn;
+  p.stats = g_test_stats; p.stats_nblk = n / 16; p.bn = g_test_bn; p.trace = g_test_trace; p.dbg_flags = g_test_flags;
   if (impl == 1) return ck(dv::launch_gemm_ref(p, rs, w, k_tot, S(stream)), "gemm_ref");
   return ck(dv::launch_gemm_tc(p, S(stream)), "gemm_tc");
 }

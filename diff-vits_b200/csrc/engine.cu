@@ -635,7 +635,7 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
                       cudaEvent_t* events) {
   int idx = 0;
   for (Op& o : list) {
-    if (events) cudaEventRecord(events[idx++], st);
+    if (events) cudaEventRecordWithFlags(events[idx++], st, cudaEventRecordExternal);
     cudaError_t e = cudaSuccess;
     switch (o.kind) {
       case OP_GEMM:
@@ -691,21 +691,39 @@ int Plan::set_cond(const float* cond, cudaStream_t st, std::string& err) {
 
 int Plan::profile_forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
                           float* ms, int cap, std::string& err) {
+  // One denoiser call captured into a CUDA graph with an external event-record node between consecutive launches, so
+  // the intervals are device-side times of the call AS IT RUNS IN THE PRODUCT (graph replay), free of CPU launch cost.
   const int n = static_cast<int>(ops.size());
   if (cap < n + 1) { err = "ms buffer too small (need ops + 1)"; return DV_ERR_INVALID; }
+  if (!cap_stream) DV_CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
   std::vector<cudaEvent_t> ev(n + 2);
   for (auto& e : ev) DV_CK(cudaEventCreate(&e));
   int launches = 0;
-  DV_CK(cudaEventRecord(ev[n + 1], st));                 // start of the prologue (layout change + time embedding)
-  int rc = forward(sample, x_only, t, t_stride, out, st, err, &launches, ev.data());
-  if (rc == DV_OK) {
-    DV_CK(cudaEventRecord(ev[n], st));
-    DV_CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
-    cudaEventElapsedTime(&ms[n], ev[n + 1], ev[0]);      // prologue
+  DV_CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+  cudaError_t ce = cudaEventRecordWithFlags(ev[n + 1], cap_stream, cudaEventRecordExternal);   // prologue start
+  int rc = ce == cudaSuccess ? forward(sample, x_only, t, t_stride, out, cap_stream, err, &launches, ev.data()) : DV_ERR_CUDA;
+  if (rc == DV_OK) ce = cudaEventRecordWithFlags(ev[n], cap_stream, cudaEventRecordExternal);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce2 = cudaStreamEndCapture(cap_stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (rc == DV_OK && ce == cudaSuccess && ce2 == cudaSuccess) ce2 = cudaGraphInstantiate(&exec, graph, 0);
+  if (rc == DV_OK && ce == cudaSuccess && ce2 == cudaSuccess) {
+    for (int rep = 0; rep < 2 && ce2 == cudaSuccess; ++rep) ce2 = cudaGraphLaunch(exec, st);   // second replay is timed
+    if (ce2 == cudaSuccess) ce2 = cudaStreamSynchronize(st);
+    if (ce2 == cudaSuccess) {
+      for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+      cudaEventElapsedTime(&ms[n], ev[n + 1], ev[0]);    // prologue (layout change + time embedding)
+    }
   }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
   for (auto& e : ev) cudaEventDestroy(e);
-  return rc;
+  if (rc != DV_OK) return rc;
+  if (ce != cudaSuccess || ce2 != cudaSuccess) {
+    err = std::string("profile_forward: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ce2);
+    return DV_ERR_CUDA;
+  }
+  return DV_OK;
 }
 
 int Plan::forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,

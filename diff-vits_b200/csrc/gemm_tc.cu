@@ -27,28 +27,123 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter: they split the tile's columns
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_PITCH = 80;                       // bytes per staged row: 32 bf16 (64 B) + 16 B pad
 constexpr int EPI_SLAB = 32 * EPI_PITCH;            // per epilogue warp
+constexpr int MAX_NPAD = 4096;                      // bias vector kept in shared memory for the whole kernel
 
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int STAGES = BN == 128 ? 5 : 3;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_SLAB;
+  static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_SLAB;
+  static constexpr int BAR_OFF = BIAS_OFF + MAX_NPAD * 4;
   static constexpr int TOTAL = BAR_OFF + 256;          // barriers + tmem slot
   static constexpr int DYN_BYTES = TOTAL + 1024;       // slack for 1024-byte alignment
   static_assert(DYN_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
+// debug timeline (enabled only when p.trace != nullptr): CTA 0, one lane per role
+__device__ __forceinline__ void trace_ev(const GemmParams& p, int role, int tile, int ev) {
+  if (p.trace && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(p.trace, 1ULL);
+    if (i < 4000) p.trace[1 + i] = (static_cast<unsigned long long>(role) << 60) | (static_cast<unsigned long long>(tile & 0xFFFF) << 44) |
+                                   (static_cast<unsigned long long>(ev & 0xF) << 40) | (clock64() & 0xFFFFFFFFFFULL);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
+}
+
+struct EpiCtx {
+  uint32_t mine;    // smem address of this thread's staged row
+  uint32_t coal;    // smem address for the row-contiguous phase (row = lane/4, 16-byte piece = lane%4)
+  uint32_t sbias;   // smem address of the bias vector
+  int lane, srow, spiece;
+};
+
+// One 32-row x 32-column chunk of a bf16 output tile: (+bias) (+residual) -> bf16, GroupNorm partials, coalesced store.
+template <bool HAS_RES, bool HAS_STATS>
+__device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx& e, uint32_t taddr_c, int gcol, int lq,
+                                              size_t rowbase, bool valid, size_t stat_chunk, bool last, uint64_t* empty_bar) {
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  uint4 rv[4];
+  if (HAS_RES) {   // row-contiguous residual fetch (64-byte segments), in flight during the TMEM load
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.res);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + e.srow;
+      rv[i] = (lq + r < p.L) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
+                             : make_uint4(0, 0, 0, 0);
+    }
+  }
+  uint32_t r[32];
+  tmem_ld32(taddr_c, r);
+  if (HAS_RES) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sts128(e.coal + i * 8 * EPI_PITCH, rv[i]);
+  }
+  tmem_ld_wait();
+  if (last) {                                           // last TMEM read of this tile by this warp
+    tc_fence_before();
+    if (e.lane == 0) mbar_arrive(empty_bar);
+  }
+  uint32_t rr[16];
+  if (HAS_RES) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = lds128(e.mine + j * 16);
+      rr[4 * j] = t.x; rr[4 * j + 1] = t.y; rr[4 * j + 2] = t.z; rr[4 * j + 3] = t.w;
+    }
+  }
+  uint32_t packed[16];
+  float2 s0 = make_float2(0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {                      // 4 columns per iteration: one broadcast LDS.128 of bias
+    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bq = lds128f(e.sbias + (gcol + 4 * j4) * 4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 4 * j4 + 2 * h;
+      float2 v = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+      v = add_f32x2(v, h ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y));
+      if (HAS_RES) v = add_f32x2(v, make_float2(bf16_lo(rr[j >> 1]), bf16_hi(rr[j >> 1])));
+      packed[j >> 1] = pack_bf16(v.x, v.y);
+      if (HAS_STATS) {
+        if (j < 16) { s0 = add_f32x2(s0, v); q0 = fma_f32x2(v, v, q0); }
+        else        { s1 = add_f32x2(s1, v); q1 = fma_f32x2(v, v, q1); }
+      }
+    }
+  }
+  if (HAS_STATS) {
+    // GroupNorm partials per 16-channel block over this warp's 32 rows (fp32 accumulator values; the stored bf16
+    // differs by rounding noise only). Fixed shuffle tree: deterministic.
+    float a0 = s0.x + s0.y, b0 = q0.x + q0.y, a1 = s1.x + s1.y, b1 = q1.x + q1.y;
+    if (!valid) { a0 = b0 = a1 = b1 = 0.f; }
+    a0 = warp_sum(a0); b0 = warp_sum(b0); a1 = warp_sum(a1); b1 = warp_sum(b1);
+    if (e.lane == 0)
+      *reinterpret_cast<float4*>(p.stats + (stat_chunk * p.stats_nblk + (gcol >> 4)) * 2) = make_float4(a0, b0, a1, b1);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts128(e.mine + j * 16, make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rrow = i * 8 + e.srow;
+    if (lq + rrow < p.L)
+      *reinterpret_cast<uint4*>(out + (rowbase + lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
+          lds128(e.coal + i * 8 * EPI_PITCH);
+  }
+  __syncwarp();
 }
 
 template <int BN>
@@ -85,6 +180,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp >= 2 && p.bias) {                         // bias vector -> shared memory, once per CTA
+    float* sb = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
+    for (int i = threadIdx.x - 64; i < p.n_pad; i += EPI_WARPS * 32) sb[i] = __ldg(p.bias + i);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -101,6 +200,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int b = mi / p.tiles_per_batch;
         const int l0 = (mi % p.tiles_per_batch) * BM;
         int kp = 0;
+        trace_ev(p, 0, tile, 0);
         for (int s = 0; s < p.nseg; ++s) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* ma = &p.mapA[sg.src];
@@ -108,6 +208,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * SL::STAGE_BYTES;
             uint8_t* sb = sa + SL::A_BYTES;
+            if (p.dbg_flags & 4) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
             mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
             tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
             // the W map's box is 64 x 128 rows: a 256-wide tile takes two boxes
@@ -129,8 +230,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        trace_ev(p, 1, tile, 0);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
+        trace_ev(p, 1, tile, 1);
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kp = 0; kp < total_panels; ++kp) {
           mbar_wait(&full_bar[stage], phase);
@@ -138,6 +241,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + SL::A_BYTES);
+          if (!(p.dbg_flags & 2))
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
@@ -147,17 +251,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
+        trace_ev(p, 1, tile, 2);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue: warps 2..9
-    // TMEM lane quarter is fixed by hardware to (warp id % 4); the two warps of a quarter split the columns.
+    // ------------------------------------------------------------------ epilogue: warps 2..17
+    // TMEM lane quarter is fixed by hardware to (warp id % 4); the four warps of a quarter split the columns.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    uint8_t* slab = smem + SL::EPI_OFF + (warp - 2) * EPI_SLAB;
-    const int srow = lane >> 2, spiece = lane & 3;       // coalesced phase: 8 rows x 4 pieces of 16 B per instruction
+    const int part = (warp - 2) >> 2;                    // 0..3
+    EpiCtx e;
+    const uint32_t slab = smem_u32(smem + SL::EPI_OFF + (warp - 2) * EPI_SLAB);
+    e.lane = lane; e.srow = lane >> 2; e.spiece = lane & 3;
+    e.mine = slab + lane * EPI_PITCH;
+    e.coal = slab + e.srow * EPI_PITCH + e.spiece * 16;
+    e.sbias = smem_u32(smem + SL::BIAS_OFF);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -168,164 +277,112 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int lq = mt * BM + quad * 32;               // first row of this warp's 32-row slab
       const int l = lq + lane;                          // this thread's accumulator row
       const bool valid = l < p.L;
+      if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 0);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 1);
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       const size_t rowbase = static_cast<size_t>(b) * p.L;
 
-      if (p.out_mode == GEMM_OUT_GEGLU) {
-        // tile columns repeat [u 64 | gate 64]; this warp takes 32-wide (u, gate) chunk pairs with index % 2 == half
+      if (p.dbg_flags & 1) {
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      } else if (p.out_mode == GEMM_OUT_GEGLU) {
+        // tile columns repeat [u 64 | gate 64]; work unit = 16 u columns + their 16 gate columns -> 16 outputs
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-        constexpr int NPAIR = BN / 64;
-        for (int pr = half; pr < NPAIR; pr += 2) {
-          const int cu = (pr >> 1) * 128 + (pr & 1) * 32;
-          const int ocol = (n0 >> 1) + (pr >> 1) * 64 + (pr & 1) * 32;
-          uint32_t u[32], g[32];
-          tmem_ld32(taddr + cu, u);
-          tmem_ld32(taddr + cu + 64, g);
+        constexpr int NUNIT = BN / 32;                   // 4 per 128 tile columns
+        const int orow = lane >> 1, opiece = lane & 1;   // row-contiguous phase: 16 rows x 2 pieces of 16 B
+#pragma unroll 1
+        for (int un = part; un < NUNIT; un += 4) {
+          const int cu = (un >> 2) * 128 + (un & 3) * 16;
+          const int ocol = (n0 >> 1) + (un >> 2) * 64 + (un & 3) * 16;
+          uint32_t u[16], g[16];
+          tmem_ld16(taddr + cu, u);
+          tmem_ld16(taddr + cu + 64, g);
           tmem_ld_wait();
-          if (pr + 2 >= NPAIR) {                          // last TMEM read of this tile by this warp
+          if (un + 4 >= NUNIT) {                          // last TMEM read of this tile by this warp
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
-          uint32_t packed[16];
+          uint32_t packed[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float u0 = __uint_as_float(u[j]), u1 = __uint_as_float(u[j + 1]);
-            float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bg = bu;
             if (p.bias) {
-              u0 += __ldg(p.bias + n0 + cu + j);
-              u1 += __ldg(p.bias + n0 + cu + j + 1);
-              g0 += __ldg(p.bias + n0 + cu + 64 + j);
-              g1 += __ldg(p.bias + n0 + cu + 64 + j + 1);
+              bu = lds128f(e.sbias + (n0 + cu + 4 * j4) * 4);
+              bg = lds128f(e.sbias + (n0 + cu + 64 + 4 * j4) * 4);
             }
-            packed[j >> 1] = pack_bf16(u0 * gelu_erf_f(g0), u1 * gelu_erf_f(g1));
+            const int j = 4 * j4;
+            const float2 ua = add_f32x2(make_float2(__uint_as_float(u[j]), __uint_as_float(u[j + 1])), make_float2(bu.x, bu.y));
+            const float2 ub = add_f32x2(make_float2(__uint_as_float(u[j + 2]), __uint_as_float(u[j + 3])), make_float2(bu.z, bu.w));
+            const float2 ga = add_f32x2(make_float2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), make_float2(bg.x, bg.y));
+            const float2 gb = add_f32x2(make_float2(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), make_float2(bg.z, bg.w));
+            packed[2 * j4] = pack_bf16(ua.x * gelu_fast_f(ga.x), ua.y * gelu_fast_f(ga.y));
+            packed[2 * j4 + 1] = pack_bf16(ub.x * gelu_fast_f(gb.x), ub.y * gelu_fast_f(gb.y));
           }
-          uint4* mine = reinterpret_cast<uint4*>(slab + lane * EPI_PITCH);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mine[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          sts128(e.mine, make_uint4(packed[0], packed[1], packed[2], packed[3]));
+          sts128(e.mine + 16, make_uint4(packed[4], packed[5], packed[6], packed[7]));
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + srow;
+          for (int i = 0; i < 2; ++i) {
+            const int r = i * 16 + orow;
             if (lq + r < p.L)
-              *reinterpret_cast<uint4*>(out + (rowbase + lq + r) * p.ld_out + ocol + spiece * 8) =
-                  *reinterpret_cast<const uint4*>(slab + r * EPI_PITCH + spiece * 16);
+              *reinterpret_cast<uint4*>(out + (rowbase + lq + r) * p.ld_out + ocol + opiece * 8) =
+                  lds128(slab + r * EPI_PITCH + opiece * 16);
           }
           __syncwarp();
         }
       } else if (p.out_mode == GEMM_OUT_F32_NCL) {
         float* out = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.N * p.L + (valid ? l : 0);
         constexpr int NCH = BN / 32;
-        for (int ch = half * (NCH / 2); ch < (half + 1) * (NCH / 2); ++ch) {
+#pragma unroll 1
+        for (int ch = part; ch < NCH; ch += 4) {
           const int c = ch * 32;
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
-          if (ch + 1 == (half + 1) * (NCH / 2)) {
+          if (ch + 4 >= NCH) {
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + c + j;
-              if (n < p.N) {
-                float v = __uint_as_float(r[j]);
-                if (p.bias) v += __ldg(p.bias + n);
-                out[static_cast<size_t>(n) * p.L] = v;  // lanes = consecutive l: coalesced
-              }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bq = lds128f(e.sbias + (n0 + c + 4 * j4) * 4);
+            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int n = n0 + c + 4 * j4 + h;
+              if (valid && n < p.N) out[static_cast<size_t>(n) * p.L] = __uint_as_float(r[4 * j4 + h]) + bb[h];
             }
           }
         }
       } else {
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.res);
         constexpr int NCH = BN / 32;
-        for (int ch = half * (NCH / 2); ch < (half + 1) * (NCH / 2); ++ch) {
-          const int c = ch * 32;
-          const int gcol = n0 + c;
-          const bool live = gcol < p.N;                   // padded output columns are neither read nor written
-          uint4 rv[4];
-          if (res && live) {                              // coalesced residual fetch, in flight during the TMEM load
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = i * 8 + srow;
-              rv[i] = (lq + r < p.L)
-                          ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + spiece * 8)
-                          : make_uint4(0, 0, 0, 0);
-            }
+        const size_t stat_chunk = (static_cast<size_t>(b) * p.tiles_per_batch + mt) * 4 + quad;
+        const bool has_res = p.res != nullptr, has_stats = p.stats != nullptr;
+        bool arrived = false;
+#pragma unroll 1
+        for (int ch = part; ch < NCH; ch += 4) {
+          const int gcol = n0 + ch * 32;
+          const bool last = ch + 4 >= NCH;
+          if (gcol >= p.N) continue;                      // padded output columns are neither read nor written
+          arrived |= last;
+          const uint32_t tc = taddr + ch * 32;
+          if (has_res) {
+            if (has_stats) epi_chunk_bf16<true, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
+            else           epi_chunk_bf16<true, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
+          } else {
+            if (has_stats) epi_chunk_bf16<false, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
+            else           epi_chunk_bf16<false, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
           }
-          uint32_t r[32];
-          tmem_ld32(taddr + c, r);
-          if (res && live) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(slab + (i * 8 + srow) * EPI_PITCH + spiece * 16) = rv[i];
-          }
-          tmem_ld_wait();
-          if (ch + 1 == (half + 1) * (NCH / 2)) {
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-          }
-          if (!live) continue;
-          __syncwarp();
-          uint4* mine = reinterpret_cast<uint4*>(slab + lane * EPI_PITCH);
-          uint32_t rr[16];
-          if (res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 t = mine[j];
-              rr[4 * j] = t.x; rr[4 * j + 1] = t.y; rr[4 * j + 2] = t.z; rr[4 * j + 3] = t.w;
-            }
-          }
-          uint32_t packed[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-            if (p.bias) {
-              v0 += __ldg(p.bias + gcol + j);
-              v1 += __ldg(p.bias + gcol + j + 1);
-            }
-            if (res) {
-              v0 += bf16_lo(rr[j >> 1]);
-              v1 += bf16_hi(rr[j >> 1]);
-            }
-            packed[j >> 1] = pack_bf16(v0, v1);
-          }
-          if (p.stats) {
-            // statistics of the STORED (bf16-rounded) values, per 16-channel block, over this warp's 32 rows
-            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float a = bf16_lo(packed[j]), c2 = bf16_hi(packed[j]);
-                s0 += a + c2; q0 += a * a + c2 * c2;
-                const float d = bf16_lo(packed[8 + j]), e = bf16_hi(packed[8 + j]);
-                s1 += d + e; q1 += d * d + e * e;
-              }
-            }
-            s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
-            if (lane == 0) {
-              const size_t chunk = (static_cast<size_t>(b) * p.tiles_per_batch + mt) * 4 + quad;
-              *reinterpret_cast<float4*>(p.stats + (chunk * p.stats_nblk + (gcol >> 4)) * 2) = make_float4(s0, q0, s1, q1);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            mine[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rrow = i * 8 + srow;
-            if (lq + rrow < p.L)
-              *reinterpret_cast<uint4*>(out + (rowbase + lq + rrow) * p.ld_out + gcol + spiece * 8) =
-                  *reinterpret_cast<const uint4*>(slab + rrow * EPI_PITCH + spiece * 16);
-          }
-          __syncwarp();
+        }
+        if (!arrived) {                                   // this warp's columns were all padding
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
       }
+      if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     tc_fence_before();
@@ -410,7 +467,7 @@ cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
     cudaError_t e = gemm_tc_init();
     if (e != cudaSuccess) return e;
   }
-  if (p.n_pad % 128 != 0 || p.nseg < 1 || p.nseg > GEMM_MAX_SEG) return cudaErrorInvalidValue;
+  if (p.n_pad % 128 != 0 || p.n_pad > MAX_NPAD || p.nseg < 1 || p.nseg > GEMM_MAX_SEG) return cudaErrorInvalidValue;
   if (p.out_mode == GEMM_OUT_GEGLU && p.n_pad % 128 != 0) return cudaErrorInvalidValue;
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
   if (bn == 256) {

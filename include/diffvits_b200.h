@@ -116,8 +116,10 @@ DV_API int dv_plan_tensor_info(const dv_plan* plan, int i, char* name, int name_
  * statistics, 2 GroupNorm apply, 3 LayerNorm, 4 attention) and its algorithmic FLOPs / HBM bytes per launch. */
 DV_API int dv_plan_op_count(const dv_plan* plan);
 DV_API int dv_plan_op_info(const dv_plan* plan, int i, char* tag, int tag_cap, int* kind, double* flops, double* bytes);
-/* One eager dv_unet_forward with a CUDA event between consecutive launches. SYNCHRONISES the stream (the only entry
- * point that does). ms[i] = device time of op i (i < op_count), ms[op_count] = prologue (layout change + time MLP). */
+/* One dv_unet_forward captured into a CUDA graph with an event-record node between consecutive launches and
+ * replayed twice; the second replay is reported. SYNCHRONISES the stream (the only entry point that does).
+ * ms[i] = device time of op i (i < op_count) incl. the gap to the next launch, ms[op_count] = prologue (layout
+ * change + time MLP). */
 DV_API int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride,
                                    float* out, float* ms, int cap, void* stream);
 
@@ -132,6 +134,12 @@ DV_API int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, i
 /* Test hooks for the next dv_gemm calls of this thread: force the N tile (128 / 256, 0 = heuristic) and let the
  * epilogue emit GroupNorm partials [B][ceil(L/128)*4][n/16][2] into `stats` (NULL = off). */
 DV_API void dv_gemm_test_options(int bn, float* stats);
+/* Debug: device buffer of >= 4001 uint64; CTA 0 of the next dv_gemm launches appends (role<<60 | tile<<44 | event<<40 |
+ * clock) records, buf[0] = count. roles: 0 TMA producer, 1 MMA issuer, 2 first epilogue warp. NULL = off. */
+DV_API void dv_gemm_test_trace(unsigned long long* buf);
+/* Debug: bit 0 skip the epilogue body, bit 1 skip the MMA issue, bit 2 skip the TMA loads (results are garbage;
+ * used to time the three pipelines of the kernel separately). */
+DV_API void dv_gemm_test_flags(int flags);
 /* F.scaled_dot_product_attention (attention_processor.py:1032); bf16 q/k/v/o with element strides. */
 DV_API int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
                  long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,

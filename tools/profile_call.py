@@ -56,7 +56,7 @@ def main():
     if a.out:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         open(a.out, "w").write(text + "\n")
-    print(f"# {desc}: eager call {sum(acc):.3f} ms over {len(ops)} launches")
+    print(f"# {desc}: graph-replayed call {sum(acc):.3f} ms over {len(ops)} launches")
     print(text)
 
 
