@@ -40,6 +40,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "r"(smem_u32(smem_ptr)));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams p) {
   constexpr int PITCH = D + 8;          // elements; +16 bytes
@@ -48,8 +54,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
   __shared__ __align__(16) __nv_bfloat16 sK[2][BKV * PITCH];
   __shared__ __align__(16) __nv_bfloat16 sV[2][BKV * PITCH];
 
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  pdl_wait();
   const int q0 = blockIdx.x * BQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -82,8 +90,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 
   constexpr float LOG2E = 1.4426950408889634f;
   const float sl2 = p.scale * LOG2E;
-  const float mask_bias = -10000.0f * LOG2E;
   const int kvlen = p.kv_len ? p.kv_len[b] : p.Lk;
+  const float mask_raw = -10000.0f / p.scale;          // the reference's additive -10000 bias, in raw-score units
+  const int kvalid = min(kvlen, p.Lk);                 // keys below this index need no masking
 
   uint32_t qf[D / 16][4];
   float o[D / 8][4];
@@ -127,30 +136,38 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
       }
     }
 
-    // ---- scale, mask, online softmax (rows g and g+8 of this warp's 16)
-    const int kbase = tile * BKV + 2 * t;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    // ---- online softmax on the raw scores (rows g and g+8 of this warp's 16). The softmax scale is folded into
+    // the exponent: p = 2^(s*c - m*c), c = scale*log2(e): one FFMA + one MUFU.EX2 per element. Masking work is only
+    // done for tiles that contain masked / out-of-range keys (warp-uniform test).
+    if (tile * BKV + BKV > kvalid) {
+      const int kbase = tile * BKV + 2 * t;
 #pragma unroll
-    for (int j = 0; j < BKV / 8; ++j) {
+      for (int j = 0; j < BKV / 8; ++j) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int key = kbase + j * 8 + e;
-        float add = 0.f;
-        if (key >= p.Lk) add = -INFINITY;
-        else if (key >= kvlen) add = mask_bias;
-        s[j][e] = s[j][e] * sl2 + add;
-        s[j][2 + e] = s[j][2 + e] * sl2 + add;
-        mx0 = fmaxf(mx0, s[j][e]);
-        mx1 = fmaxf(mx1, s[j][2 + e]);
+        for (int e = 0; e < 2; ++e) {
+          const int key = kbase + j * 8 + e;
+          float add = 0.f;
+          if (key >= p.Lk) add = -INFINITY;
+          else if (key >= kvlen) add = mask_raw;
+          s[j][e] += add;
+          s[j][2 + e] += add;
+        }
       }
+    }
+    float mx0 = fmaxf(s[0][0], s[0][1]), mx1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+    for (int j = 1; j < BKV / 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 key < Lk
-    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    const float c0 = ex2_approx((m0 - mn0) * sl2), c1 = ex2_approx((m1 - mn1) * sl2);
     m0 = mn0; m1 = mn1;
+    const float ms0 = mn0 * sl2, ms1 = mn1 * sl2;
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
@@ -158,8 +175,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
     uint32_t pf[BKV / 16][4];
 #pragma unroll
     for (int j = 0; j < BKV / 8; ++j) {
-      const float p0 = exp2f(s[j][0] - mn0), p1 = exp2f(s[j][1] - mn0);
-      const float p2 = exp2f(s[j][2] - mn1), p3 = exp2f(s[j][3] - mn1);
+      const float p0 = ex2_approx(fmaf(s[j][0], sl2, -ms0)), p1 = ex2_approx(fmaf(s[j][1], sl2, -ms0));
+      const float p2 = ex2_approx(fmaf(s[j][2], sl2, -ms1)), p3 = ex2_approx(fmaf(s[j][3], sl2, -ms1));
       l0 += p0 + p1;
       l1 += p2 + p3;
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
@@ -205,13 +222,12 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
   if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
   dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
   switch (p.D) {
-    case 16: attention_kernel<16><<<grid, ATT_THREADS, 0, st>>>(p); break;
-    case 32: attention_kernel<32><<<grid, ATT_THREADS, 0, st>>>(p); break;
-    case 48: attention_kernel<48><<<grid, ATT_THREADS, 0, st>>>(p); break;
-    case 64: attention_kernel<64><<<grid, ATT_THREADS, 0, st>>>(p); break;
+    case 16: return launch_k(attention_kernel<16>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 32: return launch_k(attention_kernel<32>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 48: return launch_k(attention_kernel<48>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 64: return launch_k(attention_kernel<64>, grid, dim3(ATT_THREADS), 0, st, p);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 }  // namespace dv

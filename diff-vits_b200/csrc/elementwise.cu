@@ -4,6 +4,8 @@
 //    (reference: unet1d/embeddings.py:24-64,157-201; unet_1d_condition.py:841-918; resnet.py:614-617),
 //  * the samplers' per-step multistep updates as single coalesced float4 passes
 //    (reference: sampler/dpm_solver.py:547-580, 796-852; sampler/uni_pc.py:471-588).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -13,6 +15,8 @@ namespace {
 // ------------------------------------------------------------------ layout
 __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                          int Csrc, int T, int ld_dst, int col0, int split, int shift) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -33,6 +37,8 @@ __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                           size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i4 + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i4);
@@ -46,57 +52,79 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ time embedding
-// One CTA per batch item: e = [cos(t f), sin(t f)] ; h = SiLU(W1 e + b1) ; emb = W2 h + b2 + aug ; out SiLU(emb).
-// w1/w2 are stored transposed ([in][out]) so consecutive threads read consecutive addresses.
+// temb_mlp: e = [cos(t f), sin(t f)] ; h = SiLU(W1 e + b1) ; emb = W2 h + b2   (embeddings.py:24-64, 192-197)
+// grid (16, nb): blockIdx.x owns 32 of the 512 outputs of the second Linear (the first Linear is recomputed by every
+// CTA: 64 K MACs), nb = 1 when all batch items share t (the sampling loop) else B. One warp per output row, lanes
+// stride the reduction axis so weight rows are read with 128-byte coalesced loads.
 __global__ void __launch_bounds__(512) temb_mlp_kernel(const TembParams p) {
+  pdl_launch_dependents();
   __shared__ float e[256];
   __shared__ float h[512];
-  const int b = blockIdx.x;
-  const int j = threadIdx.x;
-  const float t = p.t[static_cast<size_t>(b) * p.t_stride];
+  const int bi = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  const float t = p.t[static_cast<size_t>(bi) * p.t_stride];
   const int half = p.sin_dim / 2;
-  if (j < half) {
-    const float a = t * p.freqs[j];
-    e[j] = cosf(a);          // flip_sin_to_cos=True: cos half first
-    e[half + j] = sinf(a);
+  if (threadIdx.x < half) {
+    const float a = t * p.freqs[threadIdx.x];
+    e[threadIdx.x] = cosf(a);          // flip_sin_to_cos=True: cos half first
+    e[half + threadIdx.x] = sinf(a);
   }
   __syncthreads();
-  float acc = p.b1[j];
-  for (int k = 0; k < p.sin_dim; ++k) acc += p.w1[k * p.emb_dim + j] * e[k];
-  h[j] = silu_f(acc);
+  for (int o = warp; o < p.emb_dim; o += 16) {
+    float acc = 0.f;
+    for (int k = lane; k < p.sin_dim; k += 32) acc += __ldg(p.w1 + static_cast<size_t>(o) * p.sin_dim + k) * e[k];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) h[o] = silu_f(acc + p.b1[o]);
+  }
   __syncthreads();
-  float acc2 = p.b2[j];
-  for (int k = 0; k < p.emb_dim; ++k) acc2 += p.w2[k * p.emb_dim + j] * h[k];
-  if (p.aug) acc2 += p.aug[static_cast<size_t>(b) * p.emb_dim + j];
-  p.emb_act[static_cast<size_t>(b) * p.emb_dim + j] = silu_f(acc2);
+  for (int oo = warp; oo < 32; oo += 16) {
+    const int o = blockIdx.x * 32 + oo;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = lane; k < p.emb_dim; k += 32) acc += __ldg(p.w2 + static_cast<size_t>(o) * p.emb_dim + k) * h[k];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) p.emb_base[static_cast<size_t>(bi) * p.emb_dim + o] = acc + p.b2[o];
+  }
 }
 
-// ss_all[b, j] = b_all[j] + w_all[j, :] . emb_act[b, :]   (emb_dim = 512)
+// ss_all[b, j] = b_all[j] + sum_k w_all_t[k, j] * SiLU(emb_base[b] + aug[b])[k]       (resnet.py:614-617, all 22 at once)
+// CTA = 32 output columns j x 16 batch items: thread (j, 2 batch items); the transposed weight matrix makes the
+// per-k loads coalesced across the warp's 32 columns; activations are broadcast from shared memory.
 constexpr int TP_BCHUNK = 16;
-constexpr int TP_ROWS_PER_WARP = 4;
 __global__ void __launch_bounds__(256) temb_proj_kernel(const TembParams p) {
+  pdl_launch_dependents();
   __shared__ float es[TP_BCHUNK][512];
   const int b0 = blockIdx.y * TP_BCHUNK;
   const int nb = min(TP_BCHUNK, p.B - b0);
-  for (int i = threadIdx.x; i < nb * 512; i += 256) es[i / 512][i % 512] = p.emb_act[static_cast<size_t>(b0) * 512 + i];
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rr = 0; rr < TP_ROWS_PER_WARP; ++rr) {
-    const int j = (blockIdx.x * 8 + warp) * TP_ROWS_PER_WARP + rr;
-    if (j >= p.n_all) break;
-    float w[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) w[i] = __ldg(p.w_all + static_cast<size_t>(j) * 512 + lane + 32 * i);
-    const float bias = __ldg(p.b_all + j);
-    for (int bb = 0; bb < nb; ++bb) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc += w[i] * es[bb][lane + 32 * i];
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-      if (lane == 0) p.ss_all[static_cast<size_t>(b0 + bb) * p.n_all + j] = acc + bias;
+  pdl_wait();
+  for (int i = threadIdx.x; i < TP_BCHUNK * 512; i += 256) {
+    const int bb = i >> 9, k = i & 511;
+    float v = 0.f;
+    if (bb < nb) {
+      v = p.emb_base[static_cast<size_t>(p.t_stride ? (b0 + bb) : 0) * 512 + k];
+      if (p.aug) v += p.aug[static_cast<size_t>(b0 + bb) * 512 + k];
+      v = silu_f(v);
     }
+    es[bb][k] = v;
   }
+  __syncthreads();
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int bq = (threadIdx.x >> 5) * 2;
+  if (j >= p.n_all) return;
+  float a0 = 0.f, a1 = 0.f;
+  const float* w = p.w_all + j;
+#pragma unroll 8
+  for (int k = 0; k < 512; ++k) {
+    const float wv = __ldg(w + static_cast<size_t>(k) * p.n_all);
+    a0 = fmaf(wv, es[bq][k], a0);
+    a1 = fmaf(wv, es[bq + 1][k], a1);
+  }
+  const float bias = __ldg(p.b_all + j);
+  if (bq < nb) p.ss_all[static_cast<size_t>(b0 + bq) * p.n_all + j] = a0 + bias;
+  if (bq + 1 < nb) p.ss_all[static_cast<size_t>(b0 + bq + 1) * p.n_all + j] = a1 + bias;
 }
 
 // ------------------------------------------------------------------ sampler updates (fp32, float4)
@@ -112,6 +140,8 @@ __device__ __forceinline__ float roundtrip(float x, float m, float alp, float si
 __global__ void __launch_bounds__(256) axpbypcz_kernel(float* xo, const float* x, float* m1,
                                                        const float* __restrict__ m0, float a, float b, float c,
                                                        int rt, float alp, float sig, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -146,6 +176,8 @@ __global__ void __launch_bounds__(256) unipc_pred_kernel(float* xp, float* __res
                                                          const float* x, const float* __restrict__ m1,
                                                          const float* __restrict__ m0, float a, float b, float cp,
                                                          float cc, int has_m0, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -175,6 +207,8 @@ __global__ void __launch_bounds__(256) unipc_pred_kernel(float* xp, float* __res
 __global__ void __launch_bounds__(256) unipc_corr_kernel(float* __restrict__ x, const float* __restrict__ base,
                                                          const float* __restrict__ mt, const float* __restrict__ m1,
                                                          float d, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -197,41 +231,43 @@ inline int ew_grid(size_t n) {
 
 }  // namespace
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DV_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 cudaError_t launch_nct_to_ntc(const float* src, void* dst, int B, int Csrc, int T, int ld_dst, int col0, int split,
                               int shift, cudaStream_t st) {
   dim3 grid((T + 31) / 32, (Csrc + 31) / 32, B);
-  nct_to_ntc_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), Csrc, T, ld_dst, col0, split, shift);
-  return cudaGetLastError();
+  return launch_k(nct_to_ntc_kernel, grid, dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), Csrc, T, ld_dst, col0, split, shift);
 }
 cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
   const size_t blocks = (n / 4 + 256) / 256;
-  f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
-  return cudaGetLastError();
+  return launch_k(f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
 }
 cudaError_t launch_temb(const TembParams& p, cudaStream_t st) {
   if (p.emb_dim != 512 || p.sin_dim > 256 || p.sin_dim % 2) return cudaErrorInvalidValue;
-  temb_mlp_kernel<<<p.B, 512, 0, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(temb_mlp_kernel, dim3(16, p.t_stride ? p.B : 1), dim3(512), 0, st, p);
   if (e != cudaSuccess) return e;
-  dim3 grid((p.n_all + 8 * TP_ROWS_PER_WARP - 1) / (8 * TP_ROWS_PER_WARP), (p.B + TP_BCHUNK - 1) / TP_BCHUNK);
-  temb_proj_kernel<<<grid, 256, 0, st>>>(p);
-  return cudaGetLastError();
+  dim3 grid((p.n_all + 31) / 32, (p.B + TP_BCHUNK - 1) / TP_BCHUNK);
+  return launch_k(temb_proj_kernel, grid, dim3(256), 0, st, p);
 }
 
 cudaError_t launch_axpbypcz(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
                             int roundtrip_flag, float alp, float sig, size_t n, cudaStream_t st) {
-  axpbypcz_kernel<<<ew_grid(n), 256, 0, st>>>(x_out, x, m1, m0, a, b, c, roundtrip_flag, alp, sig, n);
-  return cudaGetLastError();
+  return launch_k(axpbypcz_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x_out, x, m1, m0, a, b, c, roundtrip_flag, alp, sig, n);
 }
 cudaError_t launch_unipc_pred(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a,
                               float b, float cp, float cc, int has_m0, size_t n, cudaStream_t st) {
-  unipc_pred_kernel<<<ew_grid(n), 256, 0, st>>>(xpred, base, x, m1, m0, a, b, cp, cc, has_m0, n);
-  return cudaGetLastError();
+  return launch_k(unipc_pred_kernel, dim3(ew_grid(n)), dim3(256), 0, st, xpred, base, x, m1, m0, a, b, cp, cc, has_m0, n);
 }
 cudaError_t launch_unipc_corr(float* x, const float* base, const float* mt, const float* m1, float d, size_t n,
                               cudaStream_t st) {
-  unipc_corr_kernel<<<ew_grid(n), 256, 0, st>>>(x, base, mt, m1, d, n);
-  return cudaGetLastError();
+  return launch_k(unipc_corr_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x, base, mt, m1, d, n);
 }
 
 }  // namespace dv

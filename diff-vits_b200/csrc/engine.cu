@@ -417,9 +417,9 @@ int Plan::build(std::string& err) {
 
   // ---- time embedding parameters (fp32; tiny GEMVs on CUDA cores)
   p_freqs = b.slot("time.freqs", "time_freqs", {}, "f32", {C0 / 2});
-  p_w1 = b.slot("time.w1t", "mat_t", {"time_embedding.linear_1.weight"}, "f32", {C0, emb_dim});
+  p_w1 = b.slot("time.w1", "rows", {"time_embedding.linear_1.weight"}, "f32", {emb_dim, C0});
   p_b1 = b.vec("time_embedding.linear_1.bias", emb_dim);
-  p_w2 = b.slot("time.w2t", "mat_t", {"time_embedding.linear_2.weight"}, "f32", {emb_dim, emb_dim});
+  p_w2 = b.slot("time.w2", "rows", {"time_embedding.linear_2.weight"}, "f32", {emb_dim, emb_dim});
   p_b2 = b.vec("time_embedding.linear_2.bias", emb_dim);
 
   // ---- the network (unet_1d_condition.py:943-1032)
@@ -476,7 +476,7 @@ int Plan::build(std::string& err) {
 
   // ---- stacked time_emb_proj
   n_all = b.ss_cur;
-  p_wall = b.slot("time.w_all", "rows", b.wall_keys, "f32", {n_all, emb_dim});
+  p_wall = b.slot("time.w_all_t", "rows_t", b.wall_keys, "f32", {emb_dim, n_all});
   p_ball = b.slot("time.b_all", "rows", b.ball_keys, "f32", {n_all});
   off_ss = b.ws_alloc(static_cast<size_t>(B) * n_all * 4);
   off_stats = b.ws_alloc(stats_bytes);
@@ -737,7 +737,7 @@ int Plan::forward(const float* sample, int x_only, const float* t, int t_stride,
   tp.w1 = reinterpret_cast<const float*>(params + p_w1); tp.b1 = reinterpret_cast<const float*>(params + p_b1);
   tp.w2 = reinterpret_cast<const float*>(params + p_w2); tp.b2 = reinterpret_cast<const float*>(params + p_b2);
   tp.aug = has_aug ? reinterpret_cast<const float*>(ws + off_aug) : nullptr;
-  tp.emb_act = reinterpret_cast<float*>(ws + off_embact);
+  tp.emb_base = reinterpret_cast<float*>(ws + off_embact);
   tp.w_all = reinterpret_cast<const float*>(params + p_wall); tp.b_all = reinterpret_cast<const float*>(params + p_ball);
   tp.ss_all = reinterpret_cast<float*>(ws + off_ss);
   tp.B = B; tp.n_all = n_all; tp.sin_dim = cfg.block_out_channels[0]; tp.emb_dim = emb_dim;

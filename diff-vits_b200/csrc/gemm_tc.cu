@@ -150,6 +150,7 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using SL = SmemLayout<BN>;
   constexpr int STAGES = SL::STAGES;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
@@ -188,6 +189,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only static data (weights, descriptors); activations of earlier kernels from here on
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -434,8 +437,7 @@ cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
   }
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, SL::DYN_BYTES, st>>>(p);
-  return cudaGetLastError();
+  return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), SL::DYN_BYTES, st, p);
 }
 
 }  // namespace

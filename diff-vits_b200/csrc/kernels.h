@@ -6,7 +6,24 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <utility>
+
 namespace dv {
+
+// Launch with the programmatic-stream-serialization attribute (PDL): consecutive kernels of the denoiser overlap
+// their prologue / launch latency with the previous kernel's tail. Disabled with DV_NO_PDL=1 in the environment.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ------------------------------------------------------------------ tap-GEMM (conv1d k3 / 1x1 / linear)
 // out[b, l, n] = epi( sum over K panels  A_seg[b, l + row_off, c0 + 64*p : +64] . W[n, k_run : +64] )
@@ -107,11 +124,11 @@ cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream
 struct TembParams {
   const float* t; int t_stride;          // model time per batch item (t_stride 0 = broadcast)
   const float* freqs;                    // [sin_dim/2] sinusoid frequencies exp(-ln(1e4) j / half)
-  const float* w1; const float* b1;      // [128,512] (transposed: [in][out]), [512]
-  const float* w2; const float* b2;      // [512,512] (transposed), [512]
+  const float* w1; const float* b1;      // [512,128] (nn.Linear layout [out][in]), [512]
+  const float* w2; const float* b2;      // [512,512], [512]
   const float* aug;                      // [B,512] addition embedding (or nullptr)
-  float* emb_act;                        // out [B,512] = SiLU(emb)
-  const float* w_all; const float* b_all;  // [n_all, 512], [n_all]  all time_emb_proj stacked
+  float* emb_base;                       // scratch [B or 1, 512]: time MLP output before the text embedding is added
+  const float* w_all; const float* b_all;  // [512, n_all] (all time_emb_proj stacked, TRANSPOSED), [n_all]
   float* ss_all;                         // out [B, n_all]
   int B, n_all, sin_dim, emb_dim;
 };

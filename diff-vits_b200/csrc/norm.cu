@@ -28,6 +28,8 @@ __device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, 
 
 // One CTA per (32-row chunk, batch item): partial sums per 16-channel block.
 __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p, float* __restrict__ scratch) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float ps[NT][2];
   const int C = p.c0 + p.c1;
   const int octs = C >> 3;
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p, float* _
 }
 
 __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_mean[32], s_rstd[32];
   const int C = p.c0 + p.c1;
   const int cpg = C / p.G;
@@ -150,6 +154,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int rows, float eps) {
   constexpr int C = CHUNKS * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -198,8 +204,7 @@ size_t gn_scratch_floats(int B, int L, int C) {
 cudaError_t launch_gn_stats(const GnParams& p, float* scratch, cudaStream_t st) {
   if (!gn_ok(p)) return cudaErrorInvalidValue;
   dim3 grid((p.L + 31) / 32, p.B);
-  gn_stats_kernel<<<grid, NT, 0, st>>>(p, scratch);
-  return cudaGetLastError();
+  return launch_k(gn_stats_kernel, grid, dim3(NT), 0, st, p, scratch);
 }
 cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
   if (!gn_ok(p) || p.nst < 1 || p.nst > 2) return cudaErrorInvalidValue;
@@ -208,8 +213,7 @@ cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
   int rows = (p.L + per_batch - 1) / per_batch;
   if (rows < 32) rows = 32;
   dim3 grid((p.L + rows - 1) / rows, p.B);
-  gn_apply_kernel<<<grid, NT, 0, st>>>(p, rows);
-  return cudaGetLastError();
+  return launch_k(gn_apply_kernel, grid, dim3(NT), 0, st, p, rows);
 }
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
                              float eps, cudaStream_t st) {
@@ -217,16 +221,15 @@ cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const
   __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
   dim3 grid((rows + 7) / 8);
   switch (C) {
-    case 128: layernorm_kernel<1><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
-    case 256: layernorm_kernel<2><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
-    case 384: layernorm_kernel<3><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
-    case 512: layernorm_kernel<4><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
-    case 640: layernorm_kernel<5><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
-    case 768: layernorm_kernel<6><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
-    case 1024: layernorm_kernel<8><<<grid, 256, 0, st>>>(xi, oo, gamma, beta, rows, eps); break;
+    case 128: return launch_k(layernorm_kernel<1>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    case 256: return launch_k(layernorm_kernel<2>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    case 384: return launch_k(layernorm_kernel<3>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    case 512: return launch_k(layernorm_kernel<4>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    case 640: return launch_k(layernorm_kernel<5>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    case 768: return launch_k(layernorm_kernel<6>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    case 1024: return launch_k(layernorm_kernel<8>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 }  // namespace dv

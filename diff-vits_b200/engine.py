@@ -104,6 +104,8 @@ def pack_slot(slot: dict, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
         out = w[0].t().contiguous()
     elif rec == "rows":
         out = torch.cat([v.reshape(v.shape[0], -1) for v in w], dim=0)
+    elif rec == "rows_t":
+        out = torch.cat([v.reshape(v.shape[0], -1) for v in w], dim=0).t().contiguous()
     else:
         raise ValueError(f"unknown packing recipe {rec!r}")
     out = out.contiguous()

@@ -47,7 +47,8 @@ def test_gemm_linear(U, B, L, K, N):
 @pytest.mark.parametrize("bn", [128, 256])
 def test_gemm_tile_width_and_groupnorm_partials(U, bn):
     """Both N-tile instantiations (persistent schedule over many tiles) + the epilogue's GroupNorm partial sums:
-    per (32-row chunk, 16-channel block) sum / sum of squares of the STORED bf16 values."""
+    per (32-row chunk, 16-channel block) sum / sum of squares of the fp32 accumulator values (the stored bf16 values
+    differ from them by rounding noise only, hence the 1e-3 gate against sums of the stored tensor)."""
     g = torch.Generator(device="cuda").manual_seed(21)
     B, L, K, N = 5, 1000, 384, 512            # 5 x 8 row tiles x 2-4 column tiles: several tiles per CTA... on 148 SMs
     a = _rand((B, L, K), g)
@@ -63,7 +64,7 @@ def test_gemm_tile_width_and_groupnorm_partials(U, bn):
     blk = y.reshape(B, rows // 32, 32, N // 16, 16)
     want = torch.stack([blk.sum(dim=(2, 4)), (blk * blk).sum(dim=(2, 4))], dim=-1)
     assert torch.isfinite(st).all()
-    assert U.rel_l2(st, want) < 1e-5
+    assert U.rel_l2(st, want) < 1e-3
     # many more tiles than SMs: every CTA loops (B=40 -> 320 row tiles x N/bn)
     B2 = 40
     a2 = _rand((B2, L, 128), g)
