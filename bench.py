@@ -185,15 +185,12 @@ def run_native(args):
     torch.manual_seed(1234)
     unet = UNet1DConditionModel(**UNET_KW).eval().to(dev)
     # noise / conditioning are drawn for the GLOBAL batch with one seed, then sharded (bit-identical to 1 GPU)
-    x_all, cond_all, ehs_all = inputs.make_inputs(Bg * world, T, Tp)
-    sl = slice(rank * Bg, (rank + 1) * Bg)
-    x_h, cond_h, ehs_h = (t[sl].contiguous().pin_memory() for t in (x_all, cond_all, ehs_all))
-    del x_all, cond_all, ehs_all
+    from diffvits_b200.dist import gather_latents, shard_inputs
+    x_h, cond_h, ehs_h = (t.pin_memory() for t in shard_inputs(inputs.make_inputs(Bg * world, T, Tp), rank, world))
     betas = inputs.betas_linear()
     x_d, cond_d, ehs_d = x_h.to(dev), cond_h.to(dev), ehs_h.to(dev)
     native = diffvits_b200.NativeDenoiser(unet, cond_d, ehs_d)
     eng = native.engine
-    gathered = torch.empty(world * Bg, 100, T, device=dev) if world > 1 else None
 
     def sync_all():
         if world > 1:
@@ -217,9 +214,7 @@ def run_native(args):
     def step_resident():
         lat = diffvits_b200.sample_native(unet, x_d, cond_d, ehs_d, sampler=sampler, steps=nfe, betas=betas,
                                           native=native)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, lat)
-        return lat
+        return gather_latents(lat, Bg * world)
 
     for _ in range(max(3, args.warmup)):
         step_resident()
@@ -244,9 +239,8 @@ def run_native(args):
         ed = ehs_h.to(dev, non_blocking=True)
         native.rebind(cd, ed)                                     # hoisted prompt work is part of the job
         lat = solver.sample(xd, steps=nfe, order=2, skip_type="time_uniform", method="multistep")
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, lat)
-        out_h.copy_(lat, non_blocking=True)
+        full = gather_latents(lat, Bg * world)
+        out_h.copy_(full[rank * Bg:(rank + 1) * Bg], non_blocking=True)
         torch.cuda.current_stream().synchronize()                 # the caller holds the latent on the host
         assert solver.last_run_native
 
