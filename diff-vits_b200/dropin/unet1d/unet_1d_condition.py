@@ -52,7 +52,70 @@ _FIXED = ("sample_size", "center_input_sample", "flip_sin_to_cos", "freq_shift",
           "cross_attention_norm", "mid_block_type")
 
 
+def _accelerated_config(cfg: dict) -> Optional[str]:
+    """None if the native engine implements this configuration, else the reason (mirrors Plan::build, csrc/engine.cu)."""
+    boc = tuple(cfg["block_out_channels"])
+    heads = cfg["attention_head_dim"]
+    if not isinstance(heads, int) or not isinstance(cfg["cross_attention_dim"], int):
+        return "per-level attention_head_dim / cross_attention_dim"
+    if boc[0] != 128:
+        return "block_out_channels[0] must be 128 (time_embed_dim 512)"
+    for c in boc:
+        if c % 64 or c > 1024 or c % heads or (c // heads) not in (16, 32, 48, 64):
+            return f"channel count {c} with {heads} heads (head dim must be 16/32/48/64, channels a multiple of 64)"
+        if cfg["norm_num_groups"] is None or c % (16 * cfg["norm_num_groups"]):
+            return "channels per GroupNorm group must be a multiple of 16"
+    if cfg["cross_attention_dim"] % 64 or cfg["out_channels"] > 128:
+        return "cross_attention_dim must be a multiple of 64 and out_channels <= 128"
+    return None
+
+
+def _reference_class():
+    """The reference's own UNet1DConditionModel, if a second `unet1d` package (the reference checkout) is on sys.path.
+    Used only for UNet instances OUTSIDE the accelerated configuration (model3.py builds small UNets for the duration
+    predictor and posterior encoder, :292, :493 - SURVEY section 8f 'next'), so that `import model3` keeps working with
+    the drop-in installed. The diffusion denoiser never takes this route."""
+    import importlib.util
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if "_dv_reference_unet1d" in sys.modules:
+        return sys.modules["_dv_reference_unet1d.unet_1d_condition"].UNet1DConditionModel
+    for entry in sys.path:
+        cand = os.path.join(entry or ".", "unet1d")
+        f = os.path.join(cand, "unet_1d_condition.py")
+        if os.path.isfile(f) and os.path.abspath(cand) != here:
+            spec = importlib.util.spec_from_file_location("_dv_reference_unet1d", os.path.join(cand, "__init__.py"),
+                                                          submodule_search_locations=[cand])
+            pkg = importlib.util.module_from_spec(spec)
+            sys.modules["_dv_reference_unet1d"] = pkg
+            spec.loader.exec_module(pkg)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                mod = importlib.import_module("_dv_reference_unet1d.unet_1d_condition")
+            return mod.UNet1DConditionModel
+    return None
+
+
 class UNet1DConditionModel(nn.Module):
+    def __new__(cls, *args, **kwargs):
+        if cls is UNet1DConditionModel:
+            cfg = dict(_CTOR_DEFAULTS)
+            cfg.update(dict(zip(list(_CTOR_DEFAULTS), args)))
+            cfg.update({k: v for k, v in kwargs.items() if k in _CTOR_DEFAULTS})
+            try:
+                reason = _accelerated_config(cfg)
+            except Exception:
+                reason = None            # malformed arguments: let __init__ raise the proper error
+            if reason is not None:
+                ref = _reference_class()
+                if ref is None:
+                    raise ValueError(f"UNet1DConditionModel configuration outside the B200-accelerated path ({reason}) "
+                                     "and no reference `unet1d` package on sys.path to delegate to")
+                return ref(*args, **kwargs)          # not an instance of cls: our __init__ is skipped
+        return super().__new__(cls)
+
     def __init__(self, *args, **kwargs):
         super().__init__()
         names = list(_CTOR_DEFAULTS)

@@ -259,6 +259,18 @@ def test_find_native_unwraps_reference_closure(dropin, seeded_unet):
     assert find_native(lambda x, t: x, {}) is None
 
 
+@pytest.mark.skipif(not os.path.isfile("/root/reference/model3.py"), reason="reference checkout not present (GPU box)")
+def test_reference_model3_builds_on_the_dropin():
+    """`import model3; NaturalSpeech2(cfg)` with the drop-in installed: the diffusion denoiser is the native class, the
+    duration predictor's small UNet (outside the accelerated configuration) is delegated to the reference class."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "helpers", "model3_dropin_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[-2] == "unet1d.unet_1d_condition"
+    assert "_dv_reference_unet1d.unet_1d_condition" in lines[-1] and "'unet1d.unet_1d_condition'" in lines[-1]
+
+
 def test_reference_arm_of_bench_runs_on_cpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
