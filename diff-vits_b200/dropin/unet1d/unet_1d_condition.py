@@ -100,7 +100,7 @@ def _reference_class():
 
 class UNet1DConditionModel(nn.Module):
     def __new__(cls, *args, **kwargs):
-        if cls is UNet1DConditionModel:
+        if cls is UNet1DConditionModel and not (set(kwargs) - set(_CTOR_DEFAULTS)):
             cfg = dict(_CTOR_DEFAULTS)
             cfg.update(dict(zip(list(_CTOR_DEFAULTS), args)))
             cfg.update({k: v for k, v in kwargs.items() if k in _CTOR_DEFAULTS})
