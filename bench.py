@@ -174,8 +174,8 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import diffvits_b200
-    from oracle import inputs
-    from oracle.ref_import import UNET_KW
+    from diffvits_b200 import synthetic as inputs       # the native arm never imports oracle/
+    from diffvits_b200.synthetic import UNET_KW
     diffvits_b200.install_dropin()
     import sampler.dpm_solver as dpm
     import sampler.uni_pc as uni

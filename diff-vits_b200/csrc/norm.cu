@@ -69,29 +69,60 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p, float* _
 
 __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows_per_cta) {
   pdl_launch_dependents();
-  pdl_wait();
   __shared__ float s_mean[32], s_rstd[32];
   const int C = p.c0 + p.c1;
   const int cpg = C / p.G;
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // ---- group statistics: one warp per group, lanes stride over the partials, fixed shuffle tree
+  const int octs = C >> 3;
+  const int R = NT / octs;
+  const int r = threadIdx.x / octs, o = threadIdx.x % octs;
+  const int cbase = o * 8;
+  // affine parameters are static data: fetch them before waiting on the producer kernel
+  float ga[8], be[8];
+  if (r < R) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + cbase + j));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + cbase + j));
+      ga[j] = g4.x; ga[j + 1] = g4.y; ga[j + 2] = g4.z; ga[j + 3] = g4.w;
+      be[j] = b4.x; be[j + 1] = b4.y; be[j + 2] = b4.z; be[j + 3] = b4.w;
+    }
+  }
+  pdl_wait();
+  // ---- group statistics: one warp per group; the (block, chunk, fold) index space is flattened over the lanes so
+  // every load of the warp is independent; fixed lane assignment + fixed shuffle tree: deterministic.
   for (int g = warp; g < p.G; g += NT / 32) {
     double sum = 0.0, sumsq = 0.0;
-    const int kb0 = (g * cpg) >> 4, kb1 = ((g + 1) * cpg) >> 4;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      int cov0 = 0, si = 0;
-      while (si + 1 < p.nst && (kb << 4) >= cov0 + p.st[si].cover) { cov0 += p.st[si].cover; ++si; }
+    const int kb0 = (g * cpg) >> 4, nkb = cpg >> 4;
+    // all blocks of a group come from at most two sources; walk them source by source
+    int cov0 = 0;
+    for (int si = 0; si < p.nst; ++si) {
       const GnStatSrc st = p.st[si];
-      const int kl = kb - (cov0 >> 4);
-      const int nf = st.fold ? 2 : 1;
-      const float* base = st.ptr + static_cast<size_t>(b) * st.chunks * st.nblk * 2;
-      for (int i = lane; i < st.chunks * nf; i += 32) {
-        const int ch = i / nf, f = i % nf;
-        const float2 v = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(ch) * st.nblk + kl + f * (st.nblk >> 1)) * 2));
-        sum += static_cast<double>(v.x);
-        sumsq += static_cast<double>(v.y);
+      const int lo = max(kb0, cov0 >> 4), hi = min(kb0 + nkb, (cov0 + st.cover) >> 4);
+      if (hi > lo) {
+        const int nf = st.fold ? 2 : 1;
+        const int per_blk = st.chunks * nf;
+        const int items = (hi - lo) * per_blk;
+        const float* base = st.ptr + static_cast<size_t>(b) * st.chunks * st.nblk * 2;
+        for (int i0 = 0; i0 < items; i0 += 128) {           // 4 independent loads per lane in flight
+          float2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            v[u] = make_float2(0.f, 0.f);
+            if (i < items) {
+              const int kl = lo - (cov0 >> 4) + i / per_blk;
+              const int rem = i % per_blk;
+              const int ch = rem / nf, f = rem % nf;
+              v[u] = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(ch) * st.nblk + kl + f * (st.nblk >> 1)) * 2));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { sum += static_cast<double>(v[u].x); sumsq += static_cast<double>(v[u].y); }
+        }
       }
+      cov0 += st.cover;
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -108,87 +139,120 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
     }
   }
   __syncthreads();
-  const int octs = C >> 3;
-  const int R = NT / octs;
+  if (r >= R) return;
   const int lbeg = blockIdx.x * rows_per_cta;
   const int lend = min(lbeg + rows_per_cta, p.L);
-  const int r = threadIdx.x / octs, o = threadIdx.x % octs;
-  if (r >= R) return;
-  const int cbase = o * 8;
   const int grp = cbase / cpg;
   const float mean = s_mean[grp], rstd = s_rstd[grp];
   float ca[8], cb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = cbase + j;
-    float a = rstd * __ldg(p.gamma + c);
-    float bb = __ldg(p.beta + c) - mean * a;
-    if (p.scale_shift) {
-      const float sc = 1.0f + __ldg(p.scale_shift + static_cast<size_t>(b) * p.ss_ld + c);
-      const float sh = __ldg(p.scale_shift + static_cast<size_t>(b) * p.ss_ld + C + c);
-      a *= sc;
-      bb = bb * sc + sh;
-    }
+    float a = rstd * ga[j];
+    float bb = be[j] - mean * a;
     ca[j] = a;
     cb[j] = bb;
   }
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  for (int l = lbeg + r; l < lend; l += R) {
-    const uint4 v = __ldg(gn_src(p, b, l, cbase));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t y[4];
+  if (p.scale_shift) {
+    const float* ssp = p.scale_shift + static_cast<size_t>(b) * p.ss_ld + cbase;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = bf16_lo(w[j]) * ca[2 * j] + cb[2 * j];
-      float c = bf16_hi(w[j]) * ca[2 * j + 1] + cb[2 * j + 1];
-      if (p.silu) { a = silu_f(a); c = silu_f(c); }
-      y[j] = pack_bf16(a, c);
+    for (int j = 0; j < 8; j += 4) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(ssp + j));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(ssp + C + j));
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float s1 = 1.0f + scv[k];
+        ca[j + k] *= s1;
+        cb[j + k] = cb[j + k] * s1 + shv[k];
+      }
     }
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * p.L + l) * C + cbase) = make_uint4(y[0], y[1], y[2], y[3]);
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  constexpr int UNR = 4;                                     // rows in flight per thread
+  for (int l0 = lbeg + r; l0 < lend; l0 += UNR * R) {
+    uint4 v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int l = l0 + u * R;
+      v[u] = l < lend ? __ldg(gn_src(p, b, l, cbase)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int l = l0 + u * R;
+      if (l >= lend) continue;
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint32_t y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = fmaf(bf16_lo(w[j]), ca[2 * j], cb[2 * j]);
+        float c = fmaf(bf16_hi(w[j]), ca[2 * j + 1], cb[2 * j + 1]);
+        if (p.silu) { a = silu_f(a); c = silu_f(c); }
+        y[j] = pack_bf16(a, c);
+      }
+      *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * p.L + l) * C + cbase) = make_uint4(y[0], y[1], y[2], y[3]);
+    }
   }
 }
 
-// One warp per row, row kept in registers (C <= 1024, multiple of 128): exact two-pass mean / variance.
+// One warp per row, row kept in registers (C <= 1024, multiple of 128): exact two-pass mean / variance. Each warp
+// works on LN_ROWS rows at a time with all of their loads issued up front (memory-level parallelism: at C = 128 a
+// row is only 8 bytes per lane).
+constexpr int LN_WARPS = 8;
 template <int CHUNKS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         int rows, float eps) {
   constexpr int C = CHUNKS * 128;
+  constexpr int LN_ROWS = CHUNKS <= 2 ? 4 : 2;
   pdl_launch_dependents();
-  pdl_wait();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const uint2* xr = reinterpret_cast<const uint2*>(x + static_cast<size_t>(row) * C);
-  float v[CHUNKS][4];
-  float s = 0.f;
+  float4 gm[CHUNKS], bt[CHUNKS];
 #pragma unroll
   for (int i = 0; i < CHUNKS; ++i) {
-    const uint2 w = __ldg(xr + lane + 32 * i);
-    v[i][0] = bf16_lo(w.x); v[i][1] = bf16_hi(w.x); v[i][2] = bf16_lo(w.y); v[i][3] = bf16_hi(w.y);
-    s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (lane + 32 * i) * 4));
+    bt[i] = __ldg(reinterpret_cast<const float4*>(beta + (lane + 32 * i) * 4));
+  }
+  pdl_wait();
+  const int row0 = (blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * LN_ROWS;
+  if (row0 >= rows) return;
+  uint2 w[LN_ROWS][CHUNKS];
+#pragma unroll
+  for (int rr = 0; rr < LN_ROWS; ++rr) {
+    const int row = min(row0 + rr, rows - 1);
+    const uint2* xr = reinterpret_cast<const uint2*>(x + static_cast<size_t>(row) * C);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) w[rr][i] = __ldg(xr + lane + 32 * i);
   }
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-  const float mean = s * (1.0f / C);
-  float q = 0.f;
+  for (int rr = 0; rr < LN_ROWS; ++rr) {
+    const int row = row0 + rr;
+    if (row >= rows) continue;
+    float v[CHUNKS][4];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < CHUNKS; ++i)
+    for (int i = 0; i < CHUNKS; ++i) {
+      v[i][0] = bf16_lo(w[rr][i].x); v[i][1] = bf16_hi(w[rr][i].x); v[i][2] = bf16_lo(w[rr][i].y); v[i][3] = bf16_hi(w[rr][i].y);
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) q += __shfl_xor_sync(0xffffffffu, q, m);
-  const float rstd = rsqrtf(q * (1.0f / C) + eps);
-  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C);
+    for (int i = 0; i < CHUNKS; ++i)
 #pragma unroll
-  for (int i = 0; i < CHUNKS; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
-    uint2 w;
-    w.x = pack_bf16((v[i][0] - mean) * rstd * gm.x + bt.x, (v[i][1] - mean) * rstd * gm.y + bt.y);
-    w.y = pack_bf16((v[i][2] - mean) * rstd * gm.z + bt.z, (v[i][3] - mean) * rstd * gm.w + bt.w);
-    orow[lane + 32 * i] = w;
+      for (int j = 0; j < 4; ++j) { const float d = v[i][j] - mean; q += d * d; }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) q += __shfl_xor_sync(0xffffffffu, q, m);
+    const float rstd = rsqrtf(q * (1.0f / C) + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C);
+#pragma unroll
+    for (int i = 0; i < CHUNKS; ++i) {
+      uint2 o;
+      o.x = pack_bf16((v[i][0] - mean) * rstd * gm[i].x + bt[i].x, (v[i][1] - mean) * rstd * gm[i].y + bt[i].y);
+      o.y = pack_bf16((v[i][2] - mean) * rstd * gm[i].z + bt[i].z, (v[i][3] - mean) * rstd * gm[i].w + bt[i].w);
+      orow[lane + 32 * i] = o;
+    }
   }
 }
 
@@ -208,10 +272,10 @@ cudaError_t launch_gn_stats(const GnParams& p, float* scratch, cudaStream_t st) 
 }
 cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
   if (!gn_ok(p) || p.nst < 1 || p.nst > 2) return cudaErrorInvalidValue;
-  // about two waves of CTAs on 148 SMs x 8 resident CTAs would be ideal; never fewer than 32 rows per CTA
-  int per_batch = (2 * 148 + p.B - 1) / p.B;
-  int rows = (p.L + per_batch - 1) / per_batch;
-  if (rows < 32) rows = 32;
+  // four rows in flight per thread: R = 256 / (C/8) rows per pass -> 4R rows per CTA (64 at C = 128, 8 at C = 1024)
+  const int C = p.c0 + p.c1;
+  int rows = 4 * (NT / (C >> 3));
+  if (rows < 4) rows = 4;
   dim3 grid((p.L + rows - 1) / rows, p.B);
   return launch_k(gn_apply_kernel, grid, dim3(NT), 0, st, p, rows);
 }
@@ -219,7 +283,8 @@ cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const
                              float eps, cudaStream_t st) {
   const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
-  dim3 grid((rows + 7) / 8);
+  const int rpc = LN_WARPS * (C <= 256 ? 4 : 2);   // rows per CTA, matches LN_ROWS in the kernel
+  dim3 grid((rows + rpc - 1) / rpc);
   switch (C) {
     case 128: return launch_k(layernorm_kernel<1>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
     case 256: return launch_k(layernorm_kernel<2>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);

@@ -1,27 +1,4 @@
 """ORACLE helper (test infrastructure): the seeded synthetic inputs every parity test, golden file and benchmark
-uses (weights seed 1234, inputs seed 0, N(0,1) fp32, linear betas 1e-4..2e-2 x 1000)."""
-from __future__ import annotations
-
-import torch
-
-
-def betas_linear(n: int = 1000) -> torch.Tensor:
-    """model3.py:935-942 linear_beta_schedule computed in fp64 then stored fp32 (:978-992)."""
-    scale = 1000 / n
-    return torch.linspace(scale * 0.0001, scale * 0.02, n, dtype=torch.float64).to(torch.float32)
-
-
-def make_inputs(B: int, T: int, Tp: int, seed: int = 0, x_ch: int = 100, cond_ch: int = 128, ehs_dim: int = 128):
-    g = torch.Generator().manual_seed(seed)
-    x_T = torch.randn(B, x_ch, T, generator=g)
-    cond = torch.randn(B, cond_ch, T, generator=g)
-    ehs = torch.randn(B, Tp, ehs_dim, generator=g)
-    return x_T, cond, ehs
-
-
-def ragged_mask(B: int, Tp: int, step: int = 100):
-    """lengths [Tp, Tp-step, Tp-2*step, ...] (>= 1) and the matching keep-mask; masked ehs rows must be zeroed by the
-    caller the way Diffusion_Encoder does (model3.py:905-906)."""
-    lens = torch.tensor([max(1, Tp - i * step) for i in range(B)], dtype=torch.int32)
-    mask = torch.arange(Tp)[None, :] < lens[:, None]
-    return lens, mask
+uses. Defined once in diffvits_b200.synthetic (the product may not import oracle/, the oracle may import the
+product's workload definition) and re-exported here."""
+from diffvits_b200.synthetic import betas_linear, make_inputs, ragged_mask  # noqa: F401

@@ -22,8 +22,8 @@ def main():
     ap.add_argument("--no-events", action="store_true")
     a = ap.parse_args()
     import diffvits_b200
-    from oracle import inputs
-    from oracle.ref_import import UNET_KW
+    from diffvits_b200 import synthetic as inputs
+    from diffvits_b200.synthetic import UNET_KW
     diffvits_b200.install_dropin()
     from unet1d.unet_1d_condition import UNet1DConditionModel
     Bg, T, Tp, sampler, nfe, desc = bench.WORKLOADS[a.workload]
