@@ -189,7 +189,7 @@ def run_native(args):
     x_h, cond_h, ehs_h = (t.pin_memory() for t in shard_inputs(inputs.make_inputs(Bg * world, T, Tp), rank, world))
     betas = inputs.betas_linear()
     x_d, cond_d, ehs_d = x_h.to(dev), cond_h.to(dev), ehs_h.to(dev)
-    native = diffvits_b200.NativeDenoiser(unet, cond_d, ehs_d)
+    native = diffvits_b200.NativeDenoiser(unet, cond_d, ehs_d, lanes=args.lanes)
     eng = native.engine
 
     def sync_all():
@@ -313,7 +313,8 @@ def run_native(args):
                        "weights": "random init seed 1234 (64.7 M params)", "inputs": "N(0,1) seed 0",
                        "l2": "no flush: per-step working set (workspace %.2f GB + weights 0.15 GB) >> 126 MB L2" %
                              (eng.ws_bytes / 1e9),
-                       "graph": "whole loop = one CUDA graph (%d kernel nodes)" % eng.last_sample_launches},
+                       "graph": "whole loop = one CUDA graph (%d kernel nodes, %d concurrent lanes of %s utterances)" %
+                                (eng.last_sample_launches, eng.lanes, "/".join(map(str, eng.sizes)))},
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "path": "pinned host x_T/cond/prompt -> H2D -> NativeDenoiser.rebind (prompt K/V, text-time emb) -> "
@@ -349,6 +350,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lanes", type=int, default=None,
+                    help="concurrent batch slices inside the loop graph (default: engine heuristic / DV_LANES)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "dv_set_cond": (_i, [_vp, _vp, _vp]),
     "dv_unet_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dv_sample": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp]),
+    "dv_sample_group": (_i, [C.POINTER(_vp), _i, _i, _i, C.POINTER(_f), C.POINTER(_f), C.POINTER(_vp), _i, _vp]),
     "dv_plan_tensor_count": (_i, [_vp]),
     "dv_plan_tensor_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),
     "dv_plan_op_count": (_i, [_vp]),

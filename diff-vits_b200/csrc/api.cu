@@ -97,6 +97,18 @@ int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const f
   int rc = plan->impl.sample(sampler, nsteps, t_in, coef, x, flags, S(stream), err);
   return rc == DV_OK ? rc : fail(rc, err);
 }
+int dv_sample_group(dv_plan* const* plans, int nplans, int sampler, int nsteps, const float* t_in, const float* coef,
+                    float* const* x, int flags, void* stream) {
+  if (!plans || nplans < 1 || nplans > 16) return fail(DV_ERR_INVALID, "bad lane group");
+  dv::Plan* ps[16];
+  for (int i = 0; i < nplans; ++i) {
+    if (!plans[i]) return fail(DV_ERR_INVALID, "null plan");
+    ps[i] = &plans[i]->impl;
+  }
+  std::string err;
+  int rc = dv::sample_group(ps, nplans, sampler, nsteps, t_in, coef, x, flags, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
 
 int dv_plan_tensor_count(const dv_plan* plan) { return plan ? static_cast<int>(plan->impl.named.size()) : 0; }
 int dv_plan_tensor_info(const dv_plan* plan, int i, char* name, int name_cap, size_t* offset, int* L, int* C) {

@@ -617,6 +617,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
   if (!bind_list(ops) || !bind_list(prep_ops)) return DV_ERR_CUDA;
   bound = true;
   prompt_ready = false;
+  ++graph_epoch;
   if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key = 0; }
   return DV_OK;
 }
@@ -670,6 +671,9 @@ int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_l
   if (!ehs) { err = "ehs is null"; return DV_ERR_INVALID; }
   const size_t n = static_cast<size_t>(B) * Tp * cfg.cross_attention_dim;
   DV_CK(launch_f32_to_bf16(ehs, ws + off_ehs, n, st));
+  // The captured loop reads the prompt-side tensors at fixed workspace addresses, so a new batch of the same shape
+  // keeps the graph; only a change of WHICH optional inputs exist (their pointers are baked into the launches) drops it.
+  const bool topo_changed = prompt_ready && (has_aug != (aug != nullptr) || has_kvlen != (kv_len != nullptr));
   has_aug = aug != nullptr;
   if (aug) DV_CK(cudaMemcpyAsync(ws + off_aug, aug, static_cast<size_t>(B) * emb_dim * 4, cudaMemcpyDeviceToDevice, st));
   has_kvlen = kv_len != nullptr;
@@ -677,7 +681,10 @@ int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_l
   int rc = enqueue_ops(prep_ops, nullptr, st, err, nullptr, nullptr);
   if (rc != DV_OK) return rc;
   prompt_ready = true;
-  if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key = 0; }
+  if (topo_changed) {
+    ++graph_epoch;
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; graph_key = 0; }
+  }
   return DV_OK;
 }
 
@@ -752,97 +759,147 @@ static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
   return h;
 }
 
-int Plan::sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
-                 std::string& err) {
-  if (!bound || !prompt_ready) { err = "plan not bound / prompt not prepared"; return DV_ERR_STATE; }
-  if (nsteps < 1 || nsteps > 4096) { err = "nsteps out of range"; return DV_ERR_INVALID; }
-  if (sampler != DV_SAMPLER_DPMPP_2M && sampler != DV_SAMPLER_UNIPC_BH2) { err = "unknown sampler"; return DV_ERR_INVALID; }
-  if (cfg.x_channels != cfg.out_channels) { err = "sampler needs x_channels == out_channels"; return DV_ERR_INVALID; }
-  if (!t_in || !coef || !x) { err = "null argument"; return DV_ERR_INVALID; }
+// One model evaluation per step (NFE == nsteps); history slots rotate by pointer at enqueue time.
+int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cudaStream_t s, int* launches,
+                       std::string& err) {
   const size_t n = static_cast<size_t>(B) * cfg.x_channels * T;
   float* X = reinterpret_cast<float*>(ws + off_x);
   float* XP = reinterpret_cast<float*>(ws + off_xp);
   float* BASE = reinterpret_cast<float*>(ws + off_base);
   float* H[2] = {reinterpret_cast<float*>(ws + off_h0), reinterpret_cast<float*>(ws + off_h1)};
   const float* ttab = reinterpret_cast<const float*>(ws + off_ttab);
-  const bool rt = (flags & DV_SAMPLE_ROUNDTRIP) != 0;
-
-  // One model evaluation per step (NFE == nsteps); history slots rotate by pointer at enqueue time.
-  auto body = [&](cudaStream_t s, int* launches) -> int {
-    int cur = 0;  // H[cur] = newest model output m_{-1}, H[cur^1] = m_{-2}
-    int rc = forward(X, 1, ttab, 0, H[cur], s, err, launches);
-    if (rc != DV_OK) return rc;
-    for (int i = 0; i < nsteps; ++i) {
-      const float* c = coef + static_cast<size_t>(i) * 8;
-      const bool last = (i == nsteps - 1);
-      if (sampler == DV_SAMPLER_DPMPP_2M) {
-        const bool has_prev = c[3] != 0.f;
-        DV_CK(launch_axpbypcz(X, X, H[cur], has_prev ? H[cur ^ 1] : nullptr, c[0], c[1], c[2], rt ? 1 : 0, c[4], c[5], n, s));
+  int cur = 0;  // H[cur] = newest model output m_{-1}, H[cur^1] = m_{-2}
+  int rc = forward(X, 1, ttab, 0, H[cur], s, err, launches);
+  if (rc != DV_OK) return rc;
+  for (int i = 0; i < nsteps; ++i) {
+    const float* c = coef + static_cast<size_t>(i) * 8;
+    const bool last = (i == nsteps - 1);
+    if (sampler == DV_SAMPLER_DPMPP_2M) {
+      const bool has_prev = c[3] != 0.f;
+      DV_CK(launch_axpbypcz(X, X, H[cur], has_prev ? H[cur ^ 1] : nullptr, c[0], c[1], c[2], rt ? 1 : 0, c[4], c[5], n, s));
+      ++*launches;
+      if (!last) {
+        cur ^= 1;
+        rc = forward(X, 1, ttab + i + 1, 0, H[cur], s, err, launches);
+        if (rc != DV_OK) return rc;
+      }
+    } else {
+      const bool has_prev = c[5] != 0.f, use_corr = c[6] != 0.f;
+      if (use_corr) {
+        if (last) { err = "UniPC table: corrector on the last step"; return DV_ERR_INVALID; }
+        DV_CK(launch_unipc_pred(XP, BASE, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
         ++*launches;
-        if (!last) {
-          cur ^= 1;
-          rc = forward(X, 1, ttab + i + 1, 0, H[cur], s, err, launches);
-          if (rc != DV_OK) return rc;
-        }
+        rc = forward(XP, 1, ttab + i + 1, 0, H[cur ^ 1], s, err, launches);  // m_t overwrites the consumed m_{-2}
+        if (rc != DV_OK) return rc;
+        DV_CK(launch_unipc_corr(X, BASE, H[cur ^ 1], H[cur], c[4], n, s));
+        ++*launches;
+        cur ^= 1;
       } else {
-        const bool has_prev = c[5] != 0.f, use_corr = c[6] != 0.f;
-        if (use_corr) {
-          if (last) { err = "UniPC table: corrector on the last step"; return DV_ERR_INVALID; }
-          DV_CK(launch_unipc_pred(XP, BASE, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
-          ++*launches;
-          rc = forward(XP, 1, ttab + i + 1, 0, H[cur ^ 1], s, err, launches);  // m_t overwrites the consumed m_{-2}
-          if (rc != DV_OK) return rc;
-          DV_CK(launch_unipc_corr(X, BASE, H[cur ^ 1], H[cur], c[4], n, s));
-          ++*launches;
-          cur ^= 1;
-        } else {
-          DV_CK(launch_unipc_pred(X, nullptr, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
-          ++*launches;
-        }
+        DV_CK(launch_unipc_pred(X, nullptr, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
+        ++*launches;
       }
     }
-    return DV_OK;
-  };
+  }
+  return DV_OK;
+}
 
-  DV_CK(cudaMemcpyAsync(ws + off_ttab, t_in, static_cast<size_t>(nsteps) * 4, cudaMemcpyHostToDevice, st));
-  DV_CK(cudaMemcpyAsync(X, x, n * 4, cudaMemcpyDeviceToDevice, st));
+int Plan::sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
+                 std::string& err) {
+  Plan* one[1] = {this};
+  float* xs[1] = {x};
+  return sample_group(one, 1, sampler, nsteps, t_in, coef, xs, flags, st, err);
+}
+
+// The whole loop of `n` plans ("lanes": disjoint slices of one batch of independent utterances, same T / Tp / sampler)
+// in ONE CUDA graph: lane i runs on its own captured stream forked from / joined to lane 0's, so the GPU overlaps one
+// lane's launch latencies, tails and MUFU-bound attention with the other lane's tensor-bound GEMMs. The graph is
+// cached on plans[0].
+int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float* t_in, const float* coef,
+                 float* const* x, int flags, cudaStream_t st, std::string& err) {
+  if (n < 1 || n > 16 || !plans || !x) { err = "bad lane group"; return DV_ERR_INVALID; }
+  if (nsteps < 1 || nsteps > 4096) { err = "nsteps out of range"; return DV_ERR_INVALID; }
+  if (sampler != DV_SAMPLER_DPMPP_2M && sampler != DV_SAMPLER_UNIPC_BH2) { err = "unknown sampler"; return DV_ERR_INVALID; }
+  if (!t_in || !coef) { err = "null argument"; return DV_ERR_INVALID; }
+  for (int i = 0; i < n; ++i) {
+    Plan* p = plans[i];
+    if (!p || !x[i]) { err = "null lane"; return DV_ERR_INVALID; }
+    if (!p->bound || !p->prompt_ready) { err = "plan not bound / prompt not prepared"; return DV_ERR_STATE; }
+    if (p->cfg.x_channels != p->cfg.out_channels) { err = "sampler needs x_channels == out_channels"; return DV_ERR_INVALID; }
+  }
+  const bool rt = (flags & DV_SAMPLE_ROUNDTRIP) != 0;
+  Plan* lead = plans[0];
+  for (int i = 0; i < n; ++i) {
+    Plan* p = plans[i];
+    const size_t nel = static_cast<size_t>(p->B) * p->cfg.x_channels * p->T;
+    DV_CK(cudaMemcpyAsync(p->ws + p->off_ttab, t_in, static_cast<size_t>(nsteps) * 4, cudaMemcpyHostToDevice, st));
+    DV_CK(cudaMemcpyAsync(p->ws + p->off_x, x[i], nel * 4, cudaMemcpyDeviceToDevice, st));
+  }
   if (flags & DV_SAMPLE_NO_GRAPH) {
     int launches = 0;
-    int rc = body(st, &launches);
-    if (rc != DV_OK) return rc;
-    last_sample_launches = launches;
+    for (int i = 0; i < n; ++i) {
+      int rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, st, &launches, err);
+      if (rc != DV_OK) return rc;
+    }
+    lead->last_sample_launches = launches;
   } else {
     uint64_t key = 1469598103934665603ull;
     key = fnv1a(key, &sampler, sizeof sampler);
     key = fnv1a(key, &nsteps, sizeof nsteps);
     key = fnv1a(key, &rt, sizeof rt);
     key = fnv1a(key, coef, static_cast<size_t>(nsteps) * 8 * 4);
-    if (!graph_exec || key != graph_key) {
-      if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
-      if (!cap_stream) DV_CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
-      DV_CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+    key = fnv1a(key, plans, static_cast<size_t>(n) * sizeof(Plan*));
+    for (int i = 0; i < n; ++i) key = fnv1a(key, &plans[i]->graph_epoch, sizeof(uint64_t));
+    if (!lead->graph_exec || key != lead->graph_key) {
+      if (lead->graph_exec) { cudaGraphExecDestroy(lead->graph_exec); lead->graph_exec = nullptr; }
+      for (int i = 0; i < n; ++i) {
+        Plan* p = plans[i];
+        if (!p->cap_stream) DV_CK(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+        if (!p->ev_fork) DV_CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        if (!p->ev_join) DV_CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+      }
+      cudaStream_t s0 = lead->cap_stream;
+      DV_CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
       int launches = 0;
-      int rc = body(cap_stream, &launches);
+      int rc = DV_OK;
+      cudaError_t ce = cudaSuccess;
+      if (n > 1) ce = cudaEventRecord(lead->ev_fork, s0);
+      for (int i = 1; i < n && ce == cudaSuccess; ++i) ce = cudaStreamWaitEvent(plans[i]->cap_stream, lead->ev_fork, 0);
+      for (int i = 0; i < n && rc == DV_OK && ce == cudaSuccess; ++i)
+        rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, plans[i]->cap_stream, &launches, err);
+      for (int i = 1; i < n && ce == cudaSuccess; ++i) {   // always join, also on failure, so the capture can end
+        ce = cudaEventRecord(plans[i]->ev_join, plans[i]->cap_stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s0, plans[i]->ev_join, 0);
+      }
       cudaGraph_t graph = nullptr;
-      cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+      cudaError_t ce2 = cudaStreamEndCapture(s0, &graph);
       if (rc != DV_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (ce != cudaSuccess) { err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); return DV_ERR_CUDA; }
-      ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+      if (ce != cudaSuccess || ce2 != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        err = std::string("graph capture: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ce2);
+        return DV_ERR_CUDA;
+      }
+      ce = cudaGraphInstantiate(&lead->graph_exec, graph, 0);
       cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) { graph_exec = nullptr; err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return DV_ERR_CUDA; }
-      graph_key = key;
-      graph_launches = launches;
+      if (ce != cudaSuccess) { lead->graph_exec = nullptr; err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return DV_ERR_CUDA; }
+      lead->graph_key = key;
+      lead->graph_launches = launches;
     }
-    DV_CK(cudaGraphLaunch(graph_exec, st));
-    last_sample_launches = graph_launches;
+    DV_CK(cudaGraphLaunch(lead->graph_exec, st));
+    lead->last_sample_launches = lead->graph_launches;
   }
-  DV_CK(cudaMemcpyAsync(x, X, n * 4, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < n; ++i) {
+    Plan* p = plans[i];
+    const size_t nel = static_cast<size_t>(p->B) * p->cfg.x_channels * p->T;
+    DV_CK(cudaMemcpyAsync(x[i], p->ws + p->off_x, nel * 4, cudaMemcpyDeviceToDevice, st));
+  }
   return DV_OK;
 }
 
 Plan::~Plan() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (cap_stream) cudaStreamDestroy(cap_stream);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 
 }  // namespace dv

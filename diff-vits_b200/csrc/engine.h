@@ -86,7 +86,9 @@ struct Plan {
   // graph cache for dv_sample
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t cap_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // lane fork / join inside a captured group loop
   uint64_t graph_key = 0;
+  uint64_t graph_epoch = 0;   // bumped whenever launches baked into a captured graph become stale
   int graph_launches = 0;
 
   int build(std::string& err);
@@ -102,8 +104,14 @@ struct Plan {
                       float* ms, int cap, std::string& err);
   int sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
              std::string& err);
+  // the N-step loop (denoiser calls + sampler updates) of this plan, enqueued on `s` (no copies, no graph handling)
+  int enqueue_loop(int sampler, int nsteps, const float* coef, bool roundtrip, cudaStream_t s, int* launches,
+                   std::string& err);
   ~Plan();
 };
+
+int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float* t_in, const float* coef,
+                 float* const* x, int flags, cudaStream_t st, std::string& err);
 
 bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
                   std::string& err);

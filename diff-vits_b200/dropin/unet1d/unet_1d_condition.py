@@ -100,7 +100,8 @@ def _reference_class():
 
 class UNet1DConditionModel(nn.Module):
     def __new__(cls, *args, **kwargs):
-        if cls is UNet1DConditionModel and not (set(kwargs) - set(_CTOR_DEFAULTS)):
+        # copy.deepcopy / pickle re-create instances through cls.__new__(cls) without arguments: never delegate then
+        if cls is UNet1DConditionModel and (args or kwargs) and not (set(kwargs) - set(_CTOR_DEFAULTS)):
             cfg = dict(_CTOR_DEFAULTS)
             cfg.update(dict(zip(list(_CTOR_DEFAULTS), args)))
             cfg.update({k: v for k, v in kwargs.items() if k in _CTOR_DEFAULTS})
@@ -225,12 +226,13 @@ class UNet1DConditionModel(nn.Module):
     def _weights_version(self) -> Tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def native_engine(self, B: int, T: int, Tp: int, x_channels: Optional[int] = None, private: bool = False):
+    def native_engine(self, B: int, T: int, Tp: int, x_channels: Optional[int] = None, private: bool = False,
+                      lanes: Optional[int] = None):
         """The (cached) native plan for this shape on the module's device. Weights are packed once per module and
         shared by all of its plans; they are re-packed when any parameter changed (load_state_dict, .to(...)).
         `private=True` returns a fresh plan (own workspace, prompt and cond state) that is not shared with
         `forward()` or other callers."""
-        from diffvits_b200.engine import DenoiserEngine, require_cuda
+        from diffvits_b200.engine import DenoiserGroup, require_cuda
         device = require_cuda(self.device)
         if self.dtype != torch.float32:
             raise RuntimeError("keep UNet1DConditionModel parameters in fp32; the engine packs BF16 operands itself")
@@ -238,11 +240,11 @@ class UNet1DConditionModel(nn.Module):
         if self._params_cache is not None and self._params_cache[0] != ver:
             self._params_cache = None
             self._engines.clear()          # plans hold pointers into the old blob
-        key = (B, T, Tp, x_channels)
+        key = (B, T, Tp, x_channels, lanes)
         eng = None if private else self._engines.get(key)
         if eng is None:
             blob = None if self._params_cache is None else self._params_cache[1]
-            eng = DenoiserEngine(self, B, T, Tp, device, x_channels=x_channels, params=blob)
+            eng = DenoiserGroup(self, B, T, Tp, device, x_channels=x_channels, params=blob, lanes=lanes)
             if self._params_cache is None:
                 self._params_cache = (ver, eng.params)
             if not private:

@@ -307,3 +307,102 @@ class DenoiserEngine:
     @property
     def last_sample_launches(self) -> int:
         return self.lib.dv_plan_last_sample_launches(self._plan)
+
+
+# ------------------------------------------------------------------------------------------------ lanes
+def default_lanes(B: int) -> int:
+    """How many independent batch slices ("lanes") the whole-loop graph runs on concurrent streams. Utterances never
+    interact on this path, so a batch can be cut anywhere; two lanes let one lane's launch gaps / kernel tails /
+    MUFU-bound attention overlap the other lane's tensor-bound GEMMs. DV_LANES overrides."""
+    import os
+    env = os.environ.get("DV_LANES")
+    if env:
+        return max(1, min(int(env), B))
+    return 2 if B >= 8 else 1
+
+
+class DenoiserGroup:
+    """`lanes` DenoiserEngine plans over disjoint slices of one batch, sharing one packed parameter blob. Same
+    interface as DenoiserEngine; `sample` captures all lanes into one CUDA graph (dv_sample_group)."""
+
+    def __init__(self, unet: torch.nn.Module, B: int, T: int, Tp: int, device, x_channels: Optional[int] = None,
+                 params: Optional[torch.Tensor] = None, lanes: Optional[int] = None):
+        lanes = default_lanes(B) if lanes is None else max(1, min(int(lanes), B))
+        base, extra = divmod(B, lanes)
+        self.sizes = [base + (1 if i < extra else 0) for i in range(lanes)]
+        self.bounds = [0]
+        for n in self.sizes:
+            self.bounds.append(self.bounds[-1] + n)
+        self.engines: List[DenoiserEngine] = []
+        for n in self.sizes:
+            eng = DenoiserEngine(unet, n, T, Tp, device, x_channels=x_channels, params=params)
+            params = eng.params
+            self.engines.append(eng)
+        e0 = self.engines[0]
+        self.lib, self.device, self.params, self.cfg = e0.lib, e0.device, e0.params, e0.cfg
+        self.B, self.T, self.Tp = int(B), int(T), int(Tp)
+        self.x_channels, self.in_channels, self.out_channels = e0.x_channels, e0.in_channels, e0.out_channels
+        self.manifest, self.param_bytes = e0.manifest, e0.param_bytes
+        self.ws_bytes = sum(e.ws_bytes for e in self.engines)
+        self.launches_per_forward = sum(e.launches_per_forward for e in self.engines)
+
+    @property
+    def lanes(self) -> int:
+        return len(self.engines)
+
+    def _slices(self, t: Optional[torch.Tensor]):
+        if t is None:
+            return [None] * self.lanes
+        return [t[self.bounds[i]: self.bounds[i + 1]] for i in range(self.lanes)]
+
+    def prepare_prompt(self, ehs, kv_len=None, aug=None) -> None:
+        assert ehs.shape[0] == self.B
+        for e, a, b, c in zip(self.engines, self._slices(ehs), self._slices(kv_len), self._slices(aug)):
+            e.prepare_prompt(a, b, c)
+
+    def set_cond(self, cond) -> None:
+        assert cond.shape[0] == self.B
+        for e, c in zip(self.engines, self._slices(cond)):
+            e.set_cond(c)
+
+    def forward(self, sample, t, x_only: bool = False, out=None):
+        assert sample.shape[0] == self.B
+        t = t.reshape(-1)
+        if out is None:
+            out = torch.empty(self.B, self.out_channels, self.T, dtype=torch.float32, device=self.device)
+        ts = self._slices(t) if t.numel() == self.B else [t] * self.lanes
+        for e, s, tt, o in zip(self.engines, self._slices(sample), ts, self._slices(out)):
+            e.forward(s, tt, x_only=x_only, out=o)
+        return out
+
+    def sample(self, sampler: int, t_in, coef, x, graph: bool = True, roundtrip: bool = False):
+        assert x.shape == (self.B, self.x_channels, self.T) and x.dtype == torch.float32 and x.is_contiguous()
+        assert x.device == self.device
+        t_host = t_in.detach().to("cpu", torch.float32).contiguous()
+        c_host = coef.detach().to("cpu", torch.float32).contiguous()
+        nsteps = t_host.numel()
+        assert c_host.shape == (nsteps, 8)
+        flags = (0 if graph else SAMPLE_NO_GRAPH) | (SAMPLE_ROUNDTRIP if roundtrip else 0)
+        fp = C.POINTER(C.c_float)
+        n = self.lanes
+        plans = (C.c_void_p * n)(*[e._plan for e in self.engines])
+        xs = (C.c_void_p * n)(*[C.c_void_p(s.data_ptr()) for s in self._slices(x)])
+        check(self.lib.dv_sample_group(plans, n, sampler, nsteps, C.cast(t_host.data_ptr(), fp),
+                                       C.cast(c_host.data_ptr(), fp), xs, flags, _stream(self.device)))
+        return x
+
+    def named_tensors(self) -> Dict[str, torch.Tensor]:
+        outs = [e.named_tensors() for e in self.engines]
+        return {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
+
+    # measurement support: per-launch figures are those of lane 0 (the kernels as they run in the product)
+    def op_table(self):
+        return self.engines[0].op_table()
+
+    def profile_forward(self, sample, t, x_only: bool = True):
+        return self.engines[0].profile_forward(sample[: self.sizes[0]], t if t.numel() != self.B else t[: self.sizes[0]],
+                                               x_only=x_only)
+
+    @property
+    def last_sample_launches(self) -> int:
+        return self.engines[0].last_sample_launches

@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-from .engine import SAMPLER_DPMPP_2M, SAMPLER_UNIPC_BH2, DenoiserEngine
+from .engine import SAMPLER_DPMPP_2M, SAMPLER_UNIPC_BH2, DenoiserGroup
 from .schedule import (NoiseScheduleVP, dpmpp_multistep_table, get_time_steps, unipc_multistep_table)
 
 
@@ -24,12 +24,13 @@ class NativeDenoiser:
     """
 
     def __init__(self, unet, cond: torch.Tensor, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None,
-                 aug: Optional[torch.Tensor] = None):
+                 aug: Optional[torch.Tensor] = None, lanes: Optional[int] = None):
         B, Cc, T = cond.shape
         Tp = ehs.shape[1]
         self.unet = unet
         self.x_channels = unet.config["in_channels"] - Cc
-        self.engine: DenoiserEngine = unet.native_engine(B, T, Tp, x_channels=self.x_channels, private=True)
+        self.engine: DenoiserGroup = unet.native_engine(B, T, Tp, x_channels=self.x_channels, private=True,
+                                                        lanes=lanes)
         self.calls = 0
         self.rebind(cond, ehs, kv_len, aug)
 

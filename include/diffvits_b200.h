@@ -104,7 +104,13 @@ DV_API int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const
 #define DV_SAMPLE_ROUNDTRIP 2    /* DPM++ only: reproduce the reference's x0->eps->x0 round trip bit for bit */
 DV_API int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags,
               void* stream);
-/* Kernel launches enqueued by the most recent dv_sample on this plan. */
+/* The same loop for `nplans` plans at once ("lanes": disjoint slices of one batch of independent utterances - the path
+ * has no cross-sample reduction - with the same T, Tp, sampler and tables). All lanes are captured into ONE graph,
+ * lane i on its own stream forked from lane 0's, so launch latencies and kernel tails of one lane overlap with the
+ * other lanes' kernels. x[i]: device NCT [B_i, x_channels, T] of lane i. The graph is cached on plans[0]. */
+DV_API int dv_sample_group(dv_plan* const* plans, int nplans, int sampler, int nsteps, const float* t_in,
+                           const float* coef, float* const* x, int flags, void* stream);
+/* Kernel launches enqueued by the most recent dv_sample / dv_sample_group (reported on plans[0]). */
 DV_API int dv_plan_last_sample_launches(const dv_plan* plan);
 
 /* ---- measurement support ------------------------------------------------------------------------------------- */

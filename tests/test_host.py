@@ -230,6 +230,17 @@ def test_unet_shell_api(dropin, seeded_unet):
                                     "cross_attention_dim", "attention_head_dim", "addition_embed_type",
                                     "resnet_time_scale_shift")})
     assert m2.load_state_dict(seeded_unet.state_dict()).missing_keys == []
+    # copy.deepcopy re-creates the module through __new__ without arguments: must not try to delegate to a reference
+    # checkout (there is none on the GPU box)
+    import copy
+    import sys
+    saved = list(sys.path)
+    try:
+        sys.path[:] = [e for e in sys.path if "reference" not in e]
+        m3 = copy.deepcopy(seeded_unet)
+    finally:
+        sys.path[:] = saved
+    assert type(m3) is U.UNet1DConditionModel and m3.config == seeded_unet.config
 
 
 def test_find_native_unwraps_reference_closure(dropin, seeded_unet):
