@@ -28,7 +28,7 @@ WORKLOADS = {
     "c3": (32, 1000, 282, "unipc", 10, "C3: batch 32 x 1000 frames, Tp=282, 10-step UniPC bh2 with prompt cross-attention"),
     "c5": (8, 4000, 282, "unipc", 25, "C5: long-form batch 8 x 4000 frames, Tp=282, 25-step UniPC bh2"),
 }
-KIND_NAMES = {0: "gemm_tc", 1: "gn_stats", 2: "gn_apply", 3: "layernorm", 4: "attention"}
+KIND_NAMES = {0: "gemm_tc", 1: "gn_stats", 2: "gn_apply", 3: "layernorm", 4: "attention", 5: "chain_tc"}
 
 
 def denoiser_flops(T: int, Tp: int) -> float:

@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -254,6 +255,7 @@ struct Builder {
   }
 
   TRef transformer(const std::string& pfx, TRef y) {
+    if (P.fuse && y.C % 128 == 0 && y.C <= 384 && y.C <= P.fuse_max_c) return transformer_fused(pfx, y);
     scratch_reset();
     const int L = y.L, C = y.C, H = P.cfg.num_heads, D = C / H;
     const std::string tb = pfx + ".transformer_blocks.0";
@@ -319,6 +321,116 @@ struct Builder {
     TRef yo = act(L, C);
     linear(P.ops, pfx + ".proj_out", z, "linear", {pfx + ".proj_out.weight"}, pfx + ".proj_out.bias", C, y, yo,
            GEMM_OUT_BF16, true);
+    P.named.emplace_back(pfx, yo);
+    return yo;
+  }
+
+  // ---- the same block as chained-GEMM launches (csrc/chain_tc.cu): 6 launches instead of 15
+  //   A : proj_in -> z ; LN1 ; qkv                      B1: to_out(attn1) + z -> z ; LN2 ; to_q
+  //   B2: to_out(attn2) + z -> z ; LN3 ; GEGLU ; ff.out + z ; proj_out + y -> block output (+GroupNorm partials)
+  Op& emit_chain(const std::string& tag, int L, int C) {
+    Op o;
+    o.kind = OP_CHAIN; o.tag = tag;
+    o.ch.L = L; o.ch.C = C;
+    P.ops.push_back(o);
+    return P.ops.back();
+  }
+  void set_w(ChainStageDesc& sd, const std::string& tag, const std::string& recipe, std::vector<std::string> keys,
+             const std::string& bias_key, int n, int k, bool second = false) {
+    const long long wo = slot(tag + ".W", recipe, std::move(keys), "bf16", {n, k});
+    long long bo = -1;
+    if (!bias_key.empty()) bo = slot(tag + ".b", recipe == "geglu" ? "geglu_vec" : "vec", {bias_key}, "f32", {n});
+    if (second) { sd.w2_off = wo; sd.w2_rows = n; sd.w2_k = k; sd.bias2_off = bo; }
+    else { sd.w_off = wo; sd.w_rows = n; sd.w_k = k; sd.bias_off = bo; }
+  }
+  void set_ln(ChainStageDesc& sd, const std::string& key, int C) {
+    sd.gamma = vec(key + ".weight", C);
+    sd.beta = vec(key + ".bias", C);
+    sd.eps = 1e-5f;
+  }
+
+  TRef transformer_fused(const std::string& pfx, TRef y) {
+    scratch_reset();
+    const int L = y.L, C = y.C, H = P.cfg.num_heads, D = C / H;
+    const std::string tb = pfx + ".transformer_blocks.0";
+    TRef g = tmp(L, C);
+    emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
+    TRef z = tmp(L, C);
+    TRef qkv = tmp(L, 3 * C);
+    TRef ao = tmp(L, C);
+    {
+      Op& o = emit_chain(pfx + ".chain_a", L, C);
+      ChainDesc& c = o.ch;
+      c.nstages = 2;
+      c.st[0].kind = CH_ROW; c.st[0].a = g; c.st[0].out = z;
+      set_w(c.st[0], pfx + ".proj_in", "linear", {pfx + ".proj_in.weight"}, pfx + ".proj_in.bias", C, C);
+      set_ln(c.st[0], tb + ".norm1", C);
+      c.st[1].kind = CH_STREAM; c.st[1].n = 3 * C; c.st[1].out = qkv;
+      set_w(c.st[1], tb + ".attn1.qkv", "linear",
+            {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, "", 3 * C, C);
+    }
+    {
+      Op o;
+      o.kind = OP_ATTN; o.tag = tb + ".attn1";
+      memset(&o.at, 0, sizeof o.at);
+      o.ato.q = qkv.off; o.ato.k = qkv.off + static_cast<size_t>(C) * 2; o.ato.v = qkv.off + static_cast<size_t>(C) * 4;
+      o.ato.o = ao.off; o.ato.cross = false;
+      o.at.ld_q = o.at.ld_k = o.at.ld_v = 3 * C; o.at.ld_o = C;
+      o.at.bs_q = o.at.bs_k = o.at.bs_v = static_cast<long long>(L) * 3 * C; o.at.bs_o = static_cast<long long>(L) * C;
+      o.at.B = P.B; o.at.H = H; o.at.Lq = L; o.at.Lk = L; o.at.D = D;
+      o.at.scale = 1.0f / sqrtf(static_cast<float>(D));
+      P.ops.push_back(o);
+    }
+    TRef kv;
+    kv.L = P.Tp; kv.C = 2 * C;
+    kv.off = ws_alloc(static_cast<size_t>(P.B) * P.Tp * 2 * C * 2);
+    linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
+           2 * C, TRef(), kv, GEMM_OUT_BF16);
+    TRef q = qkv;  // the first [L, C] worth of the qkv scratch, dense
+    q.C = C;
+    {
+      Op& o = emit_chain(pfx + ".chain_b1", L, C);
+      ChainDesc& c = o.ch;
+      c.nstages = 2;
+      c.st[0].kind = CH_ROW; c.st[0].a = ao; c.st[0].res = z; c.st[0].out = z;
+      set_w(c.st[0], tb + ".attn1.to_out", "linear", {tb + ".attn1.to_out.0.weight"}, tb + ".attn1.to_out.0.bias", C, C);
+      set_ln(c.st[0], tb + ".norm2", C);
+      c.st[1].kind = CH_STREAM; c.st[1].n = C; c.st[1].out = q;
+      set_w(c.st[1], tb + ".attn2.to_q", "linear", {tb + ".attn2.to_q.weight"}, "", C, C);
+    }
+    {
+      Op o;
+      o.kind = OP_ATTN; o.tag = tb + ".attn2";
+      memset(&o.at, 0, sizeof o.at);
+      o.ato.q = q.off; o.ato.k = kv.off; o.ato.v = kv.off + static_cast<size_t>(C) * 2; o.ato.o = ao.off;
+      o.ato.cross = true;
+      o.at.ld_q = C; o.at.ld_k = o.at.ld_v = 2 * C; o.at.ld_o = C;
+      o.at.bs_q = static_cast<long long>(L) * C; o.at.bs_k = o.at.bs_v = static_cast<long long>(P.Tp) * 2 * C;
+      o.at.bs_o = static_cast<long long>(L) * C;
+      o.at.B = P.B; o.at.H = H; o.at.Lq = L; o.at.Lk = P.Tp; o.at.D = D;
+      o.at.scale = 1.0f / sqrtf(static_cast<float>(D));
+      P.ops.push_back(o);
+    }
+    TRef yo = act(L, C);
+    {
+      Op& o = emit_chain(pfx + ".chain_b2", L, C);
+      ChainDesc& c = o.ch;
+      c.nstages = 3;
+      c.st[0].kind = CH_ROW; c.st[0].a = ao; c.st[0].res = z; c.st[0].out = z;
+      set_w(c.st[0], tb + ".attn2.to_out", "linear", {tb + ".attn2.to_out.0.weight"}, tb + ".attn2.to_out.0.bias", C, C);
+      set_ln(c.st[0], tb + ".norm3", C);
+      c.st[1].kind = CH_FF; c.st[1].n = 4 * C; c.st[1].res = z;
+      set_w(c.st[1], tb + ".ff.geglu", "geglu", {tb + ".ff.net.0.proj.weight"}, tb + ".ff.net.0.proj.bias", 8 * C, C);
+      set_w(c.st[1], tb + ".ff.out", "linear", {tb + ".ff.net.2.weight"}, tb + ".ff.net.2.bias", C, 4 * C, true);
+      c.st[2].kind = CH_STREAM; c.st[2].n = C; c.st[2].res = y; c.st[2].out = yo;
+      set_w(c.st[2], pfx + ".proj_out", "linear", {pfx + ".proj_out.weight"}, pfx + ".proj_out.bias", C, C);
+      // GroupNorm partials of the block output, same layout as a GEMM epilogue's
+      const int chunks = ((L + 127) / 128) * 4;
+      c.st[2].stats_off = static_cast<long long>(P.stats_bytes);
+      c.st[2].stats_nblk = C / 16;
+      P.stats_bytes += align_up(static_cast<size_t>(P.B) * chunks * (C / 16) * 2 * sizeof(float), 256);
+      yo.st_off = c.st[2].stats_off; yo.st_chunks = chunks; yo.st_nblk = C / 16; yo.st_fold = 0;
+    }
     P.named.emplace_back(pfx, yo);
     return yo;
   }
@@ -395,6 +507,12 @@ int Plan::build(std::string& err) {
   if (emb_dim != 512) { err = "time_embed_dim must be 512 (block_out_channels[0] == 128)"; return DV_ERR_UNSUPPORTED; }
   cin_pad = round_up(c.in_channels, 64);
 
+  {
+    const char* fe = getenv("DV_FUSE");
+    fuse = !(fe && fe[0] == '0');
+    const char* fm = getenv("DV_FUSE_MAXC");
+    fuse_max_c = fm ? atoi(fm) : 384;
+  }
   Builder b(*this);
   const int C0 = c.block_out_channels[0];
 
@@ -498,6 +616,14 @@ int Plan::build(std::string& err) {
           o.gn.ss_ld = n_all;
           break;
         case OP_LN: fix(o.lno.x); fix(o.lno.out); break;
+        case OP_CHAIN:
+          for (int i = 0; i < o.ch.nstages; ++i) {
+            ChainStageDesc& sd = o.ch.st[i];
+            if (sd.a.valid()) fix(sd.a.off);
+            if (sd.res.valid()) fix(sd.res.off);
+            if (sd.out.valid()) fix(sd.out.off);
+          }
+          break;
         case OP_ATTN: {
           // q/k/v offsets may carry an added column offset: fix preserves low bits
           fix(o.ato.q); fix(o.ato.k); fix(o.ato.v); fix(o.ato.o);
@@ -526,6 +652,18 @@ int Plan::build(std::string& err) {
         o.flops = 4.0 * Bd * o.at.H * o.at.Lq * static_cast<double>(o.at.Lk) * o.at.D;
         o.bytes = 2.0 * Bd * o.at.H * o.at.D * (2.0 * o.at.Lq + 2.0 * o.at.Lk);
         break;
+      case OP_CHAIN: {
+        const double rows = Bd * o.ch.L;
+        for (int i = 0; i < o.ch.nstages; ++i) {
+          const ChainStageDesc& sd = o.ch.st[i];
+          o.flops += 2.0 * rows * sd.w_rows * sd.w_k + 2.0 * rows * sd.w2_rows * sd.w2_k;
+          o.bytes += 2.0 * sd.w_rows * sd.w_k + 2.0 * sd.w2_rows * sd.w2_k;
+          if (sd.a.valid()) o.bytes += rows * sd.a.C * 2.0;
+          if (sd.res.valid()) o.bytes += rows * o.ch.C * 2.0;
+          if (sd.out.valid()) o.bytes += rows * (sd.kind == CH_STREAM ? sd.n : o.ch.C) * 2.0;
+        }
+        break;
+      }
       case OP_GN_APPLY: o.bytes = 4.0 * Bd * o.gn.L * (o.gn.c0 + o.gn.c1); break;
       case OP_LN: o.bytes = 4.0 * o.ln.rows * static_cast<double>(o.ln.C); break;
     }
@@ -562,6 +700,8 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
   {
     cudaError_t ie = gemm_tc_init();
     if (ie != cudaSuccess) { err = std::string("gemm_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
+    ie = chain_tc_init();
+    if (ie != cudaSuccess) { err = std::string("chain_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
   }
   cudaError_t ce = cudaMemsetAsync(ws, 0, ws_bytes, st);
   if (ce != cudaSuccess) { err = cudaGetErrorString(ce); return DV_ERR_CUDA; }
@@ -596,6 +736,46 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.stats = g.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + g.stats_off) : nullptr;
         p.stats_nblk = g.stats_nblk;
         p.bn = 0;
+      } else if (o.kind == OP_CHAIN) {
+        ChainParams& p = o.cp;
+        memset(&p, 0, sizeof p);
+        p.nstages = o.ch.nstages;
+        p.B = B; p.L = o.ch.L; p.C = o.ch.C;
+        p.tiles_per_batch = (o.ch.L + 127) / 128;
+        { const char* de = getenv("DV_CHAIN_DBG"); p.dbg_flags = de ? atoi(de) : 0; }
+        int na = 0, nw = 0;
+        for (int i = 0; i < o.ch.nstages; ++i) {
+          const ChainStageDesc& sd = o.ch.st[i];
+          ChainStage& cs = p.st[i];
+          cs.kind = sd.kind;
+          cs.a_map = -1;
+          if (sd.a.valid()) {
+            if (na >= 2) { err = "internal: too many streamed operands in a chain"; return false; }
+            if (!make_tmap_3d(&p.mapA[na], ws + sd.a.off, sd.a.C, sd.a.C, sd.a.L, B, static_cast<size_t>(sd.a.L) * sd.a.C, err))
+              return false;
+            cs.a_map = na++;
+          }
+          if (nw + (sd.w2_rows ? 2 : 1) > CHAIN_MAX_W) { err = "internal: too many weight matrices in a chain"; return false; }
+          if (!make_tmap_2d(&p.mapW[nw], params + sd.w_off, sd.w_k, sd.w_rows, 128, err)) return false;
+          cs.w_map = nw++;
+          cs.w2_map = 0;
+          if (sd.w2_rows) {
+            if (!make_tmap_2d(&p.mapW[nw], params + sd.w2_off, sd.w2_k, sd.w2_rows, 128, err)) return false;
+            cs.w2_map = nw++;
+          }
+          cs.n = sd.n;
+          cs.bias = pf(sd.bias_off); cs.bias2 = pf(sd.bias2_off);
+          cs.res = sd.res.valid() ? ws + sd.res.off : nullptr;
+          cs.ld_res = sd.res.valid() ? sd.res.C : 0;
+          cs.out = sd.out.valid() ? ws + sd.out.off : nullptr;
+          cs.ld_out = sd.out.valid() ? sd.out.C : 0;
+          cs.gamma = pf(sd.gamma); cs.beta = pf(sd.beta); cs.eps = sd.eps;
+          cs.stats = sd.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + sd.stats_off) : nullptr;
+          cs.stats_nblk = sd.stats_nblk;
+        }
+        // unused descriptors alias valid ones so prefetch.tensormap stays legal
+        for (int i = na; i < 2; ++i) p.mapA[i] = p.mapA[0];
+        for (int i = nw; i < CHAIN_MAX_W; ++i) p.mapW[i] = p.mapW[0];
       } else if (o.kind == OP_GN_APPLY) {
         o.gn.x0 = ws + o.gno.x0;
         o.gn.x1 = o.gn.c1 ? ws + o.gno.x1 : nullptr;
@@ -648,6 +828,7 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
           e = launch_gemm_tc(o.gp, st);
         }
         break;
+      case OP_CHAIN: e = launch_chain_tc(o.cp, st); break;
       case OP_GN_APPLY: e = launch_gn_apply(o.gn, st); break;
       case OP_LN: e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st); break;
       case OP_ATTN: {

@@ -28,7 +28,7 @@ struct ParamSlot {
   size_t off = 0, bytes = 0;
 };
 
-enum OpKind { OP_GEMM = 0, OP_GN_APPLY = 2, OP_LN = 3, OP_ATTN = 4 };
+enum OpKind { OP_GEMM = 0, OP_GN_APPLY = 2, OP_LN = 3, OP_ATTN = 4, OP_CHAIN = 5 };
 
 struct GemmDesc {
   int nsrc = 0;
@@ -45,11 +45,32 @@ struct GemmDesc {
   int stats_nblk = 0;
 };
 
+// One stage of a chained-GEMM launch (kernels.h: ChainStage), offsets instead of pointers until bind()
+struct ChainStageDesc {
+  int kind = CH_ROW;
+  TRef a;                          // CH_ROW: A operand streamed from global (invalid = X buffer)
+  size_t w_off = 0, w2_off = 0;    // packed weights [n_pad, k] / [n_pad2, k2]
+  int w_rows = 0, w_k = 0, w2_rows = 0, w2_k = 0;
+  int n = 0;
+  long long bias_off = -1, bias2_off = -1;
+  TRef res, out;
+  long long gamma = -1, beta = -1;
+  float eps = 1e-5f;
+  long long stats_off = -1;
+  int stats_nblk = 0;
+};
+struct ChainDesc {
+  int nstages = 0;
+  ChainStageDesc st[CHAIN_MAX_STAGES];
+  int L = 0, C = 0;
+};
+
 struct Op {
   OpKind kind;
   std::string tag;
   double flops = 0, bytes = 0;  // algorithmic work of one launch (for roofline accounting)
   GemmDesc g; GemmParams gp;
+  ChainDesc ch; ChainParams cp;
   GnParams gn;
   struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; } ln;
   AttnParams at;
@@ -63,6 +84,8 @@ struct Plan {
   dv_unet_cfg cfg;
   int B, T, Tp;
   int n_levels, emb_dim, cin_pad;
+  int fuse_max_c = 384;      // widest level whose transformer blocks use the chained kernels
+  bool fuse = true;          // transformer sections as chained-GEMM kernels (DV_FUSE=0 selects the one-kernel-per-op program)
   std::vector<ParamSlot> slots;
   size_t param_bytes = 0, ws_bytes = 0;
   std::vector<Op> ops;       // one denoiser call

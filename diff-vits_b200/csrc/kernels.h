@@ -74,6 +74,50 @@ cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st);
 struct GemmRefSrc { const void* ptr; int L, C, ld; };
 cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const void* W, int k_tot, cudaStream_t st);
 
+// ------------------------------------------------------------------ chained GEMMs (csrc/chain_tc.cu)
+// One persistent kernel runs a short program of row-local GEMMs of a transformer block over 128-row tiles, keeping
+// the activations between them in shared memory / TMEM instead of HBM:
+//   CH_ROW    : D[128, C] = A . W^T (+bias) (+res)  -> bf16 global (optional) -> LayerNorm (or plain copy) -> X (smem)
+//               A is streamed from global by TMA (a_map >= 0) or is the X buffer (a_map < 0).
+//   CH_STREAM : out[128, n] = X . W^T (+bias) (+res) -> bf16 global (+GroupNorm partials), 128 columns at a time
+//   CH_FF     : GEGLU feed-forward: for each 64 hidden units  h = u * gelu(g), [u|g] = X . W1_chunk^T + b1 ; the bf16
+//               h chunk goes to shared memory and is immediately contracted with W2[:, chunk] into the [128, C]
+//               accumulator; result (+bias2) (+res) -> X (smem). The [L, 8C] / [L, 4C] intermediates never exist.
+// C = 128 * U, U in {1, 2, 3}. Weights are the same packed [n_pad, K] K-major matrices the single GEMMs use.
+constexpr int CHAIN_MAX_STAGES = 4;
+constexpr int CHAIN_MAX_W = 5;
+enum ChainKind : int { CH_ROW = 0, CH_STREAM = 1, CH_FF = 2 };
+
+struct ChainStage {
+  int kind;
+  int a_map;              // CH_ROW: index into mapA of the streamed A operand, or -1 = X buffer
+  int w_map, w2_map;      // indices into mapW (w2: CH_FF second matrix)
+  int n;                  // CH_STREAM: output columns (multiple of 128); CH_FF: hidden width (multiple of 64)
+  const float* bias;      // [n] (CH_ROW: [C]; CH_FF: [2n] in the interleaved u/g packing), may be null
+  const float* bias2;     // CH_FF: [C]
+  const void* res;        // bf16 [B, L, ld_res] added before the store, or null
+  int ld_res;
+  void* out;              // bf16 [B, L, ld_out] or null
+  int ld_out;
+  const float* gamma;     // CH_ROW: LayerNorm affine (null = copy the bf16 result to X unchanged)
+  const float* beta;
+  float eps;
+  float* stats;           // CH_STREAM: GroupNorm partials of the stored tensor (layout as GemmParams::stats) or null
+  int stats_nblk;
+};
+
+struct alignas(64) ChainParams {
+  CUtensorMap mapA[2];
+  CUtensorMap mapW[CHAIN_MAX_W];
+  ChainStage st[CHAIN_MAX_STAGES];
+  int nstages;
+  int B, L, C;
+  int tiles_per_batch;    // ceil(L / 128)
+  int dbg_flags;          // timing experiments only (DV_CHAIN_DBG): 1 skip GELU math, 2 skip proxy fences, 4 skip bias loads
+};
+cudaError_t chain_tc_init();
+cudaError_t launch_chain_tc(const ChainParams& p, cudaStream_t st);
+
 // ------------------------------------------------------------------ attention (flash style, bf16 in, fp32 softmax)
 struct AttnParams {
   const void* q; const void* k; const void* v; void* o;   // bf16
