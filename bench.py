@@ -36,6 +36,16 @@ def denoiser_flops(T: int, Tp: int) -> float:
     return 31.705e6 * T + 2.35e6 * Tp + 4352.0 * T * T + 7296.0 * T * Tp
 
 
+def load_traffic() -> dict:
+    """DRAM bytes per launch per kernel class from the committed ncu capture (profiles/traffic.json, written by
+    tools/traffic_from_launches.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one call)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 def load_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -172,6 +182,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     import diffvits_b200
     from diffvits_b200 import synthetic as inputs       # the native arm never imports oracle/
@@ -291,10 +303,17 @@ def run_native(args):
         kernels["prologue(layout+time_mlp)"] = {"ms_per_call": round(acc[-1], 4)}
         total_flops = denoiser_flops(T, Tp) * Bg * nfe           # per GPU per step
         step_tflops = total_flops / (ms_res * 1e-3) / 1e12
+        traffic = load_traffic()
+        for name, ent in kernels.items():
+            if name in traffic.get("per_launch_dram_bytes", {}):
+                ent["ncu_dram_bytes_per_launch"] = traffic["per_launch_dram_bytes"][name]
         roofline = {
-            "kernel": "gemm_tc_kernel<128> (tcgen05 tap-GEMM: conv1d k3 / 1x1 / linear)",
+            "kernel": "gemm_tc_kernel (tcgen05 tap-GEMM: conv1d k3 / 1x1 / linear)",
             "bound": "tensor", "achieved": round(gemm_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": round(gemm_tflops / peak_tf, 4), "traffic": None,
+            "frac": round(gemm_tflops / peak_tf, 4),
+            "traffic": traffic.get("per_launch_dram_bytes", {}).get("gemm_tc"),
+            "traffic_source": traffic.get("source"),
+            "algorithmic_bytes_per_launch": round(g["bytes"] / g["launches"]),
             "peak_source": peaks["_source"] + ", burst figure (kernel timed launch by launch)",
             "how": f"sum of algorithmic FLOPs of the {g['launches']} GEMM launches of one denoiser call / sum of their "
                    f"CUDA-event durations (eager, events on the launching stream, mean of {reps} calls)",

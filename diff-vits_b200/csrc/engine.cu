@@ -511,7 +511,7 @@ int Plan::build(std::string& err) {
     const char* fe = getenv("DV_FUSE");
     fuse = !(fe && fe[0] == '0');
     const char* fm = getenv("DV_FUSE_MAXC");
-    fuse_max_c = fm ? atoi(fm) : 384;
+    fuse_max_c = fm ? atoi(fm) : 128;
   }
   Builder b(*this);
   const int C0 = c.block_out_channels[0];

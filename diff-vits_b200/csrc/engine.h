@@ -84,7 +84,10 @@ struct Plan {
   dv_unet_cfg cfg;
   int B, T, Tp;
   int n_levels, emb_dim, cin_pad;
-  int fuse_max_c = 384;      // widest level whose transformer blocks use the chained kernels
+  // Widest level whose transformer blocks run as chained kernels (DV_FUSE_MAXC). Measured on C2 (B200, 32 x 1000):
+  // the chain wins or ties while a level has >= ~1.5 row tiles per SM (C = 128: 250 tiles); deeper levels have too few
+  // 128-row tiles (125 / 63) to fill 148 SMs with one CTA per tile, there the one-kernel-per-op program is faster.
+  int fuse_max_c = 128;
   bool fuse = true;          // transformer sections as chained-GEMM kernels (DV_FUSE=0 selects the one-kernel-per-op program)
   std::vector<ParamSlot> slots;
   size_t param_bytes = 0, ws_bytes = 0;

@@ -17,6 +17,7 @@
 //                               GroupNorm that consumes this tensor (deterministic shuffle tree, no atomics);
 //                               conv_out stores fp32 [B, N, L] directly (lanes = consecutive frames).
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -27,24 +28,24 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter: they split the tile's columns
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+// Epilogue warps per CTA (EW): 16 (4 per TMEM lane quarter, 1 CTA per SM, deep TMA ring) or 8 (2 per quarter, small
+// enough in registers / shared memory / TMEM for TWO CTAs per SM: one CTA's epilogue and pipeline fill overlap the
+// other's main loop, and with PDL the next kernel's CTAs become resident while this kernel's last tiles drain).
 constexpr int EPI_PITCH = 80;                       // bytes per staged row: 32 bf16 (64 B) + 16 B pad
 constexpr int EPI_SLAB = 32 * EPI_PITCH;            // per epilogue warp
 constexpr int MAX_NPAD = 4096;                      // bias vector kept in shared memory for the whole kernel
 
-template <int BN>
+template <int BN, int EW>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 128 ? 5 : 3;
+  static constexpr int STAGES = EW == 8 ? 2 : (BN == 128 ? 5 : 3);
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_SLAB;
-  static constexpr int BAR_OFF = BIAS_OFF + MAX_NPAD * 4;
-  static constexpr int TOTAL = BAR_OFF + 256;          // barriers + tmem slot
-  static constexpr int DYN_BYTES = TOTAL + 1024;       // slack for 1024-byte alignment
-  static_assert(DYN_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static constexpr int BAR_OFF = EPI_OFF + EW * EPI_SLAB;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;       // barriers + tmem slot, then the bias vector (n_pad floats)
+  static constexpr int dyn_bytes(int n_pad) { return BIAS_OFF + n_pad * 4 + 1024; }   // + slack for 1024-byte alignment
+  static_assert(dyn_bytes(MAX_NPAD) <= (EW == 8 ? 116224 : 232448), "exceeds the shared memory budget");
 };
 
 // debug timeline (enabled only when p.trace != nullptr): CTA 0, one lane per role
@@ -146,9 +147,10 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
   __syncwarp();
 }
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using SL = SmemLayout<BN>;
+template <int BN, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using SL = SmemLayout<BN, EW>;
+  constexpr int PARTS = EW / 4;                       // epilogue warps per TMEM lane quarter
   constexpr int STAGES = SL::STAGES;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -176,14 +178,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], EPI_WARPS);
+      mbar_init(&tmem_empty_bar[a], EW);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   if (warp >= 2 && p.bias) {                         // bias vector -> shared memory, once per CTA
     float* sb = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
-    for (int i = threadIdx.x - 64; i < p.n_pad; i += EPI_WARPS * 32) sb[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x - 64; i < p.n_pad; i += EW * 32) sb[i] = __ldg(p.bias + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // ------------------------------------------------------------------ epilogue: warps 2..17
     // TMEM lane quarter is fixed by hardware to (warp id % 4); the four warps of a quarter split the columns.
     const int quad = warp & 3;
-    const int part = (warp - 2) >> 2;                    // 0..3
+    const int part = (warp - 2) >> 2;                    // 0..PARTS-1
     EpiCtx e;
     const uint32_t slab = smem_u32(smem + SL::EPI_OFF + (warp - 2) * EPI_SLAB);
     e.lane = lane; e.srow = lane >> 2; e.spiece = lane & 3;
@@ -296,14 +298,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         constexpr int NUNIT = BN / 32;                   // 4 per 128 tile columns
         const int orow = lane >> 1, opiece = lane & 1;   // row-contiguous phase: 16 rows x 2 pieces of 16 B
 #pragma unroll 1
-        for (int un = part; un < NUNIT; un += 4) {
+        for (int un = part; un < NUNIT; un += PARTS) {
           const int cu = (un >> 2) * 128 + (un & 3) * 16;
           const int ocol = (n0 >> 1) + (un >> 2) * 64 + (un & 3) * 16;
           uint32_t u[16], g[16];
           tmem_ld16(taddr + cu, u);
           tmem_ld16(taddr + cu + 64, g);
           tmem_ld_wait();
-          if (un + 4 >= NUNIT) {                          // last TMEM read of this tile by this warp
+          if (un + PARTS >= NUNIT) {                          // last TMEM read of this tile by this warp
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
@@ -339,12 +341,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         float* out = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.N * p.L + (valid ? l : 0);
         constexpr int NCH = BN / 32;
 #pragma unroll 1
-        for (int ch = part; ch < NCH; ch += 4) {
+        for (int ch = part; ch < NCH; ch += PARTS) {
           const int c = ch * 32;
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
-          if (ch + 4 >= NCH) {
+          if (ch + PARTS >= NCH) {
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
@@ -366,9 +368,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const bool has_res = p.res != nullptr, has_stats = p.stats != nullptr;
         bool arrived = false;
 #pragma unroll 1
-        for (int ch = part; ch < NCH; ch += 4) {
+        for (int ch = part; ch < NCH; ch += PARTS) {
           const int gcol = n0 + ch * 32;
-          const bool last = ch + 4 >= NCH;
+          const bool last = ch + PARTS >= NCH;
           if (gcol >= p.N) continue;                      // padded output columns are neither read nor written
           arrived |= last;
           const uint32_t tc = taddr + ch * 32;
@@ -425,19 +427,15 @@ __global__ void gemm_ref_kernel(GemmParams p, GemmRefSrc s0, GemmRefSrc s1, Gemm
 }
 
 int g_num_sms = 0;
+int g_force_ew = 0;   // DV_GEMM_EW: 8 / 16 force the CTA shape of the 128-wide tile kernel (0 = heuristic)
 
-template <int BN>
+template <int BN, int EW>
 cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
-  using SL = SmemLayout<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::DYN_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  using SL = SmemLayout<BN, EW>;
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / BN);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  return launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), SL::DYN_BYTES, st, p);
+  const int slots = g_num_sms * (EW == 8 ? 2 : 1);
+  const int grid = tiles < slots ? tiles : slots;
+  return launch_k(gemm_tc_kernel<BN, EW>, dim3(grid), dim3(64 + EW * 32), SL::dyn_bytes(p.n_pad), st, p);
 }
 
 }  // namespace
@@ -457,11 +455,18 @@ cudaError_t gemm_tc_init() {
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
   }
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SmemLayout<128>::DYN_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              SmemLayout<256>::DYN_BYTES);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<128, 8>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
+  {
+    const char* ev = getenv("DV_GEMM_EW");
+    if (ev) g_force_ew = atoi(ev);
+  }
+  return cudaFuncSetAttribute(gemm_tc_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
 }
 
 cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
@@ -474,9 +479,13 @@ cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
   if (bn == 256) {
     if (p.n_pad % 256 != 0) return cudaErrorInvalidValue;
-    return launch_bn<256>(p, st);
+    return launch_bn<256, 16>(p, st);
   }
-  return launch_bn<128>(p, st);
+  // two small CTAs per SM pay once there is more than one wave of 128-wide tiles (measured on the C2 shapes: 5-10 %
+  // faster at levels 0-2, slower for the few long-K tiles of level 3)
+  const int tiles = p.tiles_per_batch * p.B * (p.n_pad / 128);
+  const int ew = g_force_ew ? g_force_ew : (tiles >= g_num_sms + g_num_sms / 8 ? 8 : 16);
+  return ew == 8 ? launch_bn<128, 8>(p, st) : launch_bn<128, 16>(p, st);
 }
 
 cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const void* W, int k_tot, cudaStream_t st) {

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 TAG=${1:-r1}
 mkdir -p gpurun_out
 # every launch of one eager denoiser call (C2 shapes), device time per launch (cold cache, serialised: compare shares)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
   --nvtx --nvtx-include "dv_call/" python tools/profile_call.py --workload c2 --calls 1 --no-events \
   > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "launch list rc=$?"
 # full sections: first resnet + first transformer block at level 0 (conv, gn, ln, qkv, attention, geglu ...)
