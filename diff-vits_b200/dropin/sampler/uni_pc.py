@@ -6,8 +6,7 @@ Public surface kept: `NoiseScheduleVP` ('discrete' | 'linear' | 'cosine', no log
 
 Fast path (model3.py:1177-1192: variant 'bh2', order 2, multistep, x_start model): the predictor / corrector
 updates and the denoiser run as one CUDA graph inside libdiffvits_b200. Other multistep settings (bh1, order 3,
-noise prediction, correctors) run the generic per-step loop below. `vary_coeff` (uni_pc.py:368-469) is not used by
-Diff-VITS and is not implemented.
+noise prediction, correctors, `vary_coeff`) run the generic per-step loop below over the same denoiser.
 
 Difference from the reference on purpose: `model_wrapper` broadcasts alpha_t / sigma_t over the batch, so batch > 1
 works (the reference raises a shape error there, uni_pc.py:189-191); for batch 1 the results are identical.
@@ -85,7 +84,64 @@ class UniPC:
             t = t.view(-1)
         if "bh" in self.variant:
             return self.multistep_uni_pc_bh_update(x, model_prev_list, t_prev_list, t, order, **kwargs)
-        raise NotImplementedError("UniPC variant 'vary_coeff' is not implemented in diffvits_b200 (unused by Diff-VITS)")
+        assert self.variant == "vary_coeff"
+        return self.multistep_uni_pc_vary_update(x, model_prev_list, t_prev_list, t, order, **kwargs)
+
+    def multistep_uni_pc_vary_update(self, x, model_prev_list, t_prev_list, t, order, use_corrector=True):
+        """UniPC with varying coefficients (uni_pc.py:368-469). With r_i = (lambda_{-i} - lambda_0) / h for the history
+        points (r_K = 1 for the new point), D_i = (m_{-i} - m_0) / r_i and the Vandermonde-like matrix
+        C[i, k] = r_i^k / (k+1)! , the predictor adds  -A * sum_k phi_{k+1}(h) * (C_p^{-1}[k] . D)  to the first-order step
+        and the corrector repeats that with the full C^{-1} and the new difference (m_t - m_0). Returns (x_t, model_t)."""
+        ns = self.noise_schedule
+        assert order <= len(model_prev_list)
+        t0, m0 = t_prev_list[-1], model_prev_list[-1]
+        lam0 = ns.marginal_lambda(t0)
+        h = ns.marginal_lambda(t) - lam0
+        ratios, diffs = [], []
+        for i in range(1, order):
+            r = (ns.marginal_lambda(t_prev_list[-(i + 1)]) - lam0) / h
+            ratios.append(r)
+            diffs.append((model_prev_list[-(i + 1)] - m0) / r)
+        ratios.append(1.0)
+        rks = torch.tensor(ratios, device=x.device)
+        K = rks.numel()
+        cols, col = [], torch.ones_like(rks)
+        for k in range(1, K + 1):            # column k-1 holds r^(k-1) / k!
+            cols.append(col)
+            col = col * rks / (k + 1)
+        Cm = torch.stack(cols, dim=1)
+        inv_p = torch.linalg.inv(Cm[:-1, :-1]) if diffs else None
+        inv_c = torch.linalg.inv(Cm) if use_corrector else None
+        hh = -h if self.predict_x0 else h
+        # phi_1(h) h, then the recurrence phi_{k+1} = phi_k / h - 1/k!
+        phis, phi, fact = [], torch.expm1(hh), 1
+        for k in range(1, K + 2):
+            phis.append(phi)
+            phi = phi / hh - 1 / fact
+            fact *= (k + 1)
+        if self.predict_x0:
+            scale = ns.marginal_alpha(t)
+            lin = ns.marginal_std(t) / ns.marginal_std(t0) * x - scale * phis[0] * m0
+        else:
+            scale = ns.marginal_std(t)
+            lin = torch.exp(ns.marginal_log_mean_coeff(t) - ns.marginal_log_mean_coeff(t0)) * x - (scale * phis[0]) * m0
+        D = torch.stack(diffs, dim=1) if diffs else None          # [B, K-1, ...]
+
+        def mix(weights):                                         # sum_j weights[j] * D[:, j]
+            return torch.einsum("bk...,k->b...", D, weights)
+
+        x_t = lin
+        for k in range(K - 1):
+            x_t = x_t - scale * phis[k + 1] * mix(inv_p[k])
+        model_t = None
+        if use_corrector:
+            model_t = self.model_fn(x_t, t)
+            x_t = lin
+            for k in range(K - 1):
+                x_t = x_t - scale * phis[k + 1] * mix(inv_c[k][:-1])
+            last_row = max(K - 2, 0)     # the reference weighs the new difference with row K-2 of C^{-1} (row 0 when K = 1)
+            x_t = x_t - scale * phis[K] * ((model_t - m0) * inv_c[last_row][-1])
+        return x_t, model_t
 
     def multistep_uni_pc_bh_update(self, x, model_prev_list, t_prev_list, t, order, x_t=None, use_corrector=True):
         """UniPC-B(h) step of the given order from t_prev_list[-1] to t (uni_pc.py:471-588). Returns (x_t, model_t);
