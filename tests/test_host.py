@@ -202,8 +202,10 @@ def test_dropin_sampler_generic_loops_match_oracle(dropin):
                                                         method="multistep")
         want = sampler_oracle.unipc_bh2(_fake, betas, x0.clone(), steps, roundtrip=True)
         assert float((got - want).norm() / want.norm()) < 1e-5
-    with pytest.raises(NotImplementedError):
-        dpm.DPM_Solver(fn, ns).sample(x0, steps=4, method="singlestep")
+    single = dpm.DPM_Solver(fn, ns).sample(x0, steps=4, method="singlestep")      # generic loop (test_samplers_generic.py)
+    assert torch.isfinite(single).all()
+    with pytest.raises(ValueError):
+        dpm.DPM_Solver(fn, ns).sample(x0, steps=4, method="bogus")
     with pytest.raises(ValueError):
         dpm.NoiseScheduleVP("cosine")
     assert uni.NoiseScheduleVP("cosine").T == 0.9946
