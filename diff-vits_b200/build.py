@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdiffvits_b200.so")
-SOURCES = ["gemm_tc.cu", "chain_tc.cu", "attention.cu", "norm.cu", "elementwise.cu", "engine.cu", "api.cu"]
+SOURCES = ["gemm_tc.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "norm.cu", "elementwise.cu", "engine.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

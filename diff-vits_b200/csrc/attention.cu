@@ -10,6 +10,8 @@
 // Masking: self-attention has no mask (attention_mask=None in the reference, padded frames participate).
 // Cross-attention uses the reference's additive bias: keys >= kv_len[b] get -10000 added to the scaled score
 // (unet_1d_condition.py:816-818), reproduced literally so a fully masked row degrades the same way.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 
 }  // namespace
 
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
+// mma.sync kernel of round 1; kept selectable (DV_ATTN_LEGACY=1) as the A/B bar for the tcgen05 kernel
+cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st) {
   if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
   dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
   switch (p.D) {
@@ -228,6 +231,15 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
     case 64: return launch_k(attention_kernel<64>, grid, dim3(ATT_THREADS), 0, st, p);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("DV_ATTN_LEGACY");
+    legacy = (e && e[0] == '1') ? 1 : 0;
+  }
+  return legacy ? launch_attention_legacy(p, st) : launch_attention_tc(p, st);
 }
 
 }  // namespace dv

@@ -702,6 +702,8 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
     if (ie != cudaSuccess) { err = std::string("gemm_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
     ie = chain_tc_init();
     if (ie != cudaSuccess) { err = std::string("chain_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
+    ie = attention_tc_init();
+    if (ie != cudaSuccess) { err = std::string("attention_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
   }
   cudaError_t ce = cudaMemsetAsync(ws, 0, ws_bytes, st);
   if (ce != cudaSuccess) { err = cudaGetErrorString(ce); return DV_ERR_CUDA; }

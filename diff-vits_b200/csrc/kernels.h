@@ -127,7 +127,10 @@ struct AttnParams {
   float scale;                                             // D^-0.5
   const int* kv_len;   // per-batch number of un-masked keys (keys >= kv_len[b] get the -10000 bias), or nullptr
 };
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);          // tcgen05 kernel (csrc/attention_tc.cu)
+cudaError_t attention_tc_init();                                            // kernel attributes (call outside graph capture)
+cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st);
+cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st);   // mma.sync kernel (csrc/attention.cu)
 
 // ------------------------------------------------------------------ norms
 // Partial statistics layout (written by the GEMM epilogue or by gn_stats): float [B][chunks][nblk][2] holding the
