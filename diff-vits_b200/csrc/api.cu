@@ -200,10 +200,14 @@ int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q,
   int rc = require_device();
   if (rc != DV_OK) return rc;
   dv::AttnParams p;
+  memset(&p, 0, sizeof p);
   p.q = q; p.k = k; p.v = v; p.o = o;
   p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ld_o = ld_o;
   p.bs_q = bs_q; p.bs_k = bs_k; p.bs_v = bs_v; p.bs_o = bs_o;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.D = D; p.scale = scale; p.kv_len = kv_len;
+  p.trace = g_test_trace;   // the dv_gemm_test_trace buffer doubles as the attention kernel's debug timeline
+  const char* ae = nullptr;
+  if (!dv::attention_tc_prepare(p, &ae)) return fail(DV_ERR_CUDA, ae ? ae : "attention_tc_prepare");
   return ck(dv::launch_attention(p, S(stream)), "attention");
 }
 

@@ -11,15 +11,18 @@
 //               (O = O * corr + PV), so the tensor pipe never waits for a rescale of TMEM contents.
 //   warp 4    : MMA issuer (one lane). S(j+1) = Q.K^T is issued before P(j).V, so the tensor core fills the other
 //               S buffer while the softmax warps work on tile j. M = 128, N = 64 (S) / D (PV), K = 16 per instruction.
-//   warp 5    : loader. Q / K rows are copied into 128-byte-pitch rows with the UMMA 128-byte swizzle (only the
-//               first D columns of a row are used: the MMA K loop covers D/16 steps); V is transposed on the way in
-//               (V^T [D x 64 keys], K-major for the P.V product). Out-of-range keys are zero filled. 3-stage ring.
+//   warp 5    : TMA producer (one lane). Q / K / V tiles are [rows x D] boxes of the [B, L, H*D] operands (3-D maps,
+//               rows outside [0, L) zero filled), D*2-byte rows with the matching 32/64/128-byte swizzle (d = 48 uses a
+//               64-wide box; the MMA only walks the first 48 columns). K is consumed K-major, V as an MN-major B
+//               operand of the P.V product - no transpose anywhere. 4-stage ring.
 // At d = 16 a score costs 64 FLOP per exp: the kernel is bound by the MUFU pipe (16 ex2 / clk / SM), the tensor
 // pipe only has to stay out of the way - which is the point of moving both GEMMs off the issue slots.
 //
 // Masking: self-attention has no mask (padded frames participate, as in the reference). Cross-attention adds the
 // reference's -10000 to the scaled score of keys >= kv_len[b], literally, so a fully masked row degrades the same.
 #include <cstdlib>
+
+#include <cudaTypedefs.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -29,24 +32,40 @@ namespace {
 
 constexpr int TQ = 128;          // queries per CTA (= TMEM lanes)
 constexpr int TK = 64;           // keys per tile
-constexpr int NS = 3;            // K/V ring stages
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;   // warps 0-7 softmax, warp 8 MMA issuer, warp 9 TMA producer
 
 template <int D>
 struct AttSmem {
-  static constexpr int Q_BYTES = TQ * 128;
-  static constexpr int K_BYTES = TK * 128;
-  static constexpr int V_BYTES = TK * 128;    // same row layout as K; consumed as an MN-major B operand
-  static constexpr int P_BYTES = TQ * 128;
+  static constexpr int DB = D == 48 ? 64 : D;            // box width in elements (power of two: a swizzle span)
+  static constexpr int ROW = DB * 2;                     // bytes per operand row = swizzle span (32 / 64 / 128)
+  static constexpr int NS = ROW == 128 ? 3 : 4;          // K/V ring stages
+  static constexpr int Q_BYTES = TQ * ROW;
+  static constexpr int K_BYTES = TK * ROW;
+  static constexpr int V_BYTES = TK * ROW;
+  static constexpr int P_BYTES = TQ * 128;               // P tile: 64 keys bf16 = 128-byte rows, SWIZZLE_128B
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = Q_OFF + Q_BYTES;
   static constexpr int V_OFF = K_OFF + NS * K_BYTES;
   static constexpr int P_OFF = V_OFF + NS * V_BYTES;
   static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // + slack for the 1024-byte alignment of the operand boxes
-  static_assert(V_BYTES % 1024 == 0, "operand boxes must stay 1024-byte aligned");
+  static constexpr int RED_OFF = BAR_OFF + 256;         // row-max exchange [2 buffers][128 rows][2 halves] + row sums
+  static constexpr int TOTAL = RED_OFF + 3072 + 1024;   // + slack for the 1024-byte alignment of the operand boxes
+  static constexpr uint32_t LAYOUT = ROW == 32 ? 6u : (ROW == 64 ? 4u : 2u);   // UMMA layout type of the Q/K/V boxes
+  static_assert(K_BYTES % 1024 == 0 && Q_BYTES % 1024 == 0, "operand boxes must stay 1024-byte aligned");
   static_assert(2 * TOTAL <= 227 * 1024, "two CTAs per SM");
 };
+
+// Shared-memory matrix descriptor for a box of ROW-byte rows with the ROW-byte swizzle: 8-row groups are 8*ROW bytes
+// apart (SBO); LBO is unused (K-major: one swizzle span along K; MN-major: the tile is one span wide).
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr, uint32_t row_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -58,107 +77,79 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ uint4 ldg128(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
+// barrier of one warp pair (64 threads); ids are immediates so that only 5 hardware barriers are reserved per CTA
+__device__ __forceinline__ void pair_bar_sync(int quad) {
+  switch (quad) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
 }
-__device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(static_cast<unsigned short>(v)) : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
-
-// ROWS rows of D bf16 (row stride ld) -> 128-byte-pitch rows, 16-byte pieces XOR-swizzled by (row & 7): the K-major
-// SWIZZLE_128B operand layout. Rows >= row_end are zero filled. One warp; consecutive lanes read consecutive pieces.
-template <int D, int ROWS>
-__device__ __forceinline__ void load_rows_sw128(uint32_t box, const __nv_bfloat16* src, int ld, int row0, int row_end,
-                                                int lane) {
-  constexpr int CH = D / 8;
-  constexpr int N = ROWS * CH / 32;
-  constexpr int UB = N % 8 == 0 ? 8 : (N % 6 == 0 ? 6 : (N % 4 == 0 ? 4 : N));   // loads in flight per lane
-  static_assert(N % UB == 0, "piece count per lane");
-#pragma unroll 1
-  for (int i0 = 0; i0 < N; i0 += UB) {
-    uint4 v[UB];
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int t = (i0 + u) * 32 + lane;
-      const int r = t / CH, c = t % CH;
-      const int row = row0 + r;
-      v[u] = row < row_end ? ldg128(src + static_cast<size_t>(row) * ld + c * 8) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int t = (i0 + u) * 32 + lane;
-      const int r = t / CH, c = t % CH;
-      sts128(box + r * 128 + ((c ^ (r & 7)) << 4), v[u]);
-    }
+// waits of the single-lane MMA / TMA roles: back off between polls so the spin does not take issue slots from the
+// softmax warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    __nanosleep(40);
+    if (++spins > 40000000u) mbar_timeout_trap();
   }
 }
 
-// 64 keys x D of V -> V^T [D rows][64 keys] in the same swizzled layout (row d, 16-byte piece key/8, element key%8)
-template <int D>
-__device__ __forceinline__ void load_v_transposed(uint32_t box, const __nv_bfloat16* src, int ld, int key0, int key_end,
-                                                  int lane) {
-  constexpr int CH = D / 8;
-  constexpr int N = TK * CH / 32;     // 2 pieces per lane per 8 channels
-  constexpr int UB = N % 8 == 0 ? 8 : (N % 6 == 0 ? 6 : (N % 4 == 0 ? 4 : N));   // loads in flight per lane
-  static_assert(N % UB == 0, "piece count per lane");
-#pragma unroll 1
-  for (int i0 = 0; i0 < N; i0 += UB) {
-    uint4 v[UB];
+// o[0..N) = o * c + (this thread's row, N columns at taddr, of the P.V accumulator)
+template <int N>
+__device__ __forceinline__ void fold_pv(float (&o)[N], float c, uint32_t taddr) {
+  static_assert(N == 8 || N == 16 || N == 24 || N == 32, "columns per thread");
+  if constexpr (N == 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    tmem_ld_wait();
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int key = ((i0 + u) & 1) * 32 + lane, c = (i0 + u) >> 1;
-      const int row = key0 + key;
-      v[u] = row < key_end ? ldg128(src + static_cast<size_t>(row) * ld + c * 8) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int key = ((i0 + u) & 1) * 32 + lane, c = (i0 + u) >> 1;
-      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      const uint32_t kb = box + (c * 8) * 128 + (key & 7) * 2;
-      const int ks = key >> 3;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t val = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
-        sts16(kb + e * 128 + ((ks ^ e) << 4), val);
-      }
-    }
-  }
-}
-
-// o[0..D) = o * c + (this thread's row of the P.V accumulator at taddr)
-template <int D>
-__device__ __forceinline__ void fold_pv(float (&o)[D], float c, uint32_t taddr) {
-  if constexpr (D % 32 == 0) {
-#pragma unroll
-    for (int i = 0; i < D / 32; ++i) {
-      uint32_t r[32];
-      tmem_ld32(taddr + 32 * i, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) o[32 * i + k] = fmaf(o[32 * i + k], c, __uint_as_float(r[k]));
-    }
+    for (int k = 0; k < 32; ++k) o[k] = fmaf(o[k], c, __uint_as_float(r[k]));
   } else {
-#pragma unroll
-    for (int i = 0; i < D / 16; ++i) {
+    if constexpr (N >= 16) {
       uint32_t r[16];
-      tmem_ld16(taddr + 16 * i, r);
+      tmem_ld16(taddr, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 16; ++k) o[16 * i + k] = fmaf(o[16 * i + k], c, __uint_as_float(r[k]));
+      for (int k = 0; k < 16; ++k) o[k] = fmaf(o[k], c, __uint_as_float(r[k]));
+    }
+    if constexpr (N % 16 == 8) {
+      uint32_t r[8];
+      tmem_ld8(taddr + (N - 8), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[N - 8 + k] = fmaf(o[N - 8 + k], c, __uint_as_float(r[k]));
     }
   }
 }
 
+// debug timeline (enabled only when p.trace != nullptr): CTA (0,0,0), one lane per role; every role appends to its own
+// region of the buffer with plain stores (no atomics: the probe must not add a round trip to what it measures)
+constexpr int TRACE_CAP = 1300;
+__device__ __forceinline__ void trace_ev(const AttnParams& p, int role, int& cnt, int tile, int ev) {
+  if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && cnt < TRACE_CAP) {
+    p.trace[1 + role * TRACE_CAP + cnt] = (static_cast<unsigned long long>(role + 1) << 60) | (static_cast<unsigned long long>(tile & 0xFFFF) << 44) |
+                                          (static_cast<unsigned long long>(ev & 0xF) << 40) | (clock64() & 0xFFFFFFFFFFULL);
+    ++cnt;
+  }
+}
+
 template <int D>
-__global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const __grid_constant__ AttnParams p) {
   using SM = AttSmem<D>;
+  constexpr int NS = SM::NS;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem + SM::Q_OFF, sK = smem + SM::K_OFF, sV = smem + SM::V_OFF, sP = smem + SM::P_OFF;
-  const uint32_t bars = smem + SM::BAR_OFF;
+  const uint32_t bars = smem + SM::BAR_OFF, red = smem + SM::RED_OFF;
   constexpr uint32_t Q_FULL = 0, KV_FULL = 8, KV_EMPTY = KV_FULL + 8 * NS, S_FULL = KV_EMPTY + 8 * NS,
                      P_FULL = S_FULL + 16, O_FULL = P_FULL + 16, TMEM_SLOT = O_FULL + 16;
   static_assert(TMEM_SLOT + 4 <= 256, "barrier block too small");
@@ -167,18 +158,22 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnP
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
   const int ntiles = (p.Lk + TK - 1) / TK;
+  int tcnt = 0;   // debug trace cursor
 
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
     mbar_init_a(bars + Q_FULL, 1);
     for (int s = 0; s < NS; ++s) { mbar_init_a(bars + KV_FULL + 8 * s, 1); mbar_init_a(bars + KV_EMPTY + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init_a(bars + S_FULL + 8 * a, 1);
-      mbar_init_a(bars + P_FULL + 8 * a, 4);
+      mbar_init_a(bars + P_FULL + 8 * a, 8);
       mbar_init_a(bars + O_FULL + 8 * a, 1);
     }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + TMEM_SLOT), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -189,150 +184,169 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnP
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(bars + TMEM_SLOT));
   pdl_wait();   // Q/K/V come from the previous kernel; the output buffer may still be read by it
 
-  if (warp == 5) {
-    // ------------------------------------------------------------------ loader
-    const __nv_bfloat16* Q = reinterpret_cast<const __nv_bfloat16*>(p.q) + b * p.bs_q + h * D;
-    const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(p.k) + b * p.bs_k + h * D;
-    const __nv_bfloat16* V = reinterpret_cast<const __nv_bfloat16*>(p.v) + b * p.bs_v + h * D;
-    load_rows_sw128<D, TQ>(sQ, Q, p.ld_q, q0, p.Lq, lane);
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_a(bars + Q_FULL);
-    int st = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait_a(bars + KV_EMPTY + 8 * st, ph ^ 1);
-      load_rows_sw128<D, TK>(sK + st * SM::K_BYTES, K, p.ld_k, j * TK, p.Lk, lane);
-      load_rows_sw128<D, TK>(sV + st * SM::V_BYTES, V, p.ld_v, j * TK, p.Lk, lane);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(bars + KV_FULL + 8 * st);
-      if (++st == NS) { st = 0; ph ^= 1; }
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx_a(bars + Q_FULL, SM::Q_BYTES);
+      tma_load_3d_a(sQ, &p.mapQ, bars + Q_FULL, h * D, q0, b);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait_sleep(bars + KV_EMPTY + 8 * st, ph ^ 1);
+        trace_ev(p, 0, tcnt, j, 0);
+        mbar_arrive_expect_tx_a(bars + KV_FULL + 8 * st, SM::K_BYTES + SM::V_BYTES);
+        tma_load_3d_a(sK + st * SM::K_BYTES, &p.mapK, bars + KV_FULL + 8 * st, h * D, j * TK, b);
+        tma_load_3d_a(sV + st * SM::V_BYTES, &p.mapV, bars + KV_FULL + 8 * st, h * D, j * TK, b);
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
     }
-  } else if (warp == 4) {
+    __syncwarp();
+  } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TQ, TK);
       constexpr uint32_t idesc_o = umma_idesc_bf16(TQ, D) | (1u << 16);   // B (= V tile, [keys][D]) is MN-major
-      const uint64_t qdesc = umma_desc_sw128(sQ);
-      mbar_wait_a(bars + Q_FULL, 0);
+      const uint64_t qdesc = umma_desc_rows(sQ, SM::ROW, SM::LAYOUT);
+      mbar_wait_sleep(bars + Q_FULL, 0);
       int st_s = 0;                      // ring stage / phase of the next S tile
       uint32_t ph_s = 0;
       auto issue_s = [&](int j) {
-        mbar_wait_a(bars + KV_FULL + 8 * st_s, ph_s);
+        mbar_wait_sleep(bars + KV_FULL + 8 * st_s, ph_s);
         tc_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(sK + st_s * SM::K_BYTES);
+        trace_ev(p, 1, tcnt, j, 0);
+        const uint64_t kdesc = umma_desc_rows(sK + st_s * SM::K_BYTES, SM::ROW, SM::LAYOUT);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
           umma_bf16(tmem_base + S_COL + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
         umma_commit_a(bars + S_FULL + 8 * (j & 1));
+        trace_ev(p, 1, tcnt, j, 1);
         if (++st_s == NS) { st_s = 0; ph_s ^= 1; }
       };
       issue_s(0);
       int st = 0;
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);
-        mbar_wait_a(bars + P_FULL + 8 * (j & 1), (j >> 1) & 1);
+        mbar_wait_sleep(bars + P_FULL + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
+        trace_ev(p, 1, tcnt, j, 2);
         const uint64_t pdesc = umma_desc_sw128(sP + (j & 1) * SM::P_BYTES);
-        const uint64_t vdesc = umma_desc_sw128(sV + st * SM::V_BYTES);
+        const uint64_t vdesc = umma_desc_rows(sV + st * SM::V_BYTES, SM::ROW, SM::LAYOUT);
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k)
-          umma_bf16(tmem_base + O_COL + (j & 1) * 64, pdesc + 2 * k, vdesc + k * (16 * 128 >> 4), idesc_o, k != 0);   // 16 keys = 2048 B
+          umma_bf16(tmem_base + O_COL + (j & 1) * 64, pdesc + 2 * k, vdesc + k * (16 * SM::ROW >> 4), idesc_o, k != 0);   // 16 keys further down
         umma_commit_a(bars + KV_EMPTY + 8 * st);
         umma_commit_a(bars + O_FULL + 8 * (j & 1));
+        trace_ev(p, 1, tcnt, j, 3);
         if (++st == NS) st = 0;
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax: thread = query row
-    const int row = warp * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // ------------------------------------------------------------------ softmax: two threads per query row
+    // warps w and w + 4 share TMEM lane quarter w (hardware: quarter = warp id % 4); thread (w, lane) and thread
+    // (w + 4, lane) own row 32 w + lane and split every key tile (32 keys each) and the output columns (D/2 each).
+    // They exchange their partial row max through shared memory once per tile (named barrier per warp pair).
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     constexpr float LOG2E = 1.4426950408889634f;
+    constexpr int DH = D / 2;
     const float sl2 = p.scale * LOG2E;
     const int kvlen = p.kv_len ? __ldg(p.kv_len + b) : p.Lk;
     const int kvalid = min(kvlen, p.Lk);                 // keys below this index need no masking
     const float mask_raw = -10000.0f / p.scale;          // the reference's additive -10000 bias, in raw-score units
     float m = -INFINITY, l = 0.f, corr_pend = 0.f;
-    float o[D];
+    float o[DH];
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = 0.f;
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
     const uint32_t prow = row * 128;
     const int rsw = row & 7;
+    const uint32_t red_mine = red + (row * 2 + half) * 4, red_other = red + (row * 2 + (half ^ 1)) * 4;
 
     for (int j = 0; j < ntiles; ++j) {
       const int bs = j & 1;
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 0);
       mbar_wait_a(bars + S_FULL + 8 * bs, (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sa[32], sb[32];
-      tmem_ld32(t_lane + S_COL + bs * 64, sa);
-      tmem_ld32(t_lane + S_COL + bs * 64 + 32, sb);
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 1);
+      uint32_t sa[32];
+      tmem_ld32(t_lane + S_COL + bs * 64 + half * 32, sa);
       tmem_ld_wait();
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 2);
       if (j * TK + TK > kvalid) {                        // warp-uniform: this tile has masked / out-of-range keys
-        const int k0 = j * TK;
+        const int k0 = j * TK + half * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int ka = k0 + i, kb = k0 + 32 + i;
-          float va = __uint_as_float(sa[i]), vb = __uint_as_float(sb[i]);
+          const int ka = k0 + i;
+          float va = __uint_as_float(sa[i]);
           va = ka >= p.Lk ? -INFINITY : (ka >= kvlen ? va + mask_raw : va);
-          vb = kb >= p.Lk ? -INFINITY : (kb >= kvlen ? vb + mask_raw : vb);
           sa[i] = __float_as_uint(va);
-          sb[i] = __float_as_uint(vb);
         }
       }
-      float mx0 = __uint_as_float(sa[0]), mx1 = __uint_as_float(sa[1]), mx2 = __uint_as_float(sb[0]), mx3 = __uint_as_float(sb[1]);
+      float mx0 = __uint_as_float(sa[0]), mx1 = __uint_as_float(sa[1]);
+      float m_new = 1.0f;
+      if (!(p.dbg & 8)) {
 #pragma unroll
       for (int i = 2; i < 32; i += 4) {
         mx0 = fmax3(mx0, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
-        mx2 = fmax3(mx2, __uint_as_float(sb[i]), __uint_as_float(sb[i + 1]));
-        if (i + 3 < 32) {
-          mx1 = fmax3(mx1, __uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3]));
-          mx3 = fmax3(mx3, __uint_as_float(sb[i + 2]), __uint_as_float(sb[i + 3]));
-        }
+        if (i + 3 < 32) mx1 = fmax3(mx1, __uint_as_float(sa[i + 2]), __uint_as_float(sa[i + 3]));
       }
-      const float m_new = fmaxf(fmax3(m, mx0, mx1), fmaxf(mx2, mx3));   // finite: every tile has >= 1 key < Lk
+      const float mine = fmaxf(mx0, mx1);                // -inf if all 32 keys of this half are beyond Lk
+      sts_f32(red_mine + bs * 1024, mine);
+      pair_bar_sync(quad);
+      m_new = fmax3(m, mine, lds_f32(red_other + bs * 1024));   // finite: every tile has >= 1 key < Lk
+      }
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 3);
       const float corr = ex2f((m - m_new) * sl2);
       const float ms = m_new * sl2;
       m = m_new;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       const uint32_t pbox = sP + bs * SM::P_BYTES + prow;
+      if (!(p.dbg & 2))
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                      // 16-byte piece c = keys [8c, 8c+8) of this row
+      for (int c = 0; c < 4; ++c) {                      // 16-byte piece: keys [32 half + 8c, +8) of this row
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int i = (c & 3) * 8 + 2 * e;
-          const float x0 = __uint_as_float(c < 4 ? sa[i] : sb[i]), x1 = __uint_as_float(c < 4 ? sa[i + 1] : sb[i + 1]);
-          const float p0 = ex2f(fmaf(x0, sl2, -ms)), p1 = ex2f(fmaf(x1, sl2, -ms));
+          const int i = c * 8 + 2 * e;
+          float p0 = fmaf(__uint_as_float(sa[i]), sl2, -ms), p1 = fmaf(__uint_as_float(sa[i + 1]), sl2, -ms);
+          if (!(p.dbg & 1)) { p0 = ex2f(p0); p1 = ex2f(p1); }
           if (e & 1) { sum2 += p0; sum3 += p1; } else { sum0 += p0; sum1 += p1; }
           pk[e] = pack_bf16(p0, p1);
         }
-        sts128(pbox + ((c ^ rsw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        sts128(pbox + (((half * 4 + c) ^ rsw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
       }
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 4);
       fence_proxy_async();      // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
       tc_fence_before();        // the S loads above are complete: the issuer may overwrite this S buffer
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bars + P_FULL + 8 * bs);
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 5);
       l = fmaf(l, corr, (sum0 + sum1) + (sum2 + sum3));
       if (j > 0) {              // fold the previous tile's P.V (issued one tile ago) into the output row
         mbar_wait_a(bars + O_FULL + 8 * (bs ^ 1), ((j - 1) >> 1) & 1);
         tc_fence_after();
-        fold_pv<D>(o, corr_pend, t_lane + O_COL + (bs ^ 1) * 64);
+        if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 6);
+        if (!(p.dbg & 4)) fold_pv<DH>(o, corr_pend, t_lane + O_COL + (bs ^ 1) * 64 + half * DH);
       }
       corr_pend = corr;
+      if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 7);
     }
     {
       const int jl = ntiles - 1;
       mbar_wait_a(bars + O_FULL + 8 * (jl & 1), (jl >> 1) & 1);
       tc_fence_after();
-      fold_pv<D>(o, corr_pend, t_lane + O_COL + (jl & 1) * 64);
+      fold_pv<DH>(o, corr_pend, t_lane + O_COL + (jl & 1) * 64 + half * DH);
     }
+    // row sum = the two halves' partial sums (both are relative to the same running max)
+    sts_f32(red_mine + 2048, l);
+    pair_bar_sync(quad);
+    l += lds_f32(red_other + 2048);
     if (q0 + row < p.Lq) {
       const float inv = 1.0f / l;
-      __nv_bfloat16* O = reinterpret_cast<__nv_bfloat16*>(p.o) + b * p.bs_o + static_cast<size_t>(q0 + row) * p.ld_o + h * D;
+      __nv_bfloat16* O = reinterpret_cast<__nv_bfloat16*>(p.o) + b * p.bs_o + static_cast<size_t>(q0 + row) * p.ld_o + h * D + half * DH;
 #pragma unroll
-      for (int c = 0; c < D / 8; ++c)
+      for (int c = 0; c < DH / 8; ++c)
         *reinterpret_cast<uint4*>(O + c * 8) =
             make_uint4(pack_bf16(o[8 * c] * inv, o[8 * c + 1] * inv), pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
                        pack_bf16(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_bf16(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
@@ -340,13 +354,40 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const AttnP
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
 }
 
 bool g_att_init = false;
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  return fn;
+}
+
+// [rows x D] boxes of a bf16 operand laid out [B, L, ld] whose head h occupies columns [h*D, h*D + D)
+bool encode_rows(CUtensorMap* m, const void* base, int cols, int ld, int L, int B, long long bs, int D, int box_rows) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  const int db = D == 48 ? 64 : D;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(bs) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(db), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = db == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (db == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <int D>
 cudaError_t launch_d(const AttnParams& p, cudaStream_t st) {
@@ -370,7 +411,36 @@ cudaError_t attention_tc_init() {
   return cudaSuccess;
 }
 
-cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st) {
+bool attention_tc_prepare(AttnParams& p, const char** err) {
+  static const char* const msg_shape = "attention: unsupported shape / alignment for the TMA path";
+  static const char* const msg_enc = "attention: cuTensorMapEncodeTiled failed";
+  if ((p.D != 16 && p.D != 32 && p.D != 48 && p.D != 64) || p.Lq < 1 || p.Lk < 1 || p.B < 1 || p.H < 1 ||
+      (p.ld_q | p.ld_k | p.ld_v | p.ld_o) % 8 != 0 || (p.bs_q | p.bs_k | p.bs_v | p.bs_o) % 8 != 0 ||
+      (reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.k) | reinterpret_cast<uintptr_t>(p.v) |
+       reinterpret_cast<uintptr_t>(p.o)) % 16 != 0) {
+    if (err) *err = msg_shape;
+    return false;
+  }
+  const int cols = p.H * p.D;
+  if (!encode_rows(&p.mapQ, p.q, cols, p.ld_q, p.Lq, p.B, p.bs_q, p.D, TQ) ||
+      !encode_rows(&p.mapK, p.k, cols, p.ld_k, p.Lk, p.B, p.bs_k, p.D, TK) ||
+      !encode_rows(&p.mapV, p.v, cols, p.ld_v, p.Lk, p.B, p.bs_v, p.D, TK)) {
+    if (err) *err = msg_enc;
+    return false;
+  }
+  return true;
+}
+
+cudaError_t launch_attention_tc(const AttnParams& p_in, cudaStream_t st) {
+  AttnParams p = p_in;
+  {
+    static int dbg = -1;     // timing experiments only (DV_ATTN_DBG): 1 no ex2, 2 no exp loop / P store, 4 no fold, 8 no max / exchange
+    if (dbg < 0) {
+      const char* e = getenv("DV_ATTN_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
   if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
   if (!g_att_init) {
     cudaError_t e = attention_tc_init();

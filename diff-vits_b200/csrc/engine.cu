@@ -792,6 +792,8 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
       } else if (o.kind == OP_ATTN) {
         o.at.q = ws + o.ato.q; o.at.k = ws + o.ato.k; o.at.v = ws + o.ato.v; o.at.o = ws + o.ato.o;
         o.at.kv_len = nullptr;  // set in prompt_prepare
+        const char* ae = nullptr;
+        if (!attention_tc_prepare(o.at, &ae)) { err = std::string("attention_tc_prepare: ") + (ae ? ae : "?"); return false; }
       }
     }
     return true;

@@ -119,16 +119,22 @@ cudaError_t chain_tc_init();
 cudaError_t launch_chain_tc(const ChainParams& p, cudaStream_t st);
 
 // ------------------------------------------------------------------ attention (flash style, bf16 in, fp32 softmax)
-struct AttnParams {
+struct alignas(64) AttnParams {
+  CUtensorMap mapQ, mapK, mapV;                            // tcgen05 kernel: 3-D [H*D, L, B] maps (attention_tc_prepare)
   const void* q; const void* k; const void* v; void* o;   // bf16
   int ld_q, ld_k, ld_v, ld_o;                              // row strides in elements
   long long bs_q, bs_k, bs_v, bs_o;                        // batch strides in elements
   int B, H, Lq, Lk, D;
   float scale;                                             // D^-0.5
+  int dbg;             // set by launch_attention_tc (timing experiments)
+  unsigned long long* trace;   // debug: CTA (0,0,0) appends (role, tile, event, clock) records; [0] = record count
   const int* kv_len;   // per-batch number of un-masked keys (keys >= kv_len[b] get the -10000 bias), or nullptr
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);          // tcgen05 kernel (csrc/attention_tc.cu)
 cudaError_t attention_tc_init();                                            // kernel attributes (call outside graph capture)
+// Encodes mapQ/mapK/mapV from the pointers / strides / shape already stored in p (host only, no stream work). Must be
+// called whenever those change and before launch_attention_tc. Returns false with a message on failure.
+bool attention_tc_prepare(AttnParams& p, const char** err);
 cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st);
 cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st);   // mma.sync kernel (csrc/attention.cu)
 
