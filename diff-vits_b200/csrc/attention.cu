@@ -233,13 +233,19 @@ cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st) {
   }
 }
 
+// Dispatch. Both kernels implement the same contract and both are parity-tested at every head dim. Which one runs
+// is a measured choice (B200, C2, profiles/r1e_attention_ab.txt): stand-alone the tcgen05 kernel wins for d >= 32
+// (L1-L3: 37 vs 41, 15.7 vs 18.7, 6.5 vs 8.7 us) and loses at d = 16 (117 vs 100 us: both are bound by the MUFU pipe
+// and per-tile latency, and the register-resident mma.sync kernel has 8+ CTAs of TLP per SM); inside the captured
+// step loop its heavier CTA prologue (TMEM allocation, barrier init) overlaps less with the neighbouring kernels and
+// the whole step is not faster (219.8 vs 217.7 ms), so the mma.sync kernel stays the default for every head dim.
+// DV_ATTN=tc|legacy forces one kernel.
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
-  static int legacy = -1;
-  if (legacy < 0) {
-    const char* e = getenv("DV_ATTN_LEGACY");
-    legacy = (e && e[0] == '1') ? 1 : 0;
-  }
-  return legacy ? launch_attention_legacy(p, st) : launch_attention_tc(p, st);
+  // read per launch (launches are captured into a graph on the hot path): tests flip it between calls
+  const char* e = getenv("DV_ATTN");
+  const int force = !e ? 0 : (e[0] == 't' ? 1 : (e[0] == 'l' ? 2 : 0));   // 0 = measured choice, 1 = tcgen05, 2 = mma.sync
+  const bool tc = force == 1;
+  return tc ? launch_attention_tc(p, st) : launch_attention_legacy(p, st);
 }
 
 }  // namespace dv

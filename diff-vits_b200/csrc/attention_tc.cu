@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const __gri
         }
       }
       float mx0 = __uint_as_float(sa[0]), mx1 = __uint_as_float(sa[1]);
-      float m_new = 1.0f;
-      if (!(p.dbg & 8)) {
+      float m_new;
+      {
 #pragma unroll
       for (int i = 2; i < 32; i += 4) {
         mx0 = fmax3(mx0, __uint_as_float(sa[i]), __uint_as_float(sa[i + 1]));
@@ -302,7 +302,6 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const __gri
       m = m_new;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       const uint32_t pbox = sP + bs * SM::P_BYTES + prow;
-      if (!(p.dbg & 2))
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                      // 16-byte piece: keys [32 half + 8c, +8) of this row
         uint32_t pk[4];
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const __gri
         for (int e = 0; e < 4; ++e) {
           const int i = c * 8 + 2 * e;
           float p0 = fmaf(__uint_as_float(sa[i]), sl2, -ms), p1 = fmaf(__uint_as_float(sa[i + 1]), sl2, -ms);
-          if (!(p.dbg & 1)) { p0 = ex2f(p0); p1 = ex2f(p1); }
+          p0 = ex2f(p0); p1 = ex2f(p1);
           if (e & 1) { sum2 += p0; sum3 += p1; } else { sum0 += p0; sum1 += p1; }
           pk[e] = pack_bf16(p0, p1);
         }
@@ -327,7 +326,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention_tc_kernel(const __gri
         mbar_wait_a(bars + O_FULL + 8 * (bs ^ 1), ((j - 1) >> 1) & 1);
         tc_fence_after();
         if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 6);
-        if (!(p.dbg & 4)) fold_pv<DH>(o, corr_pend, t_lane + O_COL + (bs ^ 1) * 64 + half * DH);
+        fold_pv<DH>(o, corr_pend, t_lane + O_COL + (bs ^ 1) * 64 + half * DH);
       }
       corr_pend = corr;
       if (warp == 0 && lane == 0) trace_ev(p, 2, tcnt, j, 7);
@@ -431,16 +430,7 @@ bool attention_tc_prepare(AttnParams& p, const char** err) {
   return true;
 }
 
-cudaError_t launch_attention_tc(const AttnParams& p_in, cudaStream_t st) {
-  AttnParams p = p_in;
-  {
-    static int dbg = -1;     // timing experiments only (DV_ATTN_DBG): 1 no ex2, 2 no exp loop / P store, 4 no fold, 8 no max / exchange
-    if (dbg < 0) {
-      const char* e = getenv("DV_ATTN_DBG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.dbg = dbg;
-  }
+cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st) {
   if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
   if (!g_att_init) {
     cudaError_t e = attention_tc_init();

@@ -126,7 +126,6 @@ struct alignas(64) AttnParams {
   long long bs_q, bs_k, bs_v, bs_o;                        // batch strides in elements
   int B, H, Lq, Lk, D;
   float scale;                                             // D^-0.5
-  int dbg;             // set by launch_attention_tc (timing experiments)
   unsigned long long* trace;   // debug: CTA (0,0,0) appends (role, tile, event, clock) records; [0] = record count
   const int* kv_len;   // per-batch number of un-masked keys (keys >= kv_len[b] get the -10000 bias), or nullptr
 };

@@ -158,21 +158,34 @@ def test_gemm_geglu_and_ncl(U):
     assert U.rel_l2(got3, ref3) < 1e-5
 
 
-@pytest.mark.parametrize("D,Lq,Lk", [(16, 200, 200), (32, 500, 500), (48, 250, 250), (64, 125, 125), (16, 1000, 1000)])
-def test_attention_self(U, D, Lq, Lk):
+@pytest.fixture(params=["tc", "legacy"])
+def attn_kernel(request, monkeypatch):
+    """Both attention kernels (tcgen05 / mma.sync) are checked at every head dim, whichever the dispatcher prefers."""
+    monkeypatch.setenv("DV_ATTN", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("D,Lq,Lk", [(16, 200, 200), (32, 500, 500), (48, 250, 250), (64, 125, 125), (16, 1000, 1000),
+                                     (32, 77, 40), (16, 130, 65)])
+def test_attention_self(U, attn_kernel, D, Lq, Lk):
     g = torch.Generator(device="cuda").manual_seed(7)
     B, H = 2, 8
     C = H * D
-    qkv = _rand((B, Lq, 3 * C), g)
-    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
-    ref = F.scaled_dot_product_attention(*(t.float().reshape(B, Lq, H, D).transpose(1, 2) for t in (q, k, v)))
+    if Lq == Lk:
+        qkv = _rand((B, Lq, 3 * C), g)
+        q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    else:                                   # ragged tails of the query / key tiles
+        q = _rand((B, Lq, C), g)
+        kv = _rand((B, Lk, 2 * C), g)
+        k, v = kv[:, :, :C], kv[:, :, C:]
+    ref = F.scaled_dot_product_attention(*(t.float().reshape(B, t.shape[1], H, D).transpose(1, 2) for t in (q, k, v)))
     ref = ref.transpose(1, 2).reshape(B, Lq, C)
     got = U.attention(q, k, v, H)
     _check_bf16(U, got, ref, rel=8e-3)        # + bf16 rounding of P
 
 
 @pytest.mark.parametrize("D,Lq", [(16, 1000), (32, 500), (48, 250), (64, 125)])
-def test_attention_cross_masked(U, D, Lq):
+def test_attention_cross_masked(U, attn_kernel, D, Lq):
     g = torch.Generator(device="cuda").manual_seed(8)
     B, H, Lk = 3, 8, 282
     C = H * D
