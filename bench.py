@@ -139,6 +139,17 @@ def cpu_sample_run(B: int, T: int, Tp: int, sampler: str, steps_total: int, step
     return dt, (B * T) / (per_call * steps_total)
 
 
+def pick_cpu_sample(Bg: int, T: int, Tp: int, sampler: str, nfe: int, threads: int, target_s: float):
+    """Bounded sample of the workload for the CPU arms: up to 8 utterances and as many solver steps (>= 2) as fit in
+    about `target_s` seconds of CPU work on this host; the one-step probe doubles as the library warm-up."""
+    Bs = min(Bg, 8)
+    cpu_sample_run(Bs, T, Tp, sampler, nfe, 1, threads)     # first touch of the CPU libraries / allocator
+    _, fps1 = cpu_sample_run(Bs, T, Tp, sampler, nfe, 1, threads)
+    per_step = (Bs * T) / (fps1 * nfe)                   # seconds per solver step (= per denoiser call + update)
+    steps_run = max(2, min(nfe, int(target_s / max(per_step, 1e-3))))
+    return Bs, steps_run
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path, timed on this host's cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -146,9 +157,10 @@ def run_reference(args):
         return
     Bg, T, Tp, sampler, nfe, desc = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    Bs, steps_run = min(Bg, 4), 2
+    # each timed step is a bounded sample (~10 s of CPU work); warm-up steps are short two-step loops
+    Bs, steps_run = pick_cpu_sample(Bg, T, Tp, sampler, nfe, threads, target_s=10.0)
     for _ in range(args.warmup):
-        cpu_sample_run(Bs, T, Tp, sampler, nfe, steps_run, threads)
+        cpu_sample_run(Bs, T, Tp, sampler, nfe, 2, threads)
     secs, fps = [], []
     for _ in range(args.steps):
         dt, f = cpu_sample_run(Bs, T, Tp, sampler, nfe, steps_run, threads)
@@ -348,8 +360,7 @@ def run_native(args):
     if rank == 0:
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            Bs, steps_run = min(Bg, 4), 2
-            cpu_sample_run(1, min(T, 200), Tp, sampler, nfe, 1, threads)     # warm the CPU libraries
+            Bs, steps_run = pick_cpu_sample(Bg, T, Tp, sampler, nfe, threads, target_s=15.0)
             dt, fps = cpu_sample_run(Bs, T, Tp, sampler, nfe, steps_run, threads)
             line["cpu_baseline"] = {
                 "value": fps, "unit": "frames/s", "cores": threads, "kind": "port",

@@ -819,9 +819,13 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
 int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches,
                       cudaEvent_t* events) {
   int idx = 0;
+  // DV_SKIP_KINDS (timing experiments only, results are garbage): bit k set = do not launch ops of OpKind k, so the
+  // step-time difference is that kernel class's marginal cost inside the captured loop
+  static const int skip_kinds = [] { const char* e = getenv("DV_SKIP_KINDS"); return e ? atoi(e) : 0; }();
   for (Op& o : list) {
     if (events) cudaEventRecordWithFlags(events[idx++], st, cudaEventRecordExternal);
     cudaError_t e = cudaSuccess;
+    if (skip_kinds & (1 << o.kind)) { if (launches) ++*launches; continue; }
     switch (o.kind) {
       case OP_GEMM:
         if (o.g.out_dynamic) {
