@@ -90,6 +90,18 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
     }
   }
   pdl_wait();
+  // first batch of rows: issued before the statistics are reduced, so the two global round trips overlap
+  constexpr int UNR = 4;                                     // rows in flight per thread
+  const int lbeg = blockIdx.x * rows_per_cta;
+  const int lend = min(lbeg + rows_per_cta, p.L);
+  uint4 v[UNR];
+  if (r < R) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int l = lbeg + r + u * R;
+      v[u] = l < lend ? __ldg(gn_src(p, b, l, cbase)) : make_uint4(0, 0, 0, 0);
+    }
+  }
   // ---- group statistics: one warp per group; the (block, chunk, fold) index space is flattened over the lanes so
   // every load of the warp is independent; fixed lane assignment + fixed shuffle tree: deterministic.
   for (int g = warp; g < p.G; g += NT / 32) {
@@ -140,8 +152,6 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
   }
   __syncthreads();
   if (r >= R) return;
-  const int lbeg = blockIdx.x * rows_per_cta;
-  const int lend = min(lbeg + rows_per_cta, p.L);
   const int grp = cbase / cpg;
   const float mean = s_mean[grp], rstd = s_rstd[grp];
   float ca[8], cb[8];
@@ -168,13 +178,13 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
     }
   }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  constexpr int UNR = 4;                                     // rows in flight per thread
   for (int l0 = lbeg + r; l0 < lend; l0 += UNR * R) {
-    uint4 v[UNR];
+    if (l0 != lbeg + r) {                                    // later batches (rows_per_cta > UNR * R only)
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int l = l0 + u * R;
-      v[u] = l < lend ? __ldg(gn_src(p, b, l, cbase)) : make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < UNR; ++u) {
+        const int l = l0 + u * R;
+        v[u] = l < lend ? __ldg(gn_src(p, b, l, cbase)) : make_uint4(0, 0, 0, 0);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
