@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(512) temb_mlp_kernel(const TembParams p) {
     for (int k = lane; k < p.sin_dim; k += 32) acc += __ldg(p.w1 + static_cast<size_t>(o) * p.sin_dim + k) * e[k];
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-    if (lane == 0) h[o] = silu_fp32_f(acc + p.b1[o]);
+    if (lane == 0) h[o] = silu_f(acc + p.b1[o]);
   }
   __syncthreads();
   for (int oo = warp; oo < 32; oo += 16) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(const TembParams p) {
     if (bb < nb) {
       v = p.emb_base[static_cast<size_t>(p.t_stride ? (b0 + bb) : 0) * 512 + k];
       if (p.aug) v += p.aug[static_cast<size_t>(b0 + bb) * 512 + k];
-      v = silu_fp32_f(v);
+      v = silu_f(v);
     }
     es[bb][k] = v;
   }

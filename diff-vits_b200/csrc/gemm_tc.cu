@@ -81,7 +81,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = i * 8 + e.srow;
-      rv[i] = (lq + r < p.L) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
+      rv[i] = (lq + r < p.L && !(p.dbg_flags & 16)) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
                              : make_uint4(0, 0, 0, 0);
     }
   }
@@ -140,7 +140,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rrow = i * 8 + e.srow;
-    if (lq + rrow < p.L)
+    if (lq + rrow < p.L && !(p.dbg_flags & 8))
       *reinterpret_cast<uint4*>(out + (rowbase + lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
           lds128(e.coal + i * 8 * EPI_PITCH);
   }

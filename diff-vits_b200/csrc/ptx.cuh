@@ -223,39 +223,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
-// SiLU with ONE MUFU op: x * sigmoid(x) = h + h * tanh(h), h = x / 2 (MUFU.TANH, relative error ~2^-11; the result
-// is stored as bf16, 2^-9). The ex2 + rcp form costs two MUFU ops per element, and the GroupNorm-apply kernels are
-// otherwise pure streaming kernels: at 16 MUFU / clk / SM that was half of their run time.
+// SiLU with approximate MUFU ops (2 ulp class, output is stored as bf16): x * rcp(1 + 2^(-x log2 e)). A one-MUFU
+// form (h + h tanh(h), h = x/2) was measured 1 % faster per denoiser call but cancels in the negative tail
+// (|error| ~1e-3 at x = -4, 6x the bf16 step) and tripled the first-resnet parity error: not kept.
 __device__ __forceinline__ float silu_f(float x) {
-  const float h = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-// fp32-class SiLU for the time-embedding MLP (a handful of values, feeds every resnet): x * rcp(1 + 2^(-x log2 e))
-__device__ __forceinline__ float silu_fp32_f(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7 on erf): one rcp, one ex2 and a
-// degree-5 Horner chain instead of erff's branchy ~35 instructions. 1 + erf(z) is formed without cancellation
-// (z < 0: 1 + erf = poly * exp(-z^2)), so the negative tail keeps full relative accuracy. Output is stored as bf16.
+// GELU(x) = x * Phi(x) (the erf form F.gelu computes) as x * sigmoid(2 q(x)), q an odd degree-5 polynomial fitted to
+// atanh(erf(x / sqrt 2)) on [-8, 8] (minimax, |error| <= 2.6e-5 absolute over the whole real line, ~100x below the
+// bf16 rounding of the stored product): 10 instructions, two of them MUFU (ex2, rcp), no cancellation in the
+// negative tail. The GEGLU epilogues are bound by instruction issue, not by the tensor pipe, at K <= 256: this form
+// replaced a 16-instruction Abramowitz-Stegun erf. log2(e) and the factor 2 are folded into the coefficients.
 __device__ __forceinline__ float gelu_fast_f(float x) {
-  // branch free: MUFU.RCP / MUFU.EX2 (approx, ftz) + 6 FMA-pipe operations; exp(-z^2) = 2^(x^2 * -log2(e)/2)
-  const float az = fabsf(x) * 0.70710678118654752440f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float pe = poly * t * e;
-  const float one_plus_erf = x >= 0.f ? 2.0f - pe : pe;
-  return 0.5f * x * one_plus_erf;
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);          // the polynomial is only monotone on the fitted range
+  const float x2 = xc * xc;
+  float p = fmaf(1.0142649989575148e-3f, x2, -0.10677573829889297f);
+  p = fmaf(p, x2, -2.301121234893799f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * p));   // = exp(-2 q(x))
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 // packed fp32x2 arithmetic (sm_100): one instruction for two lanes of an accumulator pair
 __device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
