@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
             const float var = ((lds_f32(red + 2048) + lds_f32(red + 2052)) + (lds_f32(red + 2056) + lds_f32(red + 2060))) * (1.0f / C);
             rstd = rsqrtf(var + st.eps);
           }
-          mbar_wait_a(bars + X_FREE, (x_ver & 1) ^ 1);     // the tensor core is done reading the previous X
+          __nv_bfloat16* out2 = reinterpret_cast<__nv_bfloat16*>(st.out2);
+          if (!out2) mbar_wait_a(bars + X_FREE, (x_ver & 1) ^ 1);     // the tensor core is done reading the previous X
 #pragma unroll 1
           for (int i = 0; i < U; ++i) {
             const int ch = part + 4 * i;
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
               tc_fence_before();
               if (lane == 0) mbar_arrive_a(bars + MAIN_EMPTY);
             }
+            uint32_t packed[16];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               float v[8];
@@ -416,15 +418,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
                 v[4] = (v[4] - mean) * rstd * g1.x + b1.x; v[5] = (v[5] - mean) * rstd * g1.y + b1.y;
                 v[6] = (v[6] - mean) * rstd * g1.z + b1.z; v[7] = (v[7] - mean) * rstd * g1.w + b1.w;
               }
-              sts128(box_addr(box, row, (ch & 1) * 4 + jj),
-                     make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7])));
+              packed[4 * jj] = pack_bf16(v[0], v[1]); packed[4 * jj + 1] = pack_bf16(v[2], v[3]);
+              packed[4 * jj + 2] = pack_bf16(v[4], v[5]); packed[4 * jj + 3] = pack_bf16(v[6], v[7]);
+              if (!out2)
+                sts128(box_addr(box, row, (ch & 1) * 4 + jj),
+                       make_uint4(packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]));
             }
+            if (out2) store_chunk(sl, out2, st.ld_out2, row0, rows_left, ch * 32, packed);
           }
           ++main_use;
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_a(bars + X_READY);
-          ++x_ver;
+          if (!out2) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(bars + X_READY);
+            ++x_ver;
+          }
         } else if (st.kind == CH_STREAM) {
           const int units = st.n >> 7;
           const size_t stat_chunk = (static_cast<size_t>(b) * p.tiles_per_batch + mt) * 4 + quad;
@@ -594,7 +602,8 @@ cudaError_t launch_chain_tc(const ChainParams& p, cudaStream_t st) {
   for (int s = 0; s < p.nstages; ++s) {
     const ChainStage& cs = p.st[s];
     const bool reads_x = cs.kind != CH_ROW || cs.a_map < 0;
-    const bool writes_x = cs.kind != CH_STREAM;
+    const bool writes_x = cs.kind == CH_FF || (cs.kind == CH_ROW && !cs.out2);
+    if (cs.out2 && cs.kind != CH_ROW) return cudaErrorInvalidValue;
     if (reads_x && !x_live) return cudaErrorInvalidValue;
     if (!reads_x && x_live) return cudaErrorInvalidValue;
     x_live = writes_x;

@@ -262,13 +262,28 @@ struct Builder {
     TRef g = tmp(L, C);
     emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
     TRef z = tmp(L, C);
-    linear(P.ops, pfx + ".proj_in", g, "linear", {pfx + ".proj_in.weight"}, pfx + ".proj_in.bias", C, TRef(), z,
-           GEMM_OUT_BF16);
     TRef nrm = tmp(L, C);
     TRef qkv = tmp(L, 3 * C);
     TRef ao = tmp(L, C);
+    // A projection whose output row fits one CTA's TMEM accumulator (C <= 384) takes the LayerNorm that follows it
+    // along as a one-stage chain (csrc/chain_tc.cu, CH_ROW with a global LayerNorm output): one launch instead of two.
+    const bool ln_fused = P.fuse_ln && C % 128 == 0 && C <= 384;
+    auto proj_ln = [&](const std::string& tag, TRef a, const std::string& wkey, const std::string& bkey, TRef res,
+                       const std::string& lnkey) {
+      if (!ln_fused) {
+        linear(P.ops, tag, a, "linear", {wkey}, bkey, C, res, z, GEMM_OUT_BF16);
+        emit_ln(P.ops, lnkey, z, lnkey, nrm);
+        return;
+      }
+      Op& o = emit_chain(tag + "+ln", L, C);
+      ChainDesc& c = o.ch;
+      c.nstages = 1;
+      c.st[0].kind = CH_ROW; c.st[0].a = a; c.st[0].res = res; c.st[0].out = z; c.st[0].out2 = nrm;
+      set_w(c.st[0], tag, "linear", {wkey}, bkey, C, C);
+      set_ln(c.st[0], lnkey, C);
+    };
     // --- self attention
-    emit_ln(P.ops, tb + ".norm1", z, tb + ".norm1", nrm);
+    proj_ln(pfx + ".proj_in", g, pfx + ".proj_in.weight", pfx + ".proj_in.bias", TRef(), tb + ".norm1");
     linear(P.ops, tb + ".attn1.qkv", nrm, "linear",
            {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, "", 3 * C, TRef(), qkv,
            GEMM_OUT_BF16);
@@ -284,15 +299,13 @@ struct Builder {
       o.at.scale = 1.0f / sqrtf(static_cast<float>(D));
       P.ops.push_back(o);
     }
-    linear(P.ops, tb + ".attn1.to_out", ao, "linear", {tb + ".attn1.to_out.0.weight"}, tb + ".attn1.to_out.0.bias", C, z,
-           z, GEMM_OUT_BF16);
+    proj_ln(tb + ".attn1.to_out", ao, tb + ".attn1.to_out.0.weight", tb + ".attn1.to_out.0.bias", z, tb + ".norm2");
     // --- cross attention to the prompt (K/V hoisted into prep_ops)
     TRef kv;
     kv.L = P.Tp; kv.C = 2 * C;
     kv.off = ws_alloc(static_cast<size_t>(P.B) * P.Tp * 2 * C * 2);
     linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
            2 * C, TRef(), kv, GEMM_OUT_BF16);
-    emit_ln(P.ops, tb + ".norm2", z, tb + ".norm2", nrm);
     TRef q = qkv;  // reuse the first C columns' storage as a dense [L, C] tensor
     q.C = C;
     linear(P.ops, tb + ".attn2.to_q", nrm, "linear", {tb + ".attn2.to_q.weight"}, "", C, TRef(), q, GEMM_OUT_BF16);
@@ -309,10 +322,8 @@ struct Builder {
       o.at.scale = 1.0f / sqrtf(static_cast<float>(D));
       P.ops.push_back(o);
     }
-    linear(P.ops, tb + ".attn2.to_out", ao, "linear", {tb + ".attn2.to_out.0.weight"}, tb + ".attn2.to_out.0.bias", C, z,
-           z, GEMM_OUT_BF16);
+    proj_ln(tb + ".attn2.to_out", ao, tb + ".attn2.to_out.0.weight", tb + ".attn2.to_out.0.bias", z, tb + ".norm3");
     // --- GEGLU feed-forward
-    emit_ln(P.ops, tb + ".norm3", z, tb + ".norm3", nrm);
     TRef gg = tmp(L, 4 * C);
     linear(P.ops, tb + ".ff.geglu", nrm, "geglu", {tb + ".ff.net.0.proj.weight"}, tb + ".ff.net.0.proj.bias", 8 * C,
            TRef(), gg, GEMM_OUT_GEGLU);
@@ -510,6 +521,7 @@ int Plan::build(std::string& err) {
   {
     const char* fe = getenv("DV_FUSE");
     fuse = !(fe && fe[0] == '0');
+    { const char* fl = getenv("DV_FUSE_LN"); fuse_ln = fl && fl[0] == '1'; }
     const char* fm = getenv("DV_FUSE_MAXC");
     fuse_max_c = fm ? atoi(fm) : 128;
   }
@@ -622,6 +634,7 @@ int Plan::build(std::string& err) {
             if (sd.a.valid()) fix(sd.a.off);
             if (sd.res.valid()) fix(sd.res.off);
             if (sd.out.valid()) fix(sd.out.off);
+            if (sd.out2.valid()) fix(sd.out2.off);
           }
           break;
         case OP_ATTN: {
@@ -771,6 +784,8 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
           cs.ld_res = sd.res.valid() ? sd.res.C : 0;
           cs.out = sd.out.valid() ? ws + sd.out.off : nullptr;
           cs.ld_out = sd.out.valid() ? sd.out.C : 0;
+          cs.out2 = sd.out2.valid() ? ws + sd.out2.off : nullptr;
+          cs.ld_out2 = sd.out2.valid() ? sd.out2.C : 0;
           cs.gamma = pf(sd.gamma); cs.beta = pf(sd.beta); cs.eps = sd.eps;
           cs.stats = sd.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + sd.stats_off) : nullptr;
           cs.stats_nblk = sd.stats_nblk;

@@ -54,6 +54,7 @@ struct ChainStageDesc {
   int n = 0;
   long long bias_off = -1, bias2_off = -1;
   TRef res, out;
+  TRef out2;                       // CH_ROW: LayerNorm result to global instead of the X buffer
   long long gamma = -1, beta = -1;
   float eps = 1e-5f;
   long long stats_off = -1;
@@ -88,6 +89,9 @@ struct Plan {
   // the chain wins or ties while a level has >= ~1.5 row tiles per SM (C = 128: 250 tiles); deeper levels have too few
   // 128-row tiles (125 / 63) to fill 148 SMs with one CTA per tile, there the one-kernel-per-op program is faster.
   int fuse_max_c = 128;
+  bool fuse_ln = false;      // DV_FUSE_LN=1: projection + following LayerNorm as a one-stage chain where C <= 384. Measured
+                             // slower on C2 (4.62 vs 4.34 ms per call: one 128-row tile per CTA with a three-pass epilogue loses to
+                             // an N-split GEMM + a streaming LayerNorm), so it is off; kept parity-tested for wider-N shapes.
   bool fuse = true;          // transformer sections as chained-GEMM kernels (DV_FUSE=0 selects the one-kernel-per-op program)
   std::vector<ParamSlot> slots;
   size_t param_bytes = 0, ws_bytes = 0;

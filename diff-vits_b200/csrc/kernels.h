@@ -78,6 +78,7 @@ cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const v
 // One persistent kernel runs a short program of row-local GEMMs of a transformer block over 128-row tiles, keeping
 // the activations between them in shared memory / TMEM instead of HBM:
 //   CH_ROW    : D[128, C] = A . W^T (+bias) (+res)  -> bf16 global (optional) -> LayerNorm (or plain copy) -> X (smem)
+//               (or -> global `out2`: the last stage of a chain, e.g. proj_in + LayerNorm as ONE launch)
 //               A is streamed from global by TMA (a_map >= 0) or is the X buffer (a_map < 0).
 //   CH_STREAM : out[128, n] = X . W^T (+bias) (+res) -> bf16 global (+GroupNorm partials), 128 columns at a time
 //   CH_FF     : GEGLU feed-forward: for each 64 hidden units  h = u * gelu(g), [u|g] = X . W1_chunk^T + b1 ; the bf16
@@ -102,6 +103,8 @@ struct ChainStage {
   const float* gamma;     // CH_ROW: LayerNorm affine (null = copy the bf16 result to X unchanged)
   const float* beta;
   float eps;
+  void* out2;             // CH_ROW: if set, the (normalised) row goes to global bf16 [B, L, ld_out2] instead of X:
+  int ld_out2;            //         a GEMM with the LayerNorm of its own output fused in, as a one-stage chain
   float* stats;           // CH_STREAM: GroupNorm partials of the stored tensor (layout as GemmParams::stats) or null
   int stats_nblk;
 };

@@ -63,6 +63,28 @@ def test_fused_blocks_match_unfused(unet, B, T, Tp):
     assert U.rel_l2(outs[0], outs[1]) < 2e-2
 
 
+def test_projection_layernorm_chain_matches_separate_kernels(unet, monkeypatch):
+    """DV_FUSE_LN=1: proj_in / to_out + the LayerNorm that follows as a one-stage chain (CH_ROW with a global LayerNorm
+    output) at the levels the full chain does not cover (C = 256, 384)."""
+    import gpu_util as U
+    from oracle import inputs
+    B, T, Tp = 2, 200, 40
+    x, cond, ehs = (t.cuda() for t in inputs.make_inputs(B, T, Tp, seed=13))
+    t = torch.tensor([250.0], device="cuda")
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DV_FUSE_LN", flag)
+        eng = _engine(unet, B, T, Tp, False)
+        tags = [o["tag"] for o in eng.op_table()]
+        assert any(tg.endswith("+ln") for tg in tags) == (flag == "1")
+        eng.prepare_prompt(ehs)
+        eng.set_cond(cond)
+        outs.append(eng.forward(x, t, x_only=True).clone())
+        torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all()
+    assert U.rel_l2(outs[0], outs[1]) < 2e-2
+
+
 def test_fused_deterministic(unet):
     from oracle import inputs
     B, T, Tp = 2, 200, 40
