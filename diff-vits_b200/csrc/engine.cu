@@ -534,7 +534,7 @@ int Plan::build(std::string& err) {
   b.ehs_bf16.off = b.ws_alloc(static_cast<size_t>(B) * Tp * c.cross_attention_dim * 2);
   off_ehs = b.ehs_bf16.off;
   off_aug = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4);
-  off_embact = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4);
+  off_embact = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4 * 2);          // two time-table slots
   off_kvlen = b.ws_alloc(static_cast<size_t>(B) * 4);
   const size_t xbytes = static_cast<size_t>(B) * c.x_channels * T * 4;
   const size_t obytes = static_cast<size_t>(B) * c.out_channels * T * 4;
@@ -608,7 +608,7 @@ int Plan::build(std::string& err) {
   n_all = b.ss_cur;
   p_wall = b.slot("time.w_all_t", "rows_t", b.wall_keys, "f32", {emb_dim, n_all});
   p_ball = b.slot("time.b_all", "rows", b.ball_keys, "f32", {n_all});
-  off_ss = b.ws_alloc(static_cast<size_t>(B) * n_all * 4);
+  off_ss = b.ws_alloc(static_cast<size_t>(B) * n_all * 4 * 2);                // two time-table slots
   off_stats = b.ws_alloc(stats_bytes);
   const size_t scratch_base = b.ws_alloc(b.scratch_max);
   ws_bytes = align_up(b.ws_cur, 1024);
@@ -832,7 +832,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
   } while (0)
 
 int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches,
-                      cudaEvent_t* events) {
+                      cudaEvent_t* events, int ss_slot) {
   int idx = 0;
   // DV_SKIP_KINDS (timing experiments only, results are garbage): bit k set = do not launch ops of OpKind k, so the
   // step-time difference is that kernel class's marginal cost inside the captured loop
@@ -852,7 +852,15 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
         }
         break;
       case OP_CHAIN: e = launch_chain_tc(o.cp, st); break;
-      case OP_GN_APPLY: e = launch_gn_apply(o.gn, st); break;
+      case OP_GN_APPLY:
+        if (ss_slot && o.gn.scale_shift) {
+          GnParams g = o.gn;
+          g.scale_shift += static_cast<size_t>(ss_slot) * B * n_all;
+          e = launch_gn_apply(g, st);
+        } else {
+          e = launch_gn_apply(o.gn, st);
+        }
+        break;
       case OP_LN: e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st); break;
       case OP_ATTN: {
         AttnParams a = o.at;
@@ -937,24 +945,33 @@ int Plan::profile_forward(const float* sample, int x_only, const float* t, int t
   return DV_OK;
 }
 
-int Plan::forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
-                  std::string& err, int* launches, cudaEvent_t* events) {
-  if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
-  if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
-  DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st));
+int Plan::enqueue_time_tables(const float* t, int t_stride, int slot, cudaStream_t st, std::string& err) {
   TembParams tp;
   tp.t = t; tp.t_stride = t_stride;
   tp.freqs = reinterpret_cast<const float*>(params + p_freqs);
   tp.w1 = reinterpret_cast<const float*>(params + p_w1); tp.b1 = reinterpret_cast<const float*>(params + p_b1);
   tp.w2 = reinterpret_cast<const float*>(params + p_w2); tp.b2 = reinterpret_cast<const float*>(params + p_b2);
   tp.aug = has_aug ? reinterpret_cast<const float*>(ws + off_aug) : nullptr;
-  tp.emb_base = reinterpret_cast<float*>(ws + off_embact);
+  tp.emb_base = reinterpret_cast<float*>(ws + off_embact) + static_cast<size_t>(slot) * B * emb_dim;
   tp.w_all = reinterpret_cast<const float*>(params + p_wall); tp.b_all = reinterpret_cast<const float*>(params + p_ball);
-  tp.ss_all = reinterpret_cast<float*>(ws + off_ss);
+  tp.ss_all = reinterpret_cast<float*>(ws + off_ss) + static_cast<size_t>(slot) * B * n_all;
   tp.B = B; tp.n_all = n_all; tp.sin_dim = cfg.block_out_channels[0]; tp.emb_dim = emb_dim;
   DV_CK(launch_temb(tp, st));
+  return DV_OK;
+}
+
+int Plan::forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
+                  std::string& err, int* launches, cudaEvent_t* events, int tables_slot) {
+  if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
+  if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
+  DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st));
+  if (tables_slot < 0) {
+    int rc = enqueue_time_tables(t, t_stride, 0, st, err);
+    if (rc != DV_OK) return rc;
+    tables_slot = 0;
+  }
   if (launches) *launches += 3;
-  return enqueue_ops(ops, out, st, err, launches, events);
+  return enqueue_ops(ops, out, st, err, launches, events, tables_slot);
 }
 
 static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -973,7 +990,43 @@ int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cuda
   float* H[2] = {reinterpret_cast<float*>(ws + off_h0), reinterpret_cast<float*>(ws + off_h1)};
   const float* ttab = reinterpret_cast<const float*>(ws + off_ttab);
   int cur = 0;  // H[cur] = newest model output m_{-1}, H[cur^1] = m_{-2}
-  int rc = forward(X, 1, ttab, 0, H[cur], s, err, launches);
+  // Denoiser calls of the loop in order: call 0 at ttab[0], then one at ttab[i+1] for every step that evaluates the
+  // model. The time tables of call k+1 depend on t only: they are computed on a side stream while call k runs.
+  std::vector<int> tcall(1, 0);
+  for (int i = 0; i < nsteps; ++i) {
+    const float* c = coef + static_cast<size_t>(i) * 8;
+    const bool evals = sampler == DV_SAMPLER_DPMPP_2M ? (i != nsteps - 1) : (c[6] != 0.f);
+    if (evals) tcall.push_back(i + 1);
+  }
+  static const bool ahead = [] { const char* e = getenv("DV_TABLES_AHEAD"); return !(e && e[0] == '0'); }();
+  if (ahead) {
+    if (!side_stream) DV_CK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    if (!ev_tfork) DV_CK(cudaEventCreateWithFlags(&ev_tfork, cudaEventDisableTiming));
+    if (!ev_tjoin) DV_CK(cudaEventCreateWithFlags(&ev_tjoin, cudaEventDisableTiming));
+  }
+  size_t kcall = 0;
+  int rc = DV_OK;
+  // model(x, call k) -> dst. Tables of call k are in slot k & 1 (call 0: computed inline first).
+  auto model = [&](const float* xin, float* dst) -> int {
+    if (!ahead) return forward(xin, 1, ttab + tcall[kcall++], 0, dst, s, err, launches);
+    const int slot = static_cast<int>(kcall & 1);
+    if (kcall == 0) {
+      int r0 = enqueue_time_tables(ttab + tcall[0], 0, 0, s, err);
+      if (r0 != DV_OK) return r0;
+    } else {
+      DV_CK(cudaStreamWaitEvent(s, ev_tjoin, 0));            // tables of this call (side stream) are complete
+    }
+    if (kcall + 1 < tcall.size()) {                         // fork: next call's tables into the other slot
+      DV_CK(cudaEventRecord(ev_tfork, s));                   // after the previous call's last reader of that slot
+      DV_CK(cudaStreamWaitEvent(side_stream, ev_tfork, 0));
+      int r1 = enqueue_time_tables(ttab + tcall[kcall + 1], 0, slot ^ 1, side_stream, err);
+      if (r1 != DV_OK) return r1;
+      DV_CK(cudaEventRecord(ev_tjoin, side_stream));
+    }
+    ++kcall;
+    return forward(xin, 1, nullptr, 0, dst, s, err, launches, nullptr, slot);
+  };
+  rc = model(X, H[cur]);
   if (rc != DV_OK) return rc;
   for (int i = 0; i < nsteps; ++i) {
     const float* c = coef + static_cast<size_t>(i) * 8;
@@ -984,7 +1037,7 @@ int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cuda
       ++*launches;
       if (!last) {
         cur ^= 1;
-        rc = forward(X, 1, ttab + i + 1, 0, H[cur], s, err, launches);
+        rc = model(X, H[cur]);
         if (rc != DV_OK) return rc;
       }
     } else {
@@ -993,7 +1046,7 @@ int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cuda
         if (last) { err = "UniPC table: corrector on the last step"; return DV_ERR_INVALID; }
         DV_CK(launch_unipc_pred(XP, BASE, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
         ++*launches;
-        rc = forward(XP, 1, ttab + i + 1, 0, H[cur ^ 1], s, err, launches);  // m_t overwrites the consumed m_{-2}
+        rc = model(XP, H[cur ^ 1]);  // m_t overwrites the consumed m_{-2}
         if (rc != DV_OK) return rc;
         DV_CK(launch_unipc_corr(X, BASE, H[cur ^ 1], H[cur], c[4], n, s));
         ++*launches;
@@ -1104,6 +1157,9 @@ Plan::~Plan() {
   if (cap_stream) cudaStreamDestroy(cap_stream);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  if (side_stream) cudaStreamDestroy(side_stream);
+  if (ev_tfork) cudaEventDestroy(ev_tfork);
+  if (ev_tjoin) cudaEventDestroy(ev_tjoin);
 }
 
 }  // namespace dv

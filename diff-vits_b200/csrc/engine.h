@@ -117,6 +117,10 @@ struct Plan {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t cap_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // lane fork / join inside a captured group loop
+  // time tables one call ahead: the time-embedding MLP + the 22 time_emb_proj of call k+1 run on a side stream while
+  // call k computes (they depend on t only), into the other of two table slots
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_tfork = nullptr, ev_tjoin = nullptr;
   uint64_t graph_key = 0;
   uint64_t graph_epoch = 0;   // bumped whenever launches baked into a captured graph become stale
   int graph_launches = 0;
@@ -124,9 +128,12 @@ struct Plan {
   int build(std::string& err);
   int bind(void* workspace, const void* params, cudaStream_t st, std::string& err);
   int enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches,
-                  cudaEvent_t* events = nullptr);
+                  cudaEvent_t* events = nullptr, int ss_slot = 0);
+  // time-embedding MLP + all time_emb_proj for one call into table slot `slot` (2 launches)
+  int enqueue_time_tables(const float* t, int t_stride, int slot, cudaStream_t st, std::string& err);
+  // tables_slot < 0: compute the time tables inline (slot 0) before the ops; >= 0: they are already in that slot
   int forward(const float* sample, int x_only, const float* t, int t_stride, float* out, cudaStream_t st,
-              std::string& err, int* launches, cudaEvent_t* events = nullptr);
+              std::string& err, int* launches, cudaEvent_t* events = nullptr, int tables_slot = -1);
   int prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_len, cudaStream_t st, std::string& err);
   int set_cond(const float* cond, cudaStream_t st, std::string& err);
   // Debug/measurement: one eager forward with a CUDA event between consecutive launches; synchronises.
