@@ -173,7 +173,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
       return fail(DV_ERR_CUDA, err);
     rs[i] = dv::GemmRefSrc{s.ptr, s.L, s.C, s.ld};
   }
-  if (!dv::make_tmap_2d(&p.mapW, w, k_tot, n_pad, 128, err)) return fail(DV_ERR_CUDA, err);
+  if (!dv::make_tmap_2d(&p.mapW, w, k_tot, n_pad, 64, err)) return fail(DV_ERR_CUDA, err);
   int ksum = 0;
   for (int i = 0; i < nseg; ++i) {
     if (segs[i].src < 0 || segs[i].src >= nsrc) return fail(DV_ERR_INVALID, "segment source out of range");

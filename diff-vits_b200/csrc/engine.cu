@@ -737,7 +737,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
                             static_cast<size_t>(t.L) * t.C, err))
             return false;
         }
-        if (!make_tmap_2d(&p.mapW, params + g.w_off, g.k_tot, g.n_pad, 128, err)) return false;
+        if (!make_tmap_2d(&p.mapW, params + g.w_off, g.k_tot, g.n_pad, 64, err)) return false;
         for (int i = 0; i < g.nseg; ++i) p.seg[i] = g.seg[i];
         p.nseg = g.nseg;
         p.B = B; p.L = g.l_out; p.N = g.n; p.n_pad = g.n_pad;
@@ -751,6 +751,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.stats = g.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + g.stats_off) : nullptr;
         p.stats_nblk = g.stats_nblk;
         p.bn = 0;
+        { const char* de = getenv("DV_GEMM_DBG"); p.dbg_flags = de ? atoi(de) : 0; }   // timing experiments only
       } else if (o.kind == OP_CHAIN) {
         ChainParams& p = o.cp;
         memset(&p, 0, sizeof p);

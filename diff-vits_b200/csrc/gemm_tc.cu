@@ -40,7 +40,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = EW == 8 ? 2 : (BN == 128 ? 5 : 3);
+  static constexpr int STAGES = EW == 8 ? 2 : (BN == 128 ? 5 : (BN == 192 ? 4 : 3));
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EW * EPI_SLAB;
   static constexpr int BIAS_OFF = BAR_OFF + 256;       // barriers + tmem slot, then the bias vector (n_pad floats)
@@ -70,21 +70,25 @@ struct EpiCtx {
   int lane, srow, spiece;
 };
 
+__device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& e, int gcol, int lq, size_t rowbase, uint4 (&rv)[4]) {
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.res);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + e.srow;
+    rv[i] = (lq + r < p.L && !(p.dbg_flags & 16)) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
+                           : make_uint4(0, 0, 0, 0);
+  }
+}
+
 // One 32-row x 32-column chunk of a bf16 output tile: (+bias) (+residual) -> bf16, GroupNorm partials, coalesced store.
 template <bool HAS_RES, bool HAS_STATS>
 __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx& e, uint32_t taddr_c, int gcol, int lq,
-                                              size_t rowbase, bool valid, size_t stat_chunk, bool last, uint64_t* empty_bar) {
+                                              size_t rowbase, bool valid, size_t stat_chunk, bool last, uint64_t* empty_bar,
+                                              uint4 (&rv)[4], bool preloaded) {
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-  uint4 rv[4];
-  if (HAS_RES) {   // row-contiguous residual fetch (64-byte segments), in flight during the TMEM load
-    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.res);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = i * 8 + e.srow;
-      rv[i] = (lq + r < p.L && !(p.dbg_flags & 16)) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
-                             : make_uint4(0, 0, 0, 0);
-    }
-  }
+  // row-contiguous residual fetch (64-byte segments), in flight during the TMEM load; the first chunk of a tile
+  // arrives preloaded (issued before the wait on the accumulator, so its L2 latency hides behind the main loop)
+  if (HAS_RES && !preloaded) epi_load_res(p, e, gcol, lq, rowbase, rv);
   uint32_t r[32];
   tmem_ld32(taddr_c, r);
   if (HAS_RES) {
@@ -182,7 +186,8 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;   // power of two >= the two accumulators
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   if (warp >= 2 && p.bias) {                         // bias vector -> shared memory, once per CTA
     float* sb = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
     for (int i = threadIdx.x - 64; i < p.n_pad; i += EW * 32) sb[i] = __ldg(p.bias + i);
@@ -216,10 +221,10 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
             if (p.dbg_flags & 4) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
             mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
             tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
-            // the W map's box is 64 x 128 rows: a 256-wide tile takes two boxes
+            // the W map's box is 64 x 64 rows: a BN-wide tile takes BN / 64 boxes, stacked contiguously
 #pragma unroll
-            for (int h = 0; h < BN / 128; ++h)
-              tma_load_2d(sb + h * (128 * BK * 2), &p.mapW, &full_bar[stage], kp * BK, n0 + h * 128);
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sb + h * (64 * BK * 2), &p.mapW, &full_bar[stage], kp * BK, n0 + h * 64);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -283,11 +288,17 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       const int l = lq + lane;                          // this thread's accumulator row
       const bool valid = l < p.L;
       if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 0);
+      const size_t rowbase = static_cast<size_t>(b) * p.L;
+      uint4 rv[4];
+      bool preloaded = false;
+      if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && n0 + part * 32 < p.N && !(p.dbg_flags & (1 | 32))) {
+        epi_load_res(p, e, n0 + part * 32, lq, rowbase, rv);
+        preloaded = true;
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 1);
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
-      const size_t rowbase = static_cast<size_t>(b) * p.L;
 
       if (p.dbg_flags & 1) {
         tc_fence_before();
@@ -375,11 +386,11 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           arrived |= last;
           const uint32_t tc = taddr + ch * 32;
           if (has_res) {
-            if (has_stats) epi_chunk_bf16<true, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
-            else           epi_chunk_bf16<true, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
+            if (has_stats) epi_chunk_bf16<true, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<true, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           } else {
-            if (has_stats) epi_chunk_bf16<false, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
-            else           epi_chunk_bf16<false, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc]);
+            if (has_stats) epi_chunk_bf16<false, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<false, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           }
         }
         if (!arrived) {                                   // this warp's columns were all padding
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -441,8 +452,10 @@ cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
 }  // namespace
 
 int gemm_pick_bn(int m_tiles, int n_pad) {
-  if (n_pad % 256 != 0) return 128;
   if (g_num_sms == 0) return 128;
+  // N = 384 (level 2): 2 x 64 tiles of 128 x 128 rows would be 192 tiles = 1.3 waves; 192-wide tiles make it one wave
+  if (n_pad == 384 && m_tiles * 2 <= g_num_sms && !getenv("DV_GEMM_NO192")) return 192;
+  if (n_pad % 256 != 0) return 128;
   // wide tiles halve the A traffic and the shared-memory bandwidth per FLOP, but only pay when they still fill the GPU
   return (m_tiles * (n_pad / 256) >= (g_num_sms * 4) / 5) ? 256 : 128;
 }
@@ -465,6 +478,9 @@ cudaError_t gemm_tc_init() {
     const char* ev = getenv("DV_GEMM_EW");
     if (ev) g_force_ew = atoi(ev);
   }
+  e = cudaFuncSetAttribute(gemm_tc_kernel<192, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<192, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(gemm_tc_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
 }
@@ -480,6 +496,10 @@ cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   if (bn == 256) {
     if (p.n_pad % 256 != 0) return cudaErrorInvalidValue;
     return launch_bn<256, 16>(p, st);
+  }
+  if (bn == 192) {
+    if (p.n_pad % 192 != 0 || p.out_mode == GEMM_OUT_GEGLU) return cudaErrorInvalidValue;
+    return launch_bn<192, 16>(p, st);
   }
   // two small CTAs per SM pay once there is more than one wave of 128-wide tiles (measured on the C2 shapes: 5-10 %
   // faster at levels 0-2, slower for the few long-K tiles of level 3)

@@ -73,6 +73,31 @@ def test_gemm_tile_width_and_groupnorm_partials(U, bn):
     _check_bf16(U, got2, a2.float() @ w2.float().t())
 
 
+def test_gemm_tile_width_192(U):
+    """N = 384 (level 2) as two 192-wide tiles: one wave of 128 x 192 tiles instead of 1.3 waves of 128 x 128.
+    conv k3 with residual and GroupNorm partials, and a plain linear, against fp32 math and the 128-wide kernel."""
+    g = torch.Generator(device="cuda").manual_seed(22)
+    B, L, C, N = 3, 250, 384, 384
+    x = _rand((B, L, C), g)
+    w3 = _rand((N, C, 3), g, (3 * C) ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = _rand((B, L, N), g)
+    ref = F.conv1d(x.float().transpose(1, 2), w3.float(), bias, padding=1).transpose(1, 2) + res.float()
+    wp = w3.permute(0, 2, 1).reshape(N, 3 * C).contiguous()
+    segs = [(0, -1, 0, C), (0, 0, 0, C), (0, 1, 0, C)]
+    got, st = U.gemm([x], segs, wp, N, bias=bias, res=res, bn=192, stats=True)
+    _check_bf16(U, got, ref)
+    got128, st128 = U.gemm([x], segs, wp, N, bias=bias, res=res, bn=128, stats=True)
+    assert torch.equal(got, got128)                      # same K order, same accumulation: bit-identical
+    assert torch.equal(st, st128)
+    a = _rand((B, L, 4 * C), g)
+    w = _rand((N, 4 * C), g, (4 * C) ** -0.5)
+    got = U.gemm([a], [(0, 0, 0, 4 * C)], w, N, bn=192)
+    _check_bf16(U, got, a.float() @ w.float().t())
+    # automatic choice at this shape must agree too (whichever tile it picks)
+    assert torch.equal(got, U.gemm([a], [(0, 0, 0, 4 * C)], w, N))
+
+
 @pytest.mark.parametrize("B,L,Cin,Cout", [(2, 257, 128, 128), (1, 200, 256, 384), (2, 1000, 384, 128), (2, 26, 512, 512)])
 def test_gemm_conv3(U, B, L, Cin, Cout):
     """conv1d k3 s1 p1: three row-shifted K segments, zero fill outside [0, L)."""
@@ -158,11 +183,33 @@ def test_gemm_geglu_and_ncl(U):
     assert U.rel_l2(got3, ref3) < 1e-5
 
 
-@pytest.fixture(params=["tc", "legacy"])
+@pytest.fixture(params=["tc", "legacy", "poly0", "poly3", "poly5"])
 def attn_kernel(request, monkeypatch):
-    """Both attention kernels (tcgen05 / mma.sync) are checked at every head dim, whichever the dispatcher prefers."""
-    monkeypatch.setenv("DV_ATTN", request.param)
+    """Every attention kernel (tcgen05 / first mma.sync / second mma.sync with 0, 3 or 5 of 8 accumulator columns on
+    the FMA-pipe exp2) is checked at every head dim, whichever the dispatcher prefers."""
+    if request.param.startswith("poly"):
+        monkeypatch.setenv("DV_ATTN", "v2")
+        monkeypatch.setenv("DV_ATTN_POLY", request.param[4:])
+    else:
+        monkeypatch.setenv("DV_ATTN", request.param)
     return request.param
+
+
+@pytest.mark.parametrize("gain", [3.0, 12.0, 40.0])
+def test_attention_wide_score_range(U, attn_kernel, gain):
+    """Peaky softmax: scaled scores spread over tens to thousands of log2 units, so most exponents sit far below the
+    row maximum (the polynomial exp2 path clamps at 2^-126 where MUFU.EX2 flushes to zero)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, D, L = 2, 8, 16, 300
+    C = H * D
+    q = (_rand((B, L, C), g).float() * gain).to(torch.bfloat16)
+    kv = _rand((B, L, 2 * C), g)
+    k, v = kv[:, :, :C], kv[:, :, C:]
+    ref = F.scaled_dot_product_attention(*(t.float().reshape(B, L, H, D).transpose(1, 2) for t in (q, k, v)))
+    ref = ref.transpose(1, 2).reshape(B, L, C)
+    got = U.attention(q, k, v, H)
+    assert torch.isfinite(got.float()).all()
+    _check_bf16(U, got, ref, rel=8e-3)
 
 
 @pytest.mark.parametrize("D,Lq,Lk", [(16, 200, 200), (32, 500, 500), (48, 250, 250), (64, 125, 125), (16, 1000, 1000),
