@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention2_kernel(const AttnParam
   }
 }
 
+
 constexpr int kDefaultPolyJ = 0;   // measured (profiles/r1f_attention_v2.txt): every polynomial share is slower
 
 template <int POLYJ>
