@@ -70,6 +70,7 @@ SIGNATURES = {
     "dv_gemm_test_options": (None, [_i, _vp]),
     "dv_gemm_test_trace": (None, [_vp]),
     "dv_gemm_test_flags": (None, [_i]),
+    "dv_debug_skip_kinds": (_i, [_i]),
     "dv_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "dv_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
     "dv_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),

@@ -151,6 +151,7 @@ static thread_local unsigned long long* g_test_trace = nullptr;
 static thread_local int g_test_flags = 0;
 void dv_gemm_test_trace(unsigned long long* buf) { g_test_trace = buf; }
 void dv_gemm_test_flags(int flags) { g_test_flags = flags; }
+int dv_debug_skip_kinds(int mask) { int& m = dv::skip_kinds_mask(); const int old = m; m = mask; return old; }
 /* Test hooks for dv_gemm: force the N tile (0 = heuristic) and ask the epilogue for GroupNorm partials. */
 void dv_gemm_test_options(int bn, float* stats) { g_test_bn = bn; g_test_stats = stats; }
 

@@ -832,12 +832,17 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
     }                                                                                   \
   } while (0)
 
+int& skip_kinds_mask() {
+  static int mask = [] { const char* e = getenv("DV_SKIP_KINDS"); return e ? atoi(e) : 0; }();
+  return mask;
+}
+
 int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, std::string& err, int* launches,
                       cudaEvent_t* events, int ss_slot) {
   int idx = 0;
   // DV_SKIP_KINDS (timing experiments only, results are garbage): bit k set = do not launch ops of OpKind k, so the
   // step-time difference is that kernel class's marginal cost inside the captured loop
-  static const int skip_kinds = [] { const char* e = getenv("DV_SKIP_KINDS"); return e ? atoi(e) : 0; }();
+  const int skip_kinds = skip_kinds_mask();
   for (Op& o : list) {
     if (events) cudaEventRecordWithFlags(events[idx++], st, cudaEventRecordExternal);
     cudaError_t e = cudaSuccess;
@@ -1104,6 +1109,7 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
     key = fnv1a(key, &sampler, sizeof sampler);
     key = fnv1a(key, &nsteps, sizeof nsteps);
     key = fnv1a(key, &rt, sizeof rt);
+    { const int sk = skip_kinds_mask(); key = fnv1a(key, &sk, sizeof sk); }
     key = fnv1a(key, coef, static_cast<size_t>(nsteps) * 8 * 4);
     key = fnv1a(key, plans, static_cast<size_t>(n) * sizeof(Plan*));
     for (int i = 0; i < n; ++i) key = fnv1a(key, &plans[i]->graph_epoch, sizeof(uint64_t));

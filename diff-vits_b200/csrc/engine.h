@@ -29,6 +29,7 @@ struct ParamSlot {
 };
 
 enum OpKind { OP_GEMM = 0, OP_GN_APPLY = 2, OP_LN = 3, OP_ATTN = 4, OP_CHAIN = 5 };
+int& skip_kinds_mask();   // measurement hook (dv_debug_skip_kinds): op kinds that are not launched
 
 struct GemmDesc {
   int nsrc = 0;

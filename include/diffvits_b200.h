@@ -146,6 +146,11 @@ DV_API void dv_gemm_test_trace(unsigned long long* buf);
 /* Debug: bit 0 skip the epilogue body, bit 1 skip the MMA issue, bit 2 skip the TMA loads (results are garbage;
  * used to time the three pipelines of the kernel separately). */
 DV_API void dv_gemm_test_flags(int flags);
+/* Measurement hook (bench.py): bit k set = the denoiser ops of kernel class k (0 gemm, 2 groupnorm apply, 3 layernorm,
+ * 4 attention, 5 chained gemm; dv_plan_op_info's `kind`) are NOT launched by later dv_unet_forward / dv_sample calls, so
+ * the difference in step time is that class's cost inside the captured loop. Results are garbage while any bit is set.
+ * Initial value: environment variable DV_SKIP_KINDS (default 0). Returns the previous mask. */
+DV_API int dv_debug_skip_kinds(int mask);
 /* F.scaled_dot_product_attention (attention_processor.py:1032); bf16 q/k/v/o with element strides. */
 DV_API int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
                  long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,
