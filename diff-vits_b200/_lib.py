@@ -35,7 +35,7 @@ class UnetCfg(C.Structure):
 
 
 class GemmSrc(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("L", C.c_int), ("C", C.c_int), ("ld", C.c_int)]
+    _fields_ = [("ptr", C.c_void_p), ("L", C.c_int), ("C", C.c_int), ("ld", C.c_int), ("bs", C.c_longlong)]
 
 
 class GemmSeg(C.Structure):
@@ -70,6 +70,7 @@ SIGNATURES = {
     "dv_gemm_test_options": (None, [_i, _vp]),
     "dv_gemm_test_trace": (None, [_vp]),
     "dv_gemm_test_flags": (None, [_i]),
+    "dv_gemm_test_layout": (None, [C.c_longlong, _i]),
     "dv_debug_skip_kinds": (_i, [_i]),
     "dv_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "dv_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),

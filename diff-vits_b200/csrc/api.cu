@@ -151,6 +151,9 @@ static thread_local unsigned long long* g_test_trace = nullptr;
 static thread_local int g_test_flags = 0;
 void dv_gemm_test_trace(unsigned long long* buf) { g_test_trace = buf; }
 void dv_gemm_test_flags(int flags) { g_test_flags = flags; }
+static thread_local long long g_test_out_bs = 0;
+static thread_local int g_test_trim = 0;
+void dv_gemm_test_layout(long long out_bs, int trim_col) { g_test_out_bs = out_bs; g_test_trim = trim_col; }
 int dv_debug_skip_kinds(int mask) { int& m = dv::skip_kinds_mask(); const int old = m; m = mask; return old; }
 /* Test hooks for dv_gemm: force the N tile (0 = heuristic) and ask the epilogue for GroupNorm partials. */
 void dv_gemm_test_options(int bn, float* stats) { g_test_bn = bn; g_test_stats = stats; }
@@ -170,7 +173,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   for (int i = 0; i < dv::GEMM_MAX_SRC; ++i) {
     const dv_gemm_src& s = srcs[i < nsrc ? i : 0];
     if (s.C % 64) return fail(DV_ERR_INVALID, "source channels must be a multiple of 64");
-    if (!dv::make_tmap_3d(&p.mapA[i], s.ptr, s.C, s.ld, s.L, B, static_cast<size_t>(s.L) * s.ld, err))
+    if (!dv::make_tmap_3d(&p.mapA[i], s.ptr, s.C, s.ld, s.L, B, s.bs > 0 ? static_cast<size_t>(s.bs) : static_cast<size_t>(s.L) * s.ld, err))
       return fail(DV_ERR_CUDA, err);
     rs[i] = dv::GemmRefSrc{s.ptr, s.L, s.C, s.ld};
   }
@@ -190,6 +193,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   p.tiles_per_batch = (L_out + 127) / 128;
   p.out_mode = out_mode;
   p.bias = bias; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out;
+  p.out_bs = g_test_out_bs; p.trim_col = g_test_trim;
   p.stats = g_test_stats; p.stats_nblk = n / 16; p.bn = g_test_bn; p.trace = g_test_trace; p.dbg_flags = g_test_flags;
   if (impl == 1) return ck(dv::launch_gemm_ref(p, rs, w, k_tot, S(stream)), "gemm_ref");
   return ck(dv::launch_gemm_tc(p, S(stream)), "gemm_tc");

@@ -446,16 +446,22 @@ struct Builder {
     return yo;
   }
 
-  TRef downsample(const std::string& key, TRef x) {  // conv k3 s2 p1 through the [L/2, 2C] view
-    const int C = x.C, Lo = x.L / 2;
+  // conv k3 s2 p1 (resnet.py:214-223): L -> ceil(L / 2). The input is read through the pair view [L/2, 2C] (row l =
+  // x[2l] | x[2l+1]). For odd L the last pair has only its first half: the first-half tap uses a view with ceil(L/2)
+  // rows, the second-half taps a view with floor(L/2) rows, so the missing x[L] is TMA zero fill = the conv padding.
+  TRef downsample(const std::string& key, TRef x) {
+    const int C = x.C, Lo = (x.L + 1) / 2;
     TRef out = act(Lo, C);
     Op& o = emit_gemm(P.ops, key);
     GemmDesc& g = o.g;
     add_src(g, x);
     g.view_l[0] = Lo; g.view_c[0] = 2 * C;
-    add_seg(g, 0, -1, C, C);  // tap 0: x[2l-1] = second half of view row l-1
+    add_src(g, x);
+    g.view_l[1] = x.L / 2; g.view_c[1] = 2 * C;
+    g.alg_nsrc = 1;
+    add_seg(g, 1, -1, C, C);  // tap 0: x[2l-1] = second half of view row l-1
     add_seg(g, 0, 0, 0, C);   // tap 1: x[2l]
-    add_seg(g, 0, 0, C, C);   // tap 2: x[2l+1]
+    add_seg(g, 1, 0, C, C);   // tap 2: x[2l+1]
     g.n = C; g.n_pad = round_up(C, 128);
     g.w_off = slot(key + ".W", "conv3", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
     P.slots.back().shape.push_back(C);
@@ -467,20 +473,39 @@ struct Builder {
     return out;
   }
 
-  TRef upsample(const std::string& key, TRef x) {  // nearest 2x + conv k3 p1, folded: N = 2C over the low-res rows
+  // nearest resize to the skip's length Ls (2L or 2L - 1; resnet.py:138-173, `size=` path) + conv k3 p1, folded into
+  // ONE GEMM over the low-resolution rows with N = 2C (columns [0, C) = output row 2p, [C, 2C) = row 2p + 1). With
+  // u[i] = x[i / 2] for i < Ls (nearest with size = Ls is exactly that, also for Ls = 2L - 1) and zero outside:
+  //   row 2p     = W0 x[p-1] + W1 x[p] + W2 u[2p+1]        u[2p+1] = x[p], except that u[Ls] is conv padding when Ls is odd
+  //   row 2p + 1 = (W0 + W1) x[p] + W2 x[p+1]
+  // Ls even: three K segments (x, -1) (x, 0) (x, +1) with weights [W0 | W1+W2 | 0 ; 0 | W0+W1 | W2] ("conv3_up2").
+  // Ls odd:  four segments (x, -1) (x, 0) (x', 0) (x, +1), [W0 | W1 | W2 | 0 ; 0 | W0+W1 | 0 | W2] ("conv3_up2_odd"), x' = the
+  //          same tensor behind a map one row shorter (TMA zero fill removes the W2 term of the last even row); the odd
+  //          half of the last GEMM row does not exist: it is neither stored nor counted in the GroupNorm partials.
+  TRef upsample(const std::string& key, TRef x, int Ls) {
     const int C = x.C;
-    TRef out2 = act(x.L, 2 * C);
+    if (Ls != 2 * x.L && Ls != 2 * x.L - 1) { err = "internal: upsample target length"; return x; }
+    TRef out = act(Ls, C);
     Op& o = emit_gemm(P.ops, key);
     GemmDesc& g = o.g;
+    const bool odd = (Ls & 1) != 0;
     add_src(g, x);
-    for (int tap = 0; tap < 3; ++tap) add_seg(g, 0, tap - 1, 0, C);
+    add_seg(g, 0, -1, 0, C);
+    add_seg(g, 0, 0, 0, C);
+    if (odd) {
+      add_src(g, x);
+      g.view_l[1] = x.L - 1;
+      add_seg(g, 1, 0, 0, C);
+    }
+    add_seg(g, 0, 1, 0, C);
     g.n = 2 * C; g.n_pad = round_up(2 * C, 128);
-    g.w_off = slot(key + ".W", "conv3_up2", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
+    g.w_off = slot(key + ".W", odd ? "conv3_up2_odd" : "conv3_up2", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
     g.bias_off = slot(key + ".b", "vec_dup2", {key + ".bias"}, "f32", {g.n_pad});
-    g.out = out2; g.l_out = x.L; g.out_mode = GEMM_OUT_BF16; g.ld_out = 2 * C;
-    attach_stats(g, out2);
-    TRef out = out2;
-    out.L = 2 * x.L; out.C = C;  // same bytes viewed as [2L, C]
+    g.out = out; g.l_out = x.L; g.out_mode = GEMM_OUT_BF16; g.ld_out = 2 * C;
+    g.out_bs = static_cast<long long>(Ls) * C;
+    g.trim_col = (Ls & 1) ? C : 0;
+    g.alg_k = 3 * C; g.alg_nsrc = 1;   // the reference convolves 2L rows with 3 taps; the 4th K segment is bookkeeping
+    attach_stats(g, out);
     out.st_fold = 1;             // partials are indexed by low-res row chunk and 2C/16 blocks: block kb also at kb + C/16
     P.named.emplace_back(key, out);
     return out;
@@ -497,10 +522,7 @@ int Plan::build(std::string& err) {
   if (n_levels < 2 || n_levels > 8) { err = "n_levels must be in [2, 8]"; return DV_ERR_INVALID; }
   if (c.layers_per_block < 1 || c.layers_per_block > 4) { err = "layers_per_block must be in [1, 4]"; return DV_ERR_INVALID; }
   if (B < 1 || T < 1 || Tp < 1) { err = "B, T, Tp must be positive"; return DV_ERR_INVALID; }
-  if (T % (1 << (n_levels - 1)) != 0) {
-    err = "T must be a multiple of 2^(n_levels-1) on the accelerated path (nearest-resize to odd lengths not built yet)";
-    return DV_ERR_UNSUPPORTED;
-  }
+  if ((T >> (n_levels - 1)) < 2) { err = "T too short for the number of levels (need T >= 2^n_levels)"; return DV_ERR_INVALID; }
   for (int i = 0; i < n_levels; ++i) {
     const int ch = c.block_out_channels[i];
     if (ch % 64 != 0 || ch > 1024) { err = "block_out_channels must be multiples of 64 (<= 1024)"; return DV_ERR_UNSUPPORTED; }
@@ -591,7 +613,7 @@ int Plan::build(std::string& err) {
       h = b.resnet(bp + ".resnets." + std::to_string(j), h, skip, co);
       if (i > 0) h = b.transformer(bp + ".attentions." + std::to_string(j), h);
     }
-    if (!final_block) h = b.upsample(bp + ".upsamplers.0.conv", h);
+    if (!final_block) h = b.upsample(bp + ".upsamplers.0.conv", h, skips.back().L);
   }
   if (!b.err.empty()) { err = b.err; return DV_ERR_UNSUPPORTED; }
   {
@@ -654,8 +676,8 @@ int Plan::build(std::string& err) {
     switch (o.kind) {
       case OP_GEMM: {
         double abytes = 0;
-        for (int i = 0; i < o.g.nsrc; ++i) abytes += Bd * o.g.src[i].L * o.g.src[i].C * 2;
-        o.flops = 2.0 * Bd * o.g.l_out * o.g.n * o.g.k_tot;
+        for (int i = 0; i < (o.g.alg_nsrc ? o.g.alg_nsrc : o.g.nsrc); ++i) abytes += Bd * o.g.src[i].L * o.g.src[i].C * 2;
+        o.flops = 2.0 * Bd * o.g.l_out * o.g.n * (o.g.alg_k ? o.g.alg_k : o.g.k_tot);
         const double outw = o.g.out_mode == GEMM_OUT_F32_NCL ? 4.0 * o.g.n : (o.g.out_mode == GEMM_OUT_GEGLU ? o.g.n : 2.0 * o.g.n);
         o.bytes = abytes + 2.0 * o.g.n_pad * o.g.k_tot + Bd * o.g.l_out * outw +
                   (o.g.res.valid() ? Bd * o.g.l_out * o.g.n * 2.0 : 0.0);
@@ -748,6 +770,8 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.ld_res = g.res.valid() ? g.res.C : 0;
         p.out = g.out_dynamic ? nullptr : ws + g.out.off;
         p.ld_out = g.ld_out;
+        p.out_bs = g.out_bs;
+        p.trim_col = g.trim_col;
         p.stats = g.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + g.stats_off) : nullptr;
         p.stats_nblk = g.stats_nblk;
         p.bn = 0;

@@ -41,6 +41,9 @@ struct GemmDesc {
   long long bias_off = -1;
   TRef res; TRef out;
   int l_out = 0, out_mode = GEMM_OUT_BF16, ld_out = 0;
+  long long out_bs = 0;      // elements between batch items of the output (0 = dense l_out * ld_out)
+  int trim_col = 0;          // > 0: columns >= trim_col of the last GEMM row do not exist (odd-length upsample)
+  int alg_k = 0, alg_nsrc = 0;  // roofline accounting: the reference's K / distinct inputs when they differ from k_tot / nsrc
   bool out_dynamic = false;  // conv_out: destination supplied per call
   long long stats_off = -1;  // >= 0: emit GroupNorm partials of the output
   int stats_nblk = 0;

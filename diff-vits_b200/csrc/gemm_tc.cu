@@ -83,8 +83,8 @@ __device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& 
 // One 32-row x 32-column chunk of a bf16 output tile: (+bias) (+residual) -> bf16, GroupNorm partials, coalesced store.
 template <bool HAS_RES, bool HAS_STATS>
 __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx& e, uint32_t taddr_c, int gcol, int lq,
-                                              size_t rowbase, bool valid, size_t stat_chunk, bool last, uint64_t* empty_bar,
-                                              uint4 (&rv)[4], bool preloaded) {
+                                              size_t rowbase, size_t obase, bool valid, size_t stat_chunk, bool last,
+                                              uint64_t* empty_bar, uint4 (&rv)[4], bool preloaded) {
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
   // row-contiguous residual fetch (64-byte segments), in flight during the TMEM load; the first chunk of a tile
   // arrives preloaded (issued before the wait on the accumulator, so its L2 latency hides behind the main loop)
@@ -132,7 +132,8 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     // GroupNorm partials per 16-channel block over this warp's 32 rows (fp32 accumulator values; the stored bf16
     // differs by rounding noise only). Fixed shuffle tree: deterministic.
     float a0 = s0.x + s0.y, b0 = q0.x + q0.y, a1 = s1.x + s1.y, b1 = q1.x + q1.y;
-    if (!valid) { a0 = b0 = a1 = b1 = 0.f; }
+    const bool trimmed = p.trim_col > 0 && gcol >= p.trim_col && lq + e.lane == p.L - 1;   // half row that does not exist
+    if (!valid || trimmed) { a0 = b0 = a1 = b1 = 0.f; }
     a0 = warp_sum(a0); b0 = warp_sum(b0); a1 = warp_sum(a1); b1 = warp_sum(b1);
     if (e.lane == 0)
       *reinterpret_cast<float4*>(p.stats + (stat_chunk * p.stats_nblk + (gcol >> 4)) * 2) = make_float4(a0, b0, a1, b1);
@@ -144,8 +145,9 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rrow = i * 8 + e.srow;
-    if (lq + rrow < p.L && !(p.dbg_flags & 8))
-      *reinterpret_cast<uint4*>(out + (rowbase + lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
+    const bool keep = !(p.trim_col > 0 && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
+    if (lq + rrow < p.L && keep && !(p.dbg_flags & 8))
+      *reinterpret_cast<uint4*>(out + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
           lds128(e.coal + i * 8 * EPI_PITCH);
   }
   __syncwarp();
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       const bool valid = l < p.L;
       if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 0);
       const size_t rowbase = static_cast<size_t>(b) * p.L;
+      const size_t obase = static_cast<size_t>(b) * p.out_bs;
       uint4 rv[4];
       bool preloaded = false;
       if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && n0 + part * 32 < p.N && !(p.dbg_flags & (1 | 32))) {
@@ -386,11 +389,11 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           arrived |= last;
           const uint32_t tc = taddr + ch * 32;
           if (has_res) {
-            if (has_stats) epi_chunk_bf16<true, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
-            else           epi_chunk_bf16<true, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            if (has_stats) epi_chunk_bf16<true, true>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<true, false>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           } else {
-            if (has_stats) epi_chunk_bf16<false, true>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
-            else           epi_chunk_bf16<false, false>(p, e, tc, gcol, lq, rowbase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            if (has_stats) epi_chunk_bf16<false, true>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<false, false>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           }
         }
         if (!arrived) {                                   // this warp's columns were all padding
@@ -485,7 +488,10 @@ cudaError_t gemm_tc_init() {
                               SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
 }
 
-cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
+cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
+  GemmParams p = p_in;
+  if (p.out_bs == 0) p.out_bs = static_cast<long long>(p.L) * p.ld_out;
+  if (p.trim_col % 32 != 0 || (p.trim_col > 0 && p.out_mode != GEMM_OUT_BF16)) return cudaErrorInvalidValue;
   if (g_num_sms == 0) {
     cudaError_t e = gemm_tc_init();
     if (e != cudaSuccess) return e;

@@ -59,6 +59,9 @@ struct alignas(64) GemmParams {
   int ld_res;
   void* out;
   int ld_out;
+  long long out_bs;     // GEMM_OUT_BF16: elements between batch items of `out` (0 = L * ld_out, dense)
+  int trim_col;         // GEMM_OUT_BF16: if > 0, columns >= trim_col of the LAST row (l = L - 1) are neither stored nor counted in
+                        // the GroupNorm partials (odd-length nearest-2x upsample: that half row does not exist)
   float* stats;         // optional GroupNorm partials of the stored tensor: [B][tiles_per_batch*4][stats_nblk][2]
   int stats_nblk;       // 16-channel blocks per row chunk (= N / 16)
   int bn;               // N tile (128 / 256); 0 = choose

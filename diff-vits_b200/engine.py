@@ -90,15 +90,18 @@ def pack_slot(slot: dict, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
             parts.append(w[1].reshape(w[1].shape[0], -1))
         out = _pad_rows(torch.cat(parts, dim=1), n_pad)
         assert out.shape[1] == k_tot, (slot["name"], out.shape, k_tot)
-    elif rec == "conv3_up2":
-        # nearest-2x upsample folded into the conv: even output rows see taps (x[p-1], x[p], x[p]) and odd rows
-        # (x[p], x[p], x[p+1]) of the low-resolution input, so over low-res rows the weights are
-        #   even: [W0 | W1+W2 | 0]      odd: [0 | W0+W1 | W2]            (resnet.py:157-170)
+    elif rec in ("conv3_up2", "conv3_up2_odd"):
+        # nearest resize folded into the conv (resnet.py:138-173), over the low-resolution rows p:
+        #   to 2L rows,     K segments (x[p-1], x[p], x[p+1]):        even row 2p [W0 | W1+W2 | 0]   odd row 2p+1 [0 | W0+W1 | W2]
+        #   to 2L - 1 rows, K segments (x[p-1], x[p], x'[p], x[p+1]): even [W0 | W1 | W2 | 0]         odd [0 | W0+W1 | 0 | W2]
+        #   (x' = x without its last row: the W2 tap of the last even row falls on the conv padding)
         cw = w[0]
         w0, w1, w2 = cw[:, :, 0], cw[:, :, 1], cw[:, :, 2]
         z = torch.zeros_like(w0)
-        even = torch.cat([w0, w1 + w2, z], dim=1)
-        odd = torch.cat([z, w0 + w1, w2], dim=1)
+        if rec == "conv3_up2":
+            even, odd = torch.cat([w0, w1 + w2, z], dim=1), torch.cat([z, w0 + w1, w2], dim=1)
+        else:
+            even, odd = torch.cat([w0, w1, w2, z], dim=1), torch.cat([z, w0 + w1, z, w2], dim=1)
         out = _pad_rows(torch.cat([even, odd], dim=0), shape[0])
     elif rec == "mat_t":
         out = w[0].t().contiguous()

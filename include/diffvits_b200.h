@@ -130,7 +130,9 @@ DV_API int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_onl
                                    float* out, float* ms, int cap, void* stream);
 
 /* ---- single-kernel entry points (used by the parity tests and micro-benchmarks) ------------------------------- */
-typedef struct dv_gemm_src { const void* ptr; int L; int C; int ld; } dv_gemm_src;   /* bf16 [B, L, ld], C used */
+/* bf16 rows of `ld` elements, `L` rows visible per batch item (rows outside [0, L) read as zero), `C` channels used,
+ * `bs` elements between batch items (0 = L * ld) */
+typedef struct dv_gemm_src { const void* ptr; int L; int C; int ld; long long bs; } dv_gemm_src;
 typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; } dv_gemm_seg;
 /* out_mode: 0 bf16 NTC, 1 fp32 NCT, 2 GEGLU bf16. impl: 0 = tcgen05 kernel, 1 = CUDA-core reference (writes raw
  * fp32 [B, L, n_pad] accumulators + bias into `out`). Replaces F.conv1d (unet1d/lora.py:102) / nn.Linear. */
@@ -146,6 +148,10 @@ DV_API void dv_gemm_test_trace(unsigned long long* buf);
 /* Debug: bit 0 skip the epilogue body, bit 1 skip the MMA issue, bit 2 skip the TMA loads (results are garbage;
  * used to time the three pipelines of the kernel separately). */
 DV_API void dv_gemm_test_flags(int flags);
+/* Test hook for the next dv_gemm calls of this thread (bf16 output mode): `out_bs` = elements between batch items of
+ * `out` (0 = dense L_out * ld_out); `trim_col` > 0 = columns >= trim_col of the last row are neither stored nor counted in
+ * the GroupNorm partials. This is how the folded nearest-resize conv writes 2L - 1 rows (resnet.py:138-173). */
+DV_API void dv_gemm_test_layout(long long out_bs, int trim_col);
 /* Measurement hook (bench.py): bit k set = the denoiser ops of kernel class k (0 gemm, 2 groupnorm apply, 3 layernorm,
  * 4 attention, 5 chained gemm; dv_plan_op_info's `kind`) are NOT launched by later dv_unet_forward / dv_sample calls, so
  * the difference in step time is that class's cost inside the captured loop. Results are garbage while any bit is set.

@@ -44,6 +44,14 @@ def main():
     out2 = unet(torch.cat([x2, c2], 1), torch.tensor([250.25, 250.25]), e2, encoder_attention_mask=mask).sample
     np.savez_compressed(os.path.join(GOLD, "unet_ragged.npz"), lens=lens.numpy(), out=out2.numpy())
 
+    # 3b. lengths that are not multiples of 8 (203 -> 102 -> 51 -> 26 frames: the stride-2 convs see odd inputs, the
+    # nearest resizes go to 2L - 1 = 51, 2L = 102 and 2L - 1 = 203 rows; 198 -> 99 -> 50 -> 25 the other way round)
+    odd = {}
+    for T_odd, seed in ((203, 3), (198, 4)):
+        x3, c3, e3 = inputs.make_inputs(1, T_odd, 40, seed=seed)
+        odd[f"out{T_odd}"] = unet(torch.cat([x3, c3], 1), torch.tensor([613.0]), e3).sample.numpy()
+    np.savez_compressed(os.path.join(GOLD, "unet_oddlen.npz"), **odd)
+
     # 4. full sampling loops at C1 with the reference samplers wired like model3.py:1143-1158 / 1177-1192
     rdpm, runi = ref_import.load_samplers()
     betas = inputs.betas_linear()

@@ -164,17 +164,24 @@ def transformer(c: _Ctx, y: Tensor, ehs: Tensor, bias: Optional[Tensor], p: str)
 
 def upsample(c: _Ctx, x: Tensor, size: int, key: str) -> Tensor:
     """Upsample2D.forward with output_size (resnet.py:157-170): nearest resize then conv k3 p1."""
-    if c.emu and size == 2 * x.shape[-1]:
-        # the engine folds the 2x nearest resize into the weights (even rows [W0 | W1+W2 | 0], odd [0 | W0+W1 | W2])
+    up = F.interpolate(x, size=size, mode="nearest")
+    if c.emu and size in (2 * x.shape[-1], 2 * x.shape[-1] - 1):
+        # the engine folds the nearest resize into the weights (operand rounding points follow its packing):
+        # to 2L rows: even rows [W0 | W1+W2 | 0], odd rows [0 | W0+W1 | W2] over (x[p-1], x[p], x[p+1]);
+        # to 2L - 1 rows: even rows keep W0, W1, W2 one by one (the last one loses its W2 tap to the padding)
         w = c.w(key + ".weight")
         w0, w1, w2 = w[:, :, 0], w[:, :, 1], w[:, :, 2]
         z = torch.zeros_like(w0)
-        we = c.r(torch.stack([w0, w1 + w2, z], dim=-1))
-        wo = c.r(torch.stack([z, w0 + w1, w2], dim=-1))
         b = c.w(key + ".bias")
-        ye, yo = F.conv1d(x, we, b, padding=1), F.conv1d(x, wo, b, padding=1)
-        return c.r(torch.stack([ye, yo], dim=-1).reshape(x.shape[0], -1, size))
-    up = F.interpolate(x, size=size, mode="nearest")
+        wo = c.r(torch.stack([z, w0 + w1, w2], dim=-1))
+        yo = F.conv1d(x, wo, b, padding=1)
+        if size % 2 == 0:
+            we = c.r(torch.stack([w0, w1 + w2, z], dim=-1))
+            y = torch.stack([F.conv1d(x, we, b, padding=1), yo], dim=-1).reshape(x.shape[0], -1, size)
+        else:
+            y = F.conv1d(up, c.r(w), b, padding=1)
+            y[..., 1::2] = yo[..., :size // 2]
+        return c.r(y)
     return c.r(conv(c, up, key))
 
 

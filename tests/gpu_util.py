@@ -33,9 +33,10 @@ def bf16r(x: torch.Tensor) -> torch.Tensor:
 def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]], w: torch.Tensor, n: int,
          bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, out_mode: int = 0, impl: int = 0,
          l_out: Optional[int] = None, views: Optional[Sequence[Tuple[int, int]]] = None, bn: int = 0,
-         stats: bool = False):
+         stats: bool = False, layout: Optional[Tuple[int, int]] = None):
     """srcs: bf16 [B, L, C] tensors; segs: (src, row_off, c0, channels); w: bf16 [n_pad, k_tot].
-    views: optional (L_view, C_view) per source (the stride-2 conv reads [L/2, 2C])."""
+    views: optional (L_view, C_view) per source (the stride-2 conv reads [L/2, 2C]).
+    layout: optional (out_bs, trim_col) of dv_gemm_test_layout; the result is then the flat [B, out_bs] buffer."""
     lib = _lib.load()
     B = srcs[0].shape[0]
     n_pad, k_tot = w.shape
@@ -43,7 +44,7 @@ def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]]
     for i, s in enumerate(srcs):
         assert s.dtype == torch.bfloat16 and s.is_contiguous()
         L, Cc = (s.shape[1], s.shape[2]) if views is None else views[i]
-        S[i] = GemmSrc(s.data_ptr(), L, Cc, Cc)
+        S[i] = GemmSrc(s.data_ptr(), L, Cc, Cc, s.shape[1] * s.shape[2])      # batch stride of the real tensor
     G = (GemmSeg * len(segs))()
     for i, (src, ro, c0, ch) in enumerate(segs):
         G[i] = GemmSeg(src, ro, c0, ch // 64)
@@ -53,7 +54,8 @@ def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]]
         out = torch.empty(B, L_out, n_pad, dtype=torch.float32, device=dev)
         ld_out = n_pad
     elif out_mode == 0:
-        out = torch.zeros(B, L_out, n, dtype=torch.bfloat16, device=dev)
+        out = (torch.zeros(B, L_out, n, dtype=torch.bfloat16, device=dev) if layout is None else
+               torch.full((B, layout[0]), 777.0, dtype=torch.bfloat16, device=dev))
         ld_out = n
     elif out_mode == 1:
         out = torch.zeros(B, n, L_out, dtype=torch.float32, device=dev)
@@ -65,11 +67,14 @@ def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]]
     if stats:
         st = torch.full((B, (L_out + 127) // 128 * 4, n // 16, 2), float("nan"), dtype=torch.float32, device=dev)
     lib.dv_gemm_test_options(bn, vp(st))
+    if layout is not None:
+        lib.dv_gemm_test_layout(int(layout[0]), int(layout[1]))
     try:
         check(lib.dv_gemm(S, len(srcs), G, len(segs), vp(w), k_tot, n, n_pad, vp(bias), vp(res),
                           0 if res is None else res.shape[-1], vp(out), ld_out, out_mode, B, L_out, impl, stream()))
     finally:
         lib.dv_gemm_test_options(0, None)
+        lib.dv_gemm_test_layout(0, 0)
     return (out, st) if stats else out
 
 

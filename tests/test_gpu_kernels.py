@@ -127,34 +127,58 @@ def test_gemm_conv3_with_fused_shortcut_two_sources(U):
     _check_bf16(U, got, ref)
 
 
-def test_gemm_conv3_stride2_view(U):
-    """Downsample2D conv k3 s2 p1 through the [L/2, 2C] view (resnet.py:200)."""
+@pytest.mark.parametrize("L", [500, 251, 77])
+def test_gemm_conv3_stride2_view(U, L):
+    """Downsample2D conv k3 s2 p1 (resnet.py:214-223), L -> ceil(L / 2), through the pair view [L/2, 2C]: the first-half
+    tap reads a view with ceil(L/2) rows, the second-half taps one with floor(L/2) rows, so for odd L the missing x[L]
+    is TMA zero fill and nothing of the next batch item is read."""
     g = torch.Generator(device="cuda").manual_seed(4)
-    B, L, C = 2, 500, 128
+    B, C = 3, 128
+    Lo = (L + 1) // 2
     x = _rand((B, L, C), g)
     w = (torch.randn(C, C, 3, generator=g, device="cuda") * (3 * C) ** -0.5).to(torch.bfloat16)
     b = torch.randn(C, generator=g, device="cuda")
     ref = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=2, padding=1).transpose(1, 2)
+    assert ref.shape[1] == Lo
     wp = w.permute(0, 2, 1).reshape(C, 3 * C).contiguous()
-    got = U.gemm([x], [(0, -1, C, C), (0, 0, 0, C), (0, 0, C, C)], wp, C, bias=b, l_out=L // 2,
-                 views=[(L // 2, 2 * C)])
+    got = U.gemm([x, x], [(1, -1, C, C), (0, 0, 0, C), (1, 0, C, C)], wp, C, bias=b, l_out=Lo,
+                 views=[(Lo, 2 * C), (L // 2, 2 * C)])
     _check_bf16(U, got, ref)
 
 
-def test_gemm_upsample_folded(U):
-    """nearest-2x + conv k3 p1 folded into [2C, 3C] weights over the low-res rows (resnet.py:157-170)."""
+@pytest.mark.parametrize("odd", [0, 1])
+def test_gemm_upsample_folded(U, odd):
+    """nearest resize to 2L or 2L - 1 rows + conv k3 p1 folded into the weights over the low-res rows (resnet.py:138-173):
+    [2C, 3C] over (x, -1) (x, 0) (x, +1) for 2L; [2C, 4C] over (x, -1) (x, 0) (x', 0) (x, +1) for 2L - 1, x' = x behind a
+    map one row shorter, and the odd half of the last GEMM row is neither stored nor counted in the GroupNorm partials."""
     from diffvits_b200.engine import pack_slot
     g = torch.Generator(device="cuda").manual_seed(5)
-    B, L, C = 2, 125, 256
+    B, L, C = 3, 125, 256
+    Ls = 2 * L - odd
     x = _rand((B, L, C), g)
     w = (torch.randn(C, C, 3, generator=g, device="cuda") * (3 * C) ** -0.5).to(torch.bfloat16).float()
     b = torch.randn(C, generator=g, device="cuda")
-    up = F.interpolate(x.float().transpose(1, 2), size=2 * L, mode="nearest")
-    ref = F.conv1d(up, w, b, padding=1).transpose(1, 2)                       # [B, 2L, C]
-    slot = dict(recipe="conv3_up2", shape=[2 * C, 3 * C], keys=["w"], dtype="bf16", name="t")
-    wp = pack_slot(slot, {"w": w.cpu()}).reshape(2 * C, 3 * C).cuda()
-    got = U.gemm([x], [(0, -1, 0, C), (0, 0, 0, C), (0, 1, 0, C)], wp, 2 * C, bias=torch.cat([b, b]))
-    _check_bf16(U, got.reshape(B, 2 * L, C), ref, rel=6e-3)                  # W1+W2 is rounded once more
+    up = F.interpolate(x.float().transpose(1, 2), size=Ls, mode="nearest")
+    ref = F.conv1d(up, w, b, padding=1).transpose(1, 2)                       # [B, Ls, C]
+    if odd:
+        slot = dict(recipe="conv3_up2_odd", shape=[2 * C, 4 * C], keys=["w"], dtype="bf16", name="t")
+        wp = pack_slot(slot, {"w": w.cpu()}).reshape(2 * C, 4 * C).cuda()
+        got, st = U.gemm([x, x], [(0, -1, 0, C), (0, 0, 0, C), (1, 0, 0, C), (0, 1, 0, C)], wp, 2 * C,
+                         bias=torch.cat([b, b]), views=[(L, C), (L - 1, C)], stats=True, layout=(Ls * C, C))
+    else:
+        slot = dict(recipe="conv3_up2", shape=[2 * C, 3 * C], keys=["w"], dtype="bf16", name="t")
+        wp = pack_slot(slot, {"w": w.cpu()}).reshape(2 * C, 3 * C).cuda()
+        got, st = U.gemm([x], [(0, -1, 0, C), (0, 0, 0, C), (0, 1, 0, C)], wp, 2 * C, bias=torch.cat([b, b]), stats=True,
+                         layout=(Ls * C, 0))
+    got = got.reshape(B, Ls, C)                                              # dense [B, Ls, C]: nothing spilled over
+    _check_bf16(U, got, ref, rel=6e-3)                                        # W0+W1 is rounded once more
+    # GroupNorm partials cover exactly the Ls x C stored values (folded: block kb and kb + C/16 are the same channels)
+    assert torch.isfinite(st).all()
+    tot = st.sum(dim=1)                                                       # [B, 2C/16, 2]
+    tot = tot[:, :C // 16] + tot[:, C // 16:]
+    y = got.float().reshape(B, Ls, C // 16, 16)
+    want = torch.stack([y.sum(dim=(1, 3)), (y * y).sum(dim=(1, 3))], dim=-1)
+    assert U.rel_l2(tot, want) < 2e-3
 
 
 def test_gemm_geglu_and_ncl(U):

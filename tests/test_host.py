@@ -66,7 +66,10 @@ def test_plan_manifest_and_errors(lib, seeded_unet):
     lib.dv_plan_destroy(p)
     # unsupported shapes / configs report instead of crashing (reference: ValueError in the ctor)
     q = C.c_void_p()
-    assert lib.dv_plan_create(C.byref(cfg), 1, 203, 50, C.byref(q)) == -4 and b"multiple" in lib.dv_last_error()
+    assert lib.dv_plan_create(C.byref(cfg), 1, 203, 50, C.byref(q)) == 0      # any length: 203 -> 102 -> 51 -> 26 frames
+    assert lib.dv_plan_op_count(q) + 3 == lib.dv_plan_launches_per_forward(q)
+    lib.dv_plan_destroy(q)
+    assert lib.dv_plan_create(C.byref(cfg), 1, 15, 50, C.byref(q)) == -1 and b"too short" in lib.dv_last_error()
     bad = _cfg(boc=(128, 200, 384, 512))
     assert lib.dv_plan_create(C.byref(bad), 1, 200, 50, C.byref(q)) == -4
     bad = _cfg(heads=32)
@@ -76,18 +79,25 @@ def test_plan_manifest_and_errors(lib, seeded_unet):
 
 
 def _tap_gemm_cpu(srcs, segs, w, l_out, views=None):
-    """CPU emulation of the tap-GEMM contract (csrc/kernels.h): out[b,l,n] = sum over segments of shifted rows."""
+    """CPU emulation of the tap-GEMM contract (csrc/kernels.h): out[b,l,n] = sum over segments of shifted rows.
+    views[si] = (rows, cols): the source's memory seen as `rows` rows of `cols` elements per batch item (batch stride
+    stays L*C, as in the TMA maps); rows outside [0, rows) are zero (TMA out-of-bounds fill), anything read past the end of
+    the tensor is NaN so that a view that touches memory it does not own poisons the result."""
     B = srcs[0].shape[0]
     cols = []
     for (si, ro, c0, ch) in segs:
         x = srcs[si]
-        if views is not None:
-            x = x.reshape(B, views[si][0], views[si][1])
-        L = x.shape[1]
-        pad = torch.zeros(B, l_out + 2, x.shape[2])
-        pad[:, 1:L + 1] = x                       # rows -1 and L.. are zero (TMA out-of-bounds fill)
-        idx = torch.arange(l_out) + ro + 1
-        cols.append(pad[:, idx, c0:c0 + ch])
+        L, C = x.shape[1], x.shape[2]
+        rows, vc = views[si] if views is not None and views[si] is not None else (L, C)
+        flat = torch.cat([x.reshape(-1), torch.full((2 * vc,), float("nan"))])
+        out = torch.zeros(B, l_out, ch)
+        for b in range(B):
+            for l in range(l_out):
+                r = l + ro
+                if 0 <= r < rows:
+                    s0 = b * L * C + r * vc + c0
+                    out[b, l] = flat[s0:s0 + ch]
+        cols.append(out)
     a = torch.cat(cols, dim=2)
     return a @ w.t()
 
@@ -114,17 +124,26 @@ def test_packing_recipes_match_reference_ops():
     got = _tap_gemm_cpu([x_in], [(0, -1, 0, 256), (0, 0, 0, 256), (0, 1, 0, 256)], wp, L)
     ref = F.conv1d(x_in[:, :, :228].transpose(1, 2), w_in, padding=1).transpose(1, 2)
     assert torch.allclose(got, ref, atol=1e-4)
-    # stride-2 conv through the [L/2, 2C] view
+    # stride-2 conv through the pair view [L/2, 2C]: first-half tap over ceil(L/2) rows, second-half taps over floor(L/2)
     wd = torch.randn(64, 64, 3, generator=g)
     wp = pack_slot(dict(recipe="conv3", shape=[128, 192, 64], keys=["w"], dtype="f32", name="t"), {"w": wd}).reshape(128, -1)
-    got = _tap_gemm_cpu([x], [(0, -1, 64, 64), (0, 0, 0, 64), (0, 0, 64, 64)], wp, L // 2, views=[(L // 2, 128)])[:, :, :64]
-    ref = F.conv1d(x.transpose(1, 2), wd, stride=2, padding=1).transpose(1, 2)
-    assert torch.allclose(got, ref, atol=1e-4)
-    # nearest-2x upsample folded into the weights
+    for Ld in (L, L - 1):                                      # even and odd input length
+        xd = x[:, :Ld].contiguous()
+        Lo = (Ld + 1) // 2
+        got = _tap_gemm_cpu([xd, xd], [(1, -1, 64, 64), (0, 0, 0, 64), (1, 0, 64, 64)], wp, Lo,
+                            views=[(Lo, 128), (Ld // 2, 128)])[:, :, :64]
+        ref = F.conv1d(xd.transpose(1, 2), wd, stride=2, padding=1).transpose(1, 2)
+        assert ref.shape[1] == Lo and torch.allclose(got, ref, atol=1e-4)
+    # nearest resize to 2L (3 K segments) or 2L - 1 rows (4 segments, x' = x without its last row) folded into the weights
     wu = torch.randn(64, 64, 3, generator=g)
     wp = pack_slot(dict(recipe="conv3_up2", shape=[128, 192], keys=["w"], dtype="f32", name="t"), {"w": wu}).reshape(128, -1)
     got = _tap_gemm_cpu([x], [(0, -1, 0, 64), (0, 0, 0, 64), (0, 1, 0, 64)], wp, L).reshape(B, 2 * L, 64)
     ref = F.conv1d(F.interpolate(x.transpose(1, 2), size=2 * L, mode="nearest"), wu, padding=1).transpose(1, 2)
+    assert torch.allclose(got, ref, atol=1e-4)
+    wp = pack_slot(dict(recipe="conv3_up2_odd", shape=[128, 256], keys=["w"], dtype="f32", name="t"), {"w": wu}).reshape(128, -1)
+    got = _tap_gemm_cpu([x, x], [(0, -1, 0, 64), (0, 0, 0, 64), (1, 0, 0, 64), (0, 1, 0, 64)], wp, L,
+                        views=[None, (L - 1, 64)]).reshape(B, 2 * L, 64)[:, :2 * L - 1]
+    ref = F.conv1d(F.interpolate(x.transpose(1, 2), size=2 * L - 1, mode="nearest"), wu, padding=1).transpose(1, 2)
     assert torch.allclose(got, ref, atol=1e-4)
     # GEGLU tile interleave (64 value rows, 64 gate rows, ...)
     wg = torch.randn(1024, 32, generator=g)

@@ -37,6 +37,20 @@ def test_unet_oracle_matches_golden_ragged(seeded_unet):
     assert rel_l2(out, ref) < 2e-5 and float((out - ref).abs().max()) < 1e-4
 
 
+def test_unet_oracle_matches_golden_odd_lengths(seeded_unet):
+    """Frame counts that are not multiples of 8: stride-2 convs over odd lengths, nearest resize to 2L - 1 rows."""
+    g = np.load(os.path.join(GOLD, "unet_oddlen.npz"))
+    sd = seeded_unet.state_dict()
+    for T, seed in ((203, 3), (198, 4)):
+        x, c, e = inputs.make_inputs(1, T, 40, seed=seed)
+        ref = torch.from_numpy(g[f"out{T}"])
+        out = unet_oracle.unet_forward(sd, torch.cat([x, c], 1), torch.tensor([613.0]), e)
+        assert out.shape == ref.shape == (1, 100, T)
+        assert rel_l2(out, ref) < 2e-5 and float((out - ref).abs().max()) < 1e-4
+        emu = unet_oracle.unet_forward(sd, torch.cat([x, c], 1), torch.tensor([613.0]), e, emulate_bf16=True)
+        assert rel_l2(emu, ref) < 1.5e-2
+
+
 def test_bf16_emulation_is_close_to_fp32(seeded_unet):
     """BF16-operand emulation stays within the reference's own autocast-BF16 distance (SURVEY: 1.05e-2 rel-L2)."""
     x_T, cond, ehs = inputs.make_inputs(1, 64, 96)
