@@ -499,7 +499,11 @@ struct Builder {
     }
     add_seg(g, 0, 1, 0, C);
     g.n = 2 * C; g.n_pad = round_up(2 * C, 128);
-    g.w_off = slot(key + ".W", odd ? "conv3_up2_odd" : "conv3_up2", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
+    // both packings live in the parameter blob so that its layout does not depend on (B, T, Tp): one packed blob per
+    // module serves every plan (engine.py: DenoiserGroup shares it)
+    const long long w3 = slot(key + ".W", "conv3_up2", {key + ".weight"}, "bf16", {g.n_pad, 3 * C});
+    const long long w4 = slot(key + ".Wodd", "conv3_up2_odd", {key + ".weight"}, "bf16", {g.n_pad, 4 * C});
+    g.w_off = odd ? w4 : w3;
     g.bias_off = slot(key + ".b", "vec_dup2", {key + ".bias"}, "f32", {g.n_pad});
     g.out = out; g.l_out = x.L; g.out_mode = GEMM_OUT_BF16; g.ld_out = 2 * C;
     g.out_bs = static_cast<long long>(Ls) * C;

@@ -81,7 +81,7 @@ __device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& 
 }
 
 // One 32-row x 32-column chunk of a bf16 output tile: (+bias) (+residual) -> bf16, GroupNorm partials, coalesced store.
-template <bool HAS_RES, bool HAS_STATS>
+template <bool HAS_RES, bool HAS_STATS, bool TRIM>
 __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx& e, uint32_t taddr_c, int gcol, int lq,
                                               size_t rowbase, size_t obase, bool valid, size_t stat_chunk, bool last,
                                               uint64_t* empty_bar, uint4 (&rv)[4], bool preloaded) {
@@ -132,7 +132,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     // GroupNorm partials per 16-channel block over this warp's 32 rows (fp32 accumulator values; the stored bf16
     // differs by rounding noise only). Fixed shuffle tree: deterministic.
     float a0 = s0.x + s0.y, b0 = q0.x + q0.y, a1 = s1.x + s1.y, b1 = q1.x + q1.y;
-    const bool trimmed = p.trim_col > 0 && gcol >= p.trim_col && lq + e.lane == p.L - 1;   // half row that does not exist
+    const bool trimmed = TRIM && gcol >= p.trim_col && lq + e.lane == p.L - 1;   // half row that does not exist
     if (!valid || trimmed) { a0 = b0 = a1 = b1 = 0.f; }
     a0 = warp_sum(a0); b0 = warp_sum(b0); a1 = warp_sum(a1); b1 = warp_sum(b1);
     if (e.lane == 0)
@@ -145,7 +145,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rrow = i * 8 + e.srow;
-    const bool keep = !(p.trim_col > 0 && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
+    const bool keep = !(TRIM && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
     if (lq + rrow < p.L && keep && !(p.dbg_flags & 8))
       *reinterpret_cast<uint4*>(out + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
           lds128(e.coal + i * 8 * EPI_PITCH);
@@ -153,7 +153,8 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
   __syncwarp();
 }
 
-template <int BN, int EW>
+// TRIM: instantiation for the odd-length folded upsample conv (output batch stride != L * ld_out, last half row absent)
+template <int BN, int EW, bool TRIM>
 __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using SL = SmemLayout<BN, EW>;
   constexpr int PARTS = EW / 4;                       // epilogue warps per TMEM lane quarter
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       const bool valid = l < p.L;
       if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 0);
       const size_t rowbase = static_cast<size_t>(b) * p.L;
-      const size_t obase = static_cast<size_t>(b) * p.out_bs;
+      const size_t obase = TRIM ? static_cast<size_t>(b) * p.out_bs : rowbase * p.ld_out;
       uint4 rv[4];
       bool preloaded = false;
       if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && n0 + part * 32 < p.N && !(p.dbg_flags & (1 | 32))) {
@@ -389,11 +390,11 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           arrived |= last;
           const uint32_t tc = taddr + ch * 32;
           if (has_res) {
-            if (has_stats) epi_chunk_bf16<true, true>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
-            else           epi_chunk_bf16<true, false>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            if (has_stats) epi_chunk_bf16<true, true, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<true, false, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           } else {
-            if (has_stats) epi_chunk_bf16<false, true>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
-            else           epi_chunk_bf16<false, false>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            if (has_stats) epi_chunk_bf16<false, true, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<false, false, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           }
         }
         if (!arrived) {                                   // this warp's columns were all padding
@@ -443,13 +444,13 @@ __global__ void gemm_ref_kernel(GemmParams p, GemmRefSrc s0, GemmRefSrc s1, Gemm
 int g_num_sms = 0;
 int g_force_ew = 0;   // DV_GEMM_EW: 8 / 16 force the CTA shape of the 128-wide tile kernel (0 = heuristic)
 
-template <int BN, int EW>
+template <int BN, int EW, bool TRIM = false>
 cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
   using SL = SmemLayout<BN, EW>;
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / BN);
   const int slots = g_num_sms * (EW == 8 ? 2 : 1);
   const int grid = tiles < slots ? tiles : slots;
-  return launch_k(gemm_tc_kernel<BN, EW>, dim3(grid), dim3(64 + EW * 32), SL::dyn_bytes(p.n_pad), st, p);
+  return launch_k(gemm_tc_kernel<BN, EW, TRIM>, dim3(grid), dim3(64 + EW * 32), SL::dyn_bytes(p.n_pad), st, p);
 }
 
 }  // namespace
@@ -471,27 +472,33 @@ cudaError_t gemm_tc_init() {
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
   }
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SmemLayout<128, 8>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
   {
     const char* ev = getenv("DV_GEMM_EW");
     if (ev) g_force_ew = atoi(ev);
   }
-  e = cudaFuncSetAttribute(gemm_tc_kernel<192, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_tc_kernel<192, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SmemLayout<192, 16>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_tc_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<256, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_tc_kernel<256, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
 }
 
 cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   GemmParams p = p_in;
   if (p.out_bs == 0) p.out_bs = static_cast<long long>(p.L) * p.ld_out;
-  if (p.trim_col % 32 != 0 || (p.trim_col > 0 && p.out_mode != GEMM_OUT_BF16)) return cudaErrorInvalidValue;
+  if (p.trim_col % 32 != 0) return cudaErrorInvalidValue;
   if (g_num_sms == 0) {
     cudaError_t e = gemm_tc_init();
     if (e != cudaSuccess) return e;
@@ -499,6 +506,12 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   if (p.n_pad % 128 != 0 || p.n_pad > MAX_NPAD || p.nseg < 1 || p.nseg > GEMM_MAX_SEG) return cudaErrorInvalidValue;
   if (p.out_mode == GEMM_OUT_GEGLU && p.n_pad % 128 != 0) return cudaErrorInvalidValue;
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
+  const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
+  if (p.trim_col > 0 || !dense) {                        // odd-length folded upsample conv: its own instantiations
+    if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
+    if (bn == 256 && p.n_pad % 256 == 0) return launch_bn<256, 16, true>(p, st);
+    return launch_bn<128, 16, true>(p, st);
+  }
   if (bn == 256) {
     if (p.n_pad % 256 != 0) return cudaErrorInvalidValue;
     return launch_bn<256, 16>(p, st);
