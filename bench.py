@@ -193,9 +193,12 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE line (rank 0's JSON): everything libraries print there (NCCL's version banner goes to
+    # fd 1 from C) is sent to stderr by swapping the descriptors for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     import diffvits_b200
     from diffvits_b200 import synthetic as inputs       # the native arm never imports oracle/
@@ -416,7 +419,9 @@ def run_native(args):
                           f"reference (same torch CPU ops, FP32, without the reference's per-step PromptEncoder)"}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
 
 
 def main():
