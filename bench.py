@@ -326,7 +326,8 @@ def run_native(args):
             diffvits_b200.sample_native(unet, x_d, cond_d, ehs_d, sampler=sampler, steps=nfe, betas=betas, native=native)
 
         def timed_local(iters=2):
-            step_local()                                          # (re)captures the loop graph after a mask change
+            step_local()                                          # after a mask change: first sight runs eagerly,
+            step_local()                                          # the second one captures the loop graph
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

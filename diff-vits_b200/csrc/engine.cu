@@ -1125,15 +1125,13 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
     DV_CK(cudaMemcpyAsync(p->ws + p->off_ttab, t_in, static_cast<size_t>(nsteps) * 4, cudaMemcpyHostToDevice, st));
     DV_CK(cudaMemcpyAsync(p->ws + p->off_x, x[i], nel * 4, cudaMemcpyDeviceToDevice, st));
   }
-  if (flags & DV_SAMPLE_NO_GRAPH) {
-    int launches = 0;
-    for (int i = 0; i < n; ++i) {
-      int rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, st, &launches, err);
-      if (rc != DV_OK) return rc;
-    }
-    lead->last_sample_launches = launches;
-  } else {
-    uint64_t key = 1469598103934665603ull;
+  // The loop of a (plans, sampler, table) combination runs eagerly the FIRST time it is seen and is captured into a CUDA
+  // graph when it comes back: capture + instantiate of ~16 k kernel nodes costs ~45 ms, as much as a third of a one-shot
+  // synthesis (tts_infer.py sees a new T per call), while eager enqueue is as fast as a replay at those sizes and is
+  // bit-identical (tests). DV_GRAPH_FIRST=1 captures at first sight.
+  uint64_t key = 1469598103934665603ull;
+  bool eager = (flags & DV_SAMPLE_NO_GRAPH) != 0;
+  if (!eager) {
     key = fnv1a(key, &sampler, sizeof sampler);
     key = fnv1a(key, &nsteps, sizeof nsteps);
     key = fnv1a(key, &rt, sizeof rt);
@@ -1141,6 +1139,21 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
     key = fnv1a(key, coef, static_cast<size_t>(nsteps) * 8 * 4);
     key = fnv1a(key, plans, static_cast<size_t>(n) * sizeof(Plan*));
     for (int i = 0; i < n; ++i) key = fnv1a(key, &plans[i]->graph_epoch, sizeof(uint64_t));
+    const bool have = lead->graph_exec && key == lead->graph_key;
+    const char* gf = getenv("DV_GRAPH_FIRST");
+    if (!have && key != lead->pending_key && !(gf && gf[0] == '1')) {
+      lead->pending_key = key;
+      eager = true;
+    }
+  }
+  if (eager) {
+    int launches = 0;
+    for (int i = 0; i < n; ++i) {
+      int rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, st, &launches, err);
+      if (rc != DV_OK) return rc;
+    }
+    lead->last_sample_launches = launches;
+  } else {
     if (!lead->graph_exec || key != lead->graph_key) {
       if (lead->graph_exec) { cudaGraphExecDestroy(lead->graph_exec); lead->graph_exec = nullptr; }
       for (int i = 0; i < n; ++i) {

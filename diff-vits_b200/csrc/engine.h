@@ -126,6 +126,7 @@ struct Plan {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_tfork = nullptr, ev_tjoin = nullptr;
   uint64_t graph_key = 0;
+  uint64_t pending_key = 0;   // loop seen once (run eagerly): it is captured when it comes back
   uint64_t graph_epoch = 0;   // bumped whenever launches baked into a captured graph become stale
   int graph_launches = 0;
 

@@ -97,7 +97,10 @@ DV_API int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const
  * the reference's own NoiseScheduleVP formulas.  t_in: host [nsteps] model times. coef: host [nsteps * 8]:
  *   DV_SAMPLER_DPMPP_2M  row i (update to t_{i+1}): {A, B, C, has_prev, alpha_prev, sigma_prev, 0, 0}
  *   DV_SAMPLER_UNIPC_BH2 row i: {a, b, cp, cc, d, has_prev, use_corrector, 0}
- * x: device NCT [B, x_channels, T] fp32, noise in, latent out. flags: DV_SAMPLE_* */
+ * x: device NCT [B, x_channels, T] fp32, noise in, latent out. flags: DV_SAMPLE_*
+ * A loop (plan, sampler, tables) is enqueued directly the first time it is seen and captured when the same loop comes
+ * back (capture + instantiate cost ~45 ms, a third of a one-shot synthesis); DV_GRAPH_FIRST=1 in the environment
+ * captures at first sight. Both paths issue the same kernels and give identical bits. */
 #define DV_SAMPLER_DPMPP_2M 0
 #define DV_SAMPLER_UNIPC_BH2 1
 #define DV_SAMPLE_NO_GRAPH 1     /* enqueue directly instead of capturing/replaying a graph */

@@ -148,7 +148,7 @@ def test_sampling_loops_vs_reference_golden(env):
         assert torch.equal(lat, eager)          # graph replay == direct enqueue, bit for bit
         again = diffvits_b200.sample_native(unet, x_T.cuda(), cond.cuda(), ehs.cuda(), sampler=sampler, steps=steps,
                                             betas=betas, native=native)
-        assert torch.equal(lat, again)          # deterministic (no atomics on the value path except fp64 GN sums)
+        assert torch.equal(lat, again)          # second sight of the loop = captured graph replay: deterministic, same bits
     # first-step denoiser outputs are teacher forced by construction (same x_T)
     first = native(x_T.cuda(), torch.tensor([999.0], device="cuda"))
     ref0 = torch.from_numpy(g["dpm_steps"][0]).cuda()

@@ -108,6 +108,9 @@ def test_c5_long_form_call_and_loop(env):
     b = diffvits_b200.sample_native(unet, x_T, cond, ehs, sampler="unipc", steps=25, betas=betas, native=native,
                                     graph=False)
     assert torch.isfinite(a).all() and torch.equal(a, b)
+    # the first sight of a loop runs eagerly, the second one is captured: this one is the graph replay
+    c = diffvits_b200.sample_native(unet, x_T, cond, ehs, sampler="unipc", steps=25, betas=betas, native=native)
+    assert torch.equal(a, c)
 
 
 def test_eager_pytorch_bar_on_same_gpu(env):
