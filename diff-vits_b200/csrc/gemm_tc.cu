@@ -199,14 +199,28 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above touched only static data (weights, descriptors); activations of earlier kernels from here on
-  pdl_wait();
-
+  // everything above touched only static data (weights, descriptors); activations of earlier kernels are read only after
+  // griddepcontrol.wait. The producer first puts the W panels of its first ring of stages in flight (weights are static):
+  // with PDL that load latency overlaps the previous kernel's tail instead of following it.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      int pre = 0;                                        // stages whose expect_tx + W loads are already issued
+      if (!(p.dbg_flags & (4 | 64))) {
+        const int n0 = (blockIdx.x % n_tiles_n) * BN;
+        pre = total_panels < STAGES ? total_panels : STAGES;
+        for (int st = 0; st < pre; ++st) {
+          uint8_t* sb = smem + st * SL::STAGE_BYTES + SL::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[st], SL::STAGE_BYTES);
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h)
+            tma_load_2d(sb + h * (64 * BK * 2), &p.mapW, &full_bar[st], st * BK, n0 + h * 64);
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;                                     // panels issued by this CTA so far (across tiles)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mi = tile / n_tiles_n;
         const int n0 = (tile % n_tiles_n) * BN;
@@ -217,10 +231,15 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
         for (int s = 0; s < p.nseg; ++s) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* ma = &p.mapA[sg.src];
-          for (int q = 0; q < sg.npanels; ++q, ++kp) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+          for (int q = 0; q < sg.npanels; ++q, ++kp, ++issued) {
             uint8_t* sa = smem + stage * SL::STAGE_BYTES;
             uint8_t* sb = sa + SL::A_BYTES;
+            if (issued < pre) {                           // first ring: barrier armed and W already in flight
+              tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
             if (p.dbg_flags & 4) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
             mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
             tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
@@ -232,9 +251,12 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           }
         }
       }
+    } else {
+      pdl_wait();
     }
     __syncwarp();
   } else if (warp == 1) {
+    pdl_wait();
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
@@ -270,6 +292,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     }
     __syncwarp();
   } else {
+    pdl_wait();
     // ------------------------------------------------------------------ epilogue: warps 2..17
     // TMEM lane quarter is fixed by hardware to (warp id % 4); the four warps of a quarter split the columns.
     const int quad = warp & 3;

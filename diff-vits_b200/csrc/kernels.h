@@ -65,7 +65,7 @@ struct alignas(64) GemmParams {
   float* stats;         // optional GroupNorm partials of the stored tensor: [B][tiles_per_batch*4][stats_nblk][2]
   int stats_nblk;       // 16-channel blocks per row chunk (= N / 16)
   int bn;               // N tile (128 / 256); 0 = choose
-  int dbg_flags;        // debug: 1 = skip the epilogue body (release TMEM only), 2 = skip MMA issue, 4 = skip TMA loads, 32 = no residual preload
+  int dbg_flags;        // debug: 1 = skip the epilogue body (release TMEM only), 2 = skip MMA issue, 4 = skip TMA loads, 32 = no residual preload, 64 = no W prefetch before griddepcontrol.wait
   unsigned long long* trace;  // debug: CTA 0 appends (role, tile, event, clock) records; [0] = record count
 };
 
