@@ -89,6 +89,30 @@ def test_c3_ragged_prompt_call_and_unipc_loop(env):
     assert U.rel_l2(big(x_T, t)[r:r + 1], one(x_T[r:r + 1], t)) < 1e-6
 
 
+@pytest.mark.parametrize("B,T,Tp,lens", [(1, 16, 1, None), (2, 17, 5, [5, 0]), (3, 33, 282, [282, 1, 140]),
+                                         (1, 1023, 64, None), (5, 136, 40, None)])
+def test_edge_shapes_vs_emulating_oracle(env, B, T, Tp, lens):
+    """Smallest frame counts the four levels allow (16 -> 8 -> 4 -> 2, 17 -> 9 -> 5 -> 3), a one-frame prompt, a fully
+    masked prompt (length 0: the reference's -10000 bias then cancels in the softmax and every key is attended), odd
+    lengths just below a tile boundary, a batch that is not a multiple of anything. Checked against the BF16-emulating
+    oracle (itself pinned to the reference at T = 200 / 203 / 198 / 64 by goldens)."""
+    U, unet, uo = env["U"], env["unet"], env["uo"]
+    x, c, e = (v.cuda() for v in env["inputs"].make_inputs(B, T, Tp, seed=100 + T))
+    mask = None
+    if lens is not None:
+        mask = (torch.arange(Tp, device="cuda")[None, :] < torch.tensor(lens, device="cuda")[:, None])
+        e = e * mask[:, :, None]
+    t = torch.full((B,), 431.5, device="cuda")
+    sample = torch.cat([x, c], 1)
+    out = unet(sample, t, e, encoder_attention_mask=mask).sample
+    emu = uo.unet_forward(env["sd"], sample, t, e, mask=mask, emulate_bf16=True)
+    ref = uo.unet_forward(env["sd"], sample, t, e, mask=mask)
+    print(f"B={B} T={T} Tp={Tp} lens={lens}: vs emulating oracle rel {U.rel_l2(out, emu):.3e}, vs fp32 oracle "
+          f"{U.rel_l2(out, ref):.3e} max {U.max_abs(out, ref):.3e}")
+    assert out.shape == (B, 100, T) and torch.isfinite(out).all()
+    assert U.rel_l2(out, emu) < 1.5e-2 and U.rel_l2(out, ref) < 1.5e-2 and U.max_abs(out, ref) < 4e-2
+
+
 def test_c5_long_form_call_and_loop(env):
     """C5 shape (T = 4000): one call against the emulating oracle, then the 25-step UniPC loop: finite, deterministic,
     graph replay == direct enqueue."""
