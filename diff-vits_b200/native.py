@@ -102,6 +102,21 @@ def tick_progress(native: NativeDenoiser, n: int) -> None:
         bar.update(n)
 
 
+_SCHEDULES: dict = {}
+
+
+def _schedule_for(betas: torch.Tensor, clip_lambda) -> NoiseScheduleVP:
+    """One NoiseScheduleVP per (betas content, clip): building it costs ~1 ms of host time per call otherwise."""
+    b = betas.detach().to("cpu", torch.float32).contiguous()
+    key = (hash(b.numpy().tobytes()), b.numel(), clip_lambda)
+    ns = _SCHEDULES.get(key)
+    if ns is None:
+        if len(_SCHEDULES) >= 16:
+            _SCHEDULES.clear()
+        ns = _SCHEDULES[key] = NoiseScheduleVP("discrete", betas=b, clip_lambda=clip_lambda)
+    return ns
+
+
 @torch.no_grad()
 def sample_native(unet, x_T: torch.Tensor, cond: torch.Tensor, ehs: torch.Tensor,
                   kv_len: Optional[torch.Tensor] = None, *, sampler: str = "dpmsolver++", steps: int = 50,
@@ -114,8 +129,7 @@ def sample_native(unet, x_T: torch.Tensor, cond: torch.Tensor, ehs: torch.Tensor
     if noise_schedule is None:
         if betas is None:
             raise ValueError("pass `betas` (the model's discrete schedule, model3.py:978) or a NoiseScheduleVP")
-        noise_schedule = NoiseScheduleVP("discrete", betas=betas.detach().cpu(),
-                                         clip_lambda=-5.1 if sampler == "dpmsolver++" else None)
+        noise_schedule = _schedule_for(betas, -5.1 if sampler == "dpmsolver++" else None)
     ns = noise_schedule
     if native is None:
         native = NativeDenoiser(unet, cond, ehs, kv_len)
