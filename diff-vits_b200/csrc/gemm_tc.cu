@@ -40,7 +40,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = EW == 8 ? 2 : (BN == 128 ? 5 : (BN == 192 ? 4 : 3));
+  static constexpr int STAGES = EW == 8 ? 2 : (BN == 64 ? 6 : (BN == 128 ? 5 : (BN == 192 ? 4 : 3)));
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EW * EPI_SLAB;
   static constexpr int BIAS_OFF = BAR_OFF + 256;       // barriers + tmem slot, then the bias vector (n_pad floats)
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       const size_t obase = TRIM ? static_cast<size_t>(b) * p.out_bs : rowbase * p.ld_out;
       uint4 rv[4];
       bool preloaded = false;
-      if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && n0 + part * 32 < p.N && !(p.dbg_flags & (1 | 32))) {
+      if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && part * 32 < BN && n0 + part * 32 < p.N && !(p.dbg_flags & (1 | 32))) {
         epi_load_res(p, e, n0 + part * 32, lq, rowbase, rv);
         preloaded = true;
       }
@@ -480,6 +480,9 @@ cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
 
 int gemm_pick_bn(int m_tiles, int n_pad) {
   if (g_num_sms == 0) return 128;
+  // small problems (a handful of row tiles: batch 1-4): 64-wide tiles put twice as many SMs to work and halve the W bytes
+  // each CTA streams; the main loop of a lone CTA is bound by what one SM can pull from L2 (~0.3 us per 32 KB panel)
+  if (m_tiles * (n_pad / 128) <= g_num_sms / 4 && !getenv("DV_GEMM_NO64")) return 64;
   // N = 384 (level 2): 2 x 64 tiles of 128 x 128 rows would be 192 tiles = 1.3 waves; 192-wide tiles make it one wave
   if (n_pad == 384 && m_tiles * 2 <= g_num_sms && !getenv("DV_GEMM_NO192")) return 192;
   if (n_pad % 256 != 0) return 128;
@@ -507,6 +510,9 @@ cudaError_t gemm_tc_init() {
   }
   e = cudaFuncSetAttribute(gemm_tc_kernel<192, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SmemLayout<192, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<64, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<64, 16>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
@@ -543,6 +549,7 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
     if (p.n_pad % 192 != 0 || p.out_mode == GEMM_OUT_GEGLU) return cudaErrorInvalidValue;
     return launch_bn<192, 16>(p, st);
   }
+  if (bn == 64 && p.out_mode != GEMM_OUT_GEGLU) return launch_bn<64, 16>(p, st);   // GEGLU pairs u / gate inside 128 columns
   // two small CTAs per SM pay once there is more than one wave of 128-wide tiles (measured on the C2 shapes: 5-10 %
   // faster at levels 0-2, slower for the few long-K tiles of level 3)
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / 128);

@@ -44,7 +44,7 @@ def test_gemm_linear(U, B, L, K, N):
     assert U.rel_l2(raw[:, :, :N], a.float() @ w.float().t() + bias) < 1e-5
 
 
-@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 256])
 def test_gemm_tile_width_and_groupnorm_partials(U, bn):
     """Both N-tile instantiations (persistent schedule over many tiles) + the epilogue's GroupNorm partial sums:
     per (32-row chunk, 16-channel block) sum / sum of squares of the fp32 accumulator values (the stored bf16 values

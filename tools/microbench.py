@@ -85,8 +85,8 @@ def main():
                 segs = [(0, t - 1, 0, K1) for t in range(3)] if taps == 3 else [(0, 0, 0, K1)]
                 G = (GemmSeg * len(segs))(*[GemmSeg(s, ro, c0, ch // 64) for (s, ro, c0, ch) in segs])
                 stt = torch.zeros(B, (L + 127) // 128 * 4, N // 16, 2, device="cuda") if stats else None
-                for bn in (128, 192, 256):
-                    if N % bn or (bn == 192 and (N != 384 or mode == 2)):
+                for bn in (64, 128, 192, 256):
+                    if N % bn or (bn == 192 and (N != 384 or mode == 2)) or (bn == 64 and (mode == 2 or B * L > 4096)):
                         continue
 
                     def fn(st):
