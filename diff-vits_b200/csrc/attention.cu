@@ -257,8 +257,10 @@ __device__ __forceinline__ uint32_t exp2_poly_pack(float2 t) {
   return pack_bf16(__uint_as_float(r0), __uint_as_float(r1));
 }
 
-template <int D, int POLYJ>
-__global__ void __launch_bounds__(ATT_THREADS) attention2_kernel(const AttnParams p) {
+template <int D, int POLYJ, int NW>
+__global__ void __launch_bounds__(32 * NW) attention2_kernel(const AttnParams p) {
+  constexpr int BQ = 16 * NW;           // queries per CTA (shadows the file-level 64)
+  constexpr int ATT_THREADS = 32 * NW;
   constexpr int PITCH = D + 8;          // elements; +16 bytes
   constexpr int CHUNKS = D / 8;         // 16-byte chunks per row
   __shared__ __align__(16) __nv_bfloat16 sQ[BQ * PITCH];
@@ -435,11 +437,16 @@ constexpr int kDefaultPolyJ = 0;   // measured (profiles/r1f_attention_v2.txt): 
 template <int POLYJ>
 cudaError_t launch_attention2(const AttnParams& p, cudaStream_t st) {
   dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
+  // d = 32: 8 warps / 128 queries per CTA share every K/V tile load between twice the rows: 38.6 vs 40.2 us (self) and 26.3 vs
+  // 27.3 us (cross) at the C2 level-1 shapes; at d = 16 the same is slower (104.6 vs 100.4 us). DV_ATTN_NW4=1 turns it off.
+  static const bool wide32 = getenv("DV_ATTN_NW4") == nullptr;
+  if (POLYJ == 0 && wide32 && p.D == 32 && p.Lq > 64)
+    return launch_k(attention2_kernel<32, 0, 8>, dim3((p.Lq + 127) / 128, p.H, p.B), dim3(256), 0, st, p);
   switch (p.D) {
-    case 16: return launch_k(attention2_kernel<16, POLYJ>, grid, dim3(ATT_THREADS), 0, st, p);
-    case 32: return launch_k(attention2_kernel<32, POLYJ>, grid, dim3(ATT_THREADS), 0, st, p);
-    case 48: return launch_k(attention2_kernel<48, POLYJ>, grid, dim3(ATT_THREADS), 0, st, p);
-    case 64: return launch_k(attention2_kernel<64, POLYJ>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 16: return launch_k(attention2_kernel<16, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 32: return launch_k(attention2_kernel<32, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 48: return launch_k(attention2_kernel<48, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 64: return launch_k(attention2_kernel<64, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
     default: return cudaErrorInvalidValue;
   }
 }
