@@ -437,11 +437,15 @@ constexpr int kDefaultPolyJ = 0;   // measured (profiles/r1f_attention_v2.txt): 
 template <int POLYJ>
 cudaError_t launch_attention2(const AttnParams& p, cudaStream_t st) {
   dim3 grid((p.Lq + BQ - 1) / BQ, p.H, p.B);
-  // d = 32: 8 warps / 128 queries per CTA share every K/V tile load between twice the rows: 38.6 vs 40.2 us (self) and 26.3 vs
-  // 27.3 us (cross) at the C2 level-1 shapes; at d = 16 the same is slower (104.6 vs 100.4 us). DV_ATTN_NW4=1 turns it off.
-  static const bool wide32 = getenv("DV_ATTN_NW4") == nullptr;
-  if (POLYJ == 0 && wide32 && p.D == 32 && p.Lq > 64)
-    return launch_k(attention2_kernel<32, 0, 8>, dim3((p.Lq + 127) / 128, p.H, p.B), dim3(256), 0, st, p);
+  // d = 32 / 48: 8 warps / 128 queries per CTA share every K/V tile load between twice the rows: 38.6 vs 40.2 us (self) and 26.3
+  // vs 27.3 us (cross) at the C2 level-1 shapes, 18.3 vs 18.8 and 21.3 vs 22.0 us at level 2; at d = 16 the same is slower
+  // (104.6 vs 100.4 us) and at d = 64 the tiles do not fit the static 48 KB. DV_ATTN_NW4=1 turns it off.
+  static const bool wide = getenv("DV_ATTN_NW4") == nullptr;
+  if (POLYJ == 0 && wide && p.Lq > 64) {
+    dim3 grid8((p.Lq + 127) / 128, p.H, p.B);
+    if (p.D == 32) return launch_k(attention2_kernel<32, 0, 8>, grid8, dim3(256), 0, st, p);
+    if (p.D == 48) return launch_k(attention2_kernel<48, 0, 8>, grid8, dim3(256), 0, st, p);
+  }
   switch (p.D) {
     case 16: return launch_k(attention2_kernel<16, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
     case 32: return launch_k(attention2_kernel<32, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
