@@ -257,8 +257,9 @@ __device__ __forceinline__ uint32_t exp2_poly_pack(float2 t) {
   return pack_bf16(__uint_as_float(r0), __uint_as_float(r1));
 }
 
-template <int D, int POLYJ, int NW>
+template <int D, int POLYJ, int NW, int TK>
 __global__ void __launch_bounds__(32 * NW) attention2_kernel(const AttnParams p) {
+  constexpr int BKV = TK;               // keys per tile (shadows the file-level 64): 48 when that pads Lk less (Lk = 282)
   constexpr int BQ = 16 * NW;           // queries per CTA (shadows the file-level 64)
   constexpr int ATT_THREADS = 32 * NW;
   constexpr int PITCH = D + 8;          // elements; +16 bytes
@@ -440,17 +441,28 @@ cudaError_t launch_attention2(const AttnParams& p, cudaStream_t st) {
   // d = 32 / 48: 8 warps / 128 queries per CTA share every K/V tile load between twice the rows: 38.6 vs 40.2 us (self) and 26.3
   // vs 27.3 us (cross) at the C2 level-1 shapes, 18.3 vs 18.8 and 21.3 vs 22.0 us at level 2; at d = 16 the same is slower
   // (104.6 vs 100.4 us) and at d = 64 the tiles do not fit the static 48 KB. DV_ATTN_NW4=1 turns it off.
+  // 48-key tiles when they pad the key count less than 64-key tiles do (prompt cross-attention: Lk = 282 -> 288 instead of 320)
+  static const bool tk48 = getenv("DV_ATTN_NO48") == nullptr;
+  // (C2 shapes, us: d = 16 31.7 vs 35.4, d = 32 24.4 vs 26.3, d = 48 20.8 vs 21.3; d = 64 is slower with them: 15.5 vs 14.1)
+  const bool use48 = tk48 && POLYJ == 0 && p.D <= 48 && ((p.Lk + 47) / 48) * 48 * 100 < ((p.Lk + 63) / 64) * 64 * 92;
   static const bool wide = getenv("DV_ATTN_NW4") == nullptr;
   if (POLYJ == 0 && wide && p.Lq > 64) {
     dim3 grid8((p.Lq + 127) / 128, p.H, p.B);
-    if (p.D == 32) return launch_k(attention2_kernel<32, 0, 8>, grid8, dim3(256), 0, st, p);
-    if (p.D == 48) return launch_k(attention2_kernel<48, 0, 8>, grid8, dim3(256), 0, st, p);
+    if (p.D == 32) return use48 ? launch_k(attention2_kernel<32, 0, 8, 48>, grid8, dim3(256), 0, st, p)
+                                : launch_k(attention2_kernel<32, 0, 8, 64>, grid8, dim3(256), 0, st, p);
+    if (p.D == 48) return use48 ? launch_k(attention2_kernel<48, 0, 8, 48>, grid8, dim3(256), 0, st, p)
+                                : launch_k(attention2_kernel<48, 0, 8, 64>, grid8, dim3(256), 0, st, p);
+  }
+  if (use48) {
+    if (p.D == 16) return launch_k(attention2_kernel<16, 0, 4, 48>, grid, dim3(ATT_THREADS), 0, st, p);
+    if (p.D == 32) return launch_k(attention2_kernel<32, 0, 4, 48>, grid, dim3(ATT_THREADS), 0, st, p);
+    if (p.D == 48) return launch_k(attention2_kernel<48, 0, 4, 48>, grid, dim3(ATT_THREADS), 0, st, p);
   }
   switch (p.D) {
-    case 16: return launch_k(attention2_kernel<16, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
-    case 32: return launch_k(attention2_kernel<32, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
-    case 48: return launch_k(attention2_kernel<48, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
-    case 64: return launch_k(attention2_kernel<64, POLYJ, 4>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 16: return launch_k(attention2_kernel<16, POLYJ, 4, 64>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 32: return launch_k(attention2_kernel<32, POLYJ, 4, 64>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 48: return launch_k(attention2_kernel<48, POLYJ, 4, 64>, grid, dim3(ATT_THREADS), 0, st, p);
+    case 64: return launch_k(attention2_kernel<64, POLYJ, 4, 64>, grid, dim3(ATT_THREADS), 0, st, p);
     default: return cudaErrorInvalidValue;
   }
 }
