@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiffvits_b200.so")
+# DV_DEBUG_LIB=1 loads the measurement build (libdiffvits_b200_dbg.so, include/diffvits_b200_debug.h) instead of the
+# product library; it is only ever selected explicitly, by profiling tools.
+DEBUG_LIB = os.environ.get("DV_DEBUG_LIB", "0") == "1"
+LIB_PATH = os.path.join(_HERE, "libdiffvits_b200_dbg.so" if DEBUG_LIB else "libdiffvits_b200.so")
 
 
 class DVError(RuntimeError):
@@ -42,6 +45,10 @@ class GemmSeg(C.Structure):
     _fields_ = [("src", C.c_int), ("row_off", C.c_int), ("c0", C.c_int), ("npanels", C.c_int)]
 
 
+class GemmOpts(C.Structure):
+    _fields_ = [("bn", C.c_int), ("stats", C.c_void_p), ("out_bs", C.c_longlong), ("trim_col", C.c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/diffvits_b200.h one to one
 _vp, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 SIGNATURES = {
@@ -66,12 +73,7 @@ SIGNATURES = {
     "dv_plan_op_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dv_plan_profile_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp, C.POINTER(_f), _i, _vp]),
     "dv_gemm": (_i, [C.POINTER(GemmSrc), _i, C.POINTER(GemmSeg), _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i,
-                     _i, _i, _vp]),
-    "dv_gemm_test_options": (None, [_i, _vp]),
-    "dv_gemm_test_trace": (None, [_vp]),
-    "dv_gemm_test_flags": (None, [_i]),
-    "dv_gemm_test_layout": (None, [C.c_longlong, _i]),
-    "dv_debug_skip_kinds": (_i, [_i]),
+                     _i, _i, C.POINTER(GemmOpts), _vp]),
     "dv_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "dv_groupnorm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
     "dv_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
@@ -80,6 +82,13 @@ SIGNATURES = {
     "dv_unipc_predict": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _sz, _vp]),
     "dv_unipc_correct": (_i, [_vp, _vp, _vp, _vp, _f, _sz, _vp]),
     "dv_nct_to_ntc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+# include/diffvits_b200_debug.h: present only in the debug library
+DEBUG_SIGNATURES = {
+    "dv_gemm_test_trace": (None, [_vp]),
+    "dv_gemm_test_flags": (None, [_i]),
+    "dv_debug_skip_kinds": (_i, [_i]),
 }
 
 _lib = None
@@ -96,7 +105,10 @@ def load() -> C.CDLL:
             "diffvits_b200 has no CPU or PyTorch fallback path."
         )
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    sigs = dict(SIGNATURES)
+    if DEBUG_LIB:
+        sigs.update(DEBUG_SIGNATURES)
+    for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args

@@ -13,14 +13,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libdiffvits_b200.so")
+# DV_DEBUG=1 builds the measurement variant (-DDV_DEBUG_HOOKS: timing-ablation switches, CTA timelines, dv_debug_* entry
+# points of include/diffvits_b200_debug.h) as a separate library; the product library never contains them.
+DEBUG = os.environ.get("DV_DEBUG", "0") == "1"
+BUILD = os.path.join(HERE, "build_dbg" if DEBUG else "build")
+LIB = os.path.join(HERE, "libdiffvits_b200_dbg.so" if DEBUG else "libdiffvits_b200.so")
 SOURCES = ["gemm_tc.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "norm.cu", "elementwise.cu", "engine.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-diag-suppress", "550",
-]
+] + (["-DDV_DEBUG_HOOKS"] if DEBUG else [])
 
 
 def _nvcc() -> str:
@@ -33,6 +36,7 @@ def _nvcc() -> str:
 def _newest_header() -> float:
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hs.append(os.path.join(HERE, "..", "include", "diffvits_b200.h"))
+    hs.append(os.path.join(HERE, "..", "include", "diffvits_b200_debug.h"))
     return max(os.path.getmtime(h) for h in hs)
 
 

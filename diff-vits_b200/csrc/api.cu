@@ -4,6 +4,9 @@
 #include <string>
 
 #include "engine.h"
+#ifdef DV_DEBUG_HOOKS
+#include "../../include/diffvits_b200_debug.h"
+#endif
 
 struct dv_plan {
   dv::Plan impl;
@@ -21,6 +24,18 @@ int ck(cudaError_t e, const char* what) {
   return DV_ERR_CUDA;
 }
 cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+// Every entry point that takes a plan runs on the plan's device (the one its workspace lives on, recorded by dv_plan_bind),
+// whatever device is current in the calling thread; the caller's current device is restored on return.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(int dev) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 // There is no CPU path: refuse loudly when no sm_100 device is current.
 int require_device() {
@@ -55,7 +70,11 @@ int dv_plan_create(const dv_unet_cfg* cfg, int B, int T, int Tp, dv_plan** out) 
   *out = p;
   return DV_OK;
 }
-void dv_plan_destroy(dv_plan* plan) { delete plan; }
+void dv_plan_destroy(dv_plan* plan) {
+  if (!plan) return;
+  DevGuard guard(plan->impl.device);   // streams / events / graph were created on the plan's device
+  delete plan;
+}
 size_t dv_plan_workspace_bytes(const dv_plan* plan) { return plan ? plan->impl.ws_bytes : 0; }
 size_t dv_plan_param_bytes(const dv_plan* plan) { return plan ? plan->impl.param_bytes : 0; }
 const char* dv_plan_manifest_json(const dv_plan* plan) { return plan ? plan->impl.manifest.c_str() : ""; }
@@ -64,6 +83,16 @@ int dv_plan_last_sample_launches(const dv_plan* plan) { return plan ? plan->impl
 
 int dv_plan_bind(dv_plan* plan, void* workspace, const void* params, void* stream) {
   if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  {
+    cudaPointerAttributes at;
+    cudaError_t pe = cudaPointerGetAttributes(&at, workspace);
+    if (pe != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+      cudaGetLastError();
+      return fail(DV_ERR_INVALID, "workspace is not a device allocation");
+    }
+    plan->impl.device = at.device;
+  }
+  DevGuard guard(plan->impl.device);
   int rc = require_device();
   if (rc != DV_OK) return rc;
   std::string err;
@@ -72,12 +101,14 @@ int dv_plan_bind(dv_plan* plan, void* workspace, const void* params, void* strea
 }
 int dv_prompt_prepare(dv_plan* plan, const float* ehs, const float* aug, const int32_t* kv_len, void* stream) {
   if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  DevGuard guard(plan->impl.device);
   std::string err;
   int rc = plan->impl.prompt_prepare(ehs, aug, kv_len, S(stream), err);
   return rc == DV_OK ? rc : fail(rc, err);
 }
 int dv_set_cond(dv_plan* plan, const float* cond, void* stream) {
   if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  DevGuard guard(plan->impl.device);
   std::string err;
   int rc = plan->impl.set_cond(cond, S(stream), err);
   return rc == DV_OK ? rc : fail(rc, err);
@@ -85,6 +116,7 @@ int dv_set_cond(dv_plan* plan, const float* cond, void* stream) {
 int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride, float* out,
                     void* stream) {
   if (!plan || !sample || !t || !out) return fail(DV_ERR_INVALID, "null argument");
+  DevGuard guard(plan->impl.device);
   std::string err;
   int launches = 0;
   int rc = plan->impl.forward(sample, x_only, t, t_stride, out, S(stream), err, &launches);
@@ -93,6 +125,7 @@ int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const float*
 int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags,
               void* stream) {
   if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  DevGuard guard(plan->impl.device);
   std::string err;
   int rc = plan->impl.sample(sampler, nsteps, t_in, coef, x, flags, S(stream), err);
   return rc == DV_OK ? rc : fail(rc, err);
@@ -104,7 +137,9 @@ int dv_sample_group(dv_plan* const* plans, int nplans, int sampler, int nsteps, 
   for (int i = 0; i < nplans; ++i) {
     if (!plans[i]) return fail(DV_ERR_INVALID, "null plan");
     ps[i] = &plans[i]->impl;
+    if (ps[i]->device != ps[0]->device) return fail(DV_ERR_INVALID, "lanes of one group must live on one device");
   }
+  DevGuard guard(ps[0]->device);
   std::string err;
   int rc = dv::sample_group(ps, nplans, sampler, nsteps, t_in, coef, x, flags, S(stream), err);
   return rc == DV_OK ? rc : fail(rc, err);
@@ -139,28 +174,25 @@ int dv_plan_op_info(const dv_plan* plan, int i, char* tag, int tag_cap, int* kin
 int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, const float* t, int t_stride, float* out,
                             float* ms, int cap, void* stream) {
   if (!plan || !sample || !t || !out || !ms) return fail(DV_ERR_INVALID, "null argument");
+  DevGuard guard(plan->impl.device);
   std::string err;
   int rc = plan->impl.profile_forward(sample, x_only, t, t_stride, out, S(stream), ms, cap, err);
   return rc == DV_OK ? rc : fail(rc, err);
 }
 
 // ------------------------------------------------------------------------------------------ single kernels
-static thread_local float* g_test_stats = nullptr;
-static thread_local int g_test_bn = 0;
+#ifdef DV_DEBUG_HOOKS
+// Debug library only (include/diffvits_b200_debug.h): timing ablations and CTA timelines.
 static thread_local unsigned long long* g_test_trace = nullptr;
 static thread_local int g_test_flags = 0;
 void dv_gemm_test_trace(unsigned long long* buf) { g_test_trace = buf; }
 void dv_gemm_test_flags(int flags) { g_test_flags = flags; }
-static thread_local long long g_test_out_bs = 0;
-static thread_local int g_test_trim = 0;
-void dv_gemm_test_layout(long long out_bs, int trim_col) { g_test_out_bs = out_bs; g_test_trim = trim_col; }
 int dv_debug_skip_kinds(int mask) { int& m = dv::skip_kinds_mask(); const int old = m; m = mask; return old; }
-/* Test hooks for dv_gemm: force the N tile (0 = heuristic) and ask the epilogue for GroupNorm partials. */
-void dv_gemm_test_options(int bn, float* stats) { g_test_bn = bn; g_test_stats = stats; }
+#endif
 
 int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
             int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
-            int L_out, int impl, void* stream) {
+            int L_out, int impl, const dv_gemm_opts* opts, void* stream) {
   if (!srcs || !segs || !w || !out) return fail(DV_ERR_INVALID, "null argument");
   if (nsrc < 1 || nsrc > dv::GEMM_MAX_SRC || nseg < 1 || nseg > dv::GEMM_MAX_SEG) return fail(DV_ERR_INVALID, "bad nsrc/nseg");
   if (n_pad % 128 || k_tot % 64) return fail(DV_ERR_INVALID, "n_pad must be a multiple of 128 and k_tot of 64");
@@ -193,8 +225,11 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   p.tiles_per_batch = (L_out + 127) / 128;
   p.out_mode = out_mode;
   p.bias = bias; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out;
-  p.out_bs = g_test_out_bs; p.trim_col = g_test_trim;
-  p.stats = g_test_stats; p.stats_nblk = n / 16; p.bn = g_test_bn; p.trace = g_test_trace; p.dbg_flags = g_test_flags;
+  if (opts) { p.out_bs = opts->out_bs; p.trim_col = opts->trim_col; p.stats = opts->stats; p.bn = opts->bn; }
+  p.stats_nblk = n / 16;
+#ifdef DV_DEBUG_HOOKS
+  p.trace = g_test_trace; p.dbg_flags = g_test_flags;
+#endif
   if (impl == 1) return ck(dv::launch_gemm_ref(p, rs, w, k_tot, S(stream)), "gemm_ref");
   return ck(dv::launch_gemm_tc(p, S(stream)), "gemm_tc");
 }
@@ -210,7 +245,9 @@ int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q,
   p.ld_q = ld_q; p.ld_k = ld_k; p.ld_v = ld_v; p.ld_o = ld_o;
   p.bs_q = bs_q; p.bs_k = bs_k; p.bs_v = bs_v; p.bs_o = bs_o;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.D = D; p.scale = scale; p.kv_len = kv_len;
+#ifdef DV_DEBUG_HOOKS
   p.trace = g_test_trace;   // the dv_gemm_test_trace buffer doubles as the attention kernel's debug timeline
+#endif
   const char* ae = nullptr;
   if (!dv::attention_tc_prepare(p, &ae)) return fail(DV_ERR_CUDA, ae ? ae : "attention_tc_prepare");
   return ck(dv::launch_attention(p, S(stream)), "attention");

@@ -134,11 +134,13 @@ __device__ __forceinline__ void fold_pv(float (&o)[N], float c, uint32_t taddr) 
 // region of the buffer with plain stores (no atomics: the probe must not add a round trip to what it measures)
 constexpr int TRACE_CAP = 1300;
 __device__ __forceinline__ void trace_ev(const AttnParams& p, int role, int& cnt, int tile, int ev) {
+#ifdef DV_DEBUG_HOOKS
   if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && cnt < TRACE_CAP) {
     p.trace[1 + role * TRACE_CAP + cnt] = (static_cast<unsigned long long>(role + 1) << 60) | (static_cast<unsigned long long>(tile & 0xFFFF) << 44) |
                                           (static_cast<unsigned long long>(ev & 0xF) << 40) | (clock64() & 0xFFFFFFFFFFULL);
     ++cnt;
   }
+#endif
 }
 
 template <int D>

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
               const float2 ub = add_f32x2(make_float2(__uint_as_float(u[jb + 2]), __uint_as_float(u[jb + 3])), make_float2(bu.z, bu.w));
               const float2 ga = add_f32x2(make_float2(__uint_as_float(g[jb]), __uint_as_float(g[jb + 1])), make_float2(bg.x, bg.y));
               const float2 gb = add_f32x2(make_float2(__uint_as_float(g[jb + 2]), __uint_as_float(g[jb + 3])), make_float2(bg.z, bg.w));
-              if (p.dbg_flags & 1) {
+              if (DV_DBG(p, 1)) {
                 packed[2 * j4] = pack_bf16(ua.x * ga.x, ua.y * ga.y);
                 packed[2 * j4 + 1] = pack_bf16(ub.x * gb.x, ub.y * gb.y);
               } else {

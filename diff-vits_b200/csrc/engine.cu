@@ -535,7 +535,12 @@ int Plan::build(std::string& err) {
     if (i < n_levels - 1 || true) {
       if (d != 16 && d != 32 && d != 48 && d != 64) { err = "head dim must be 16/32/48/64"; return DV_ERR_UNSUPPORTED; }
     }
-    if (ch % (8 * c.norm_num_groups) != 0) { err = "channels/groups must be a multiple of 8"; return DV_ERR_UNSUPPORTED; }
+    // GroupNorm statistics are kept per 16-channel block (GEMM epilogue partials, gn_apply's kb0 / nkb): a group must be a
+    // whole number of blocks, for every level and therefore for every concat of two levels
+    if (c.norm_num_groups < 1 || ch % (16 * c.norm_num_groups) != 0) {
+      err = "block_out_channels must be multiples of 16 * norm_num_groups";
+      return DV_ERR_UNSUPPORTED;
+    }
   }
   if (c.cross_attention_dim % 64 != 0) { err = "cross_attention_dim must be a multiple of 64"; return DV_ERR_UNSUPPORTED; }
   if (c.x_channels < 1 || c.x_channels > c.in_channels) { err = "x_channels out of range"; return DV_ERR_INVALID; }
@@ -779,14 +784,18 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.stats = g.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + g.stats_off) : nullptr;
         p.stats_nblk = g.stats_nblk;
         p.bn = 0;
+#ifdef DV_DEBUG_HOOKS
         { const char* de = getenv("DV_GEMM_DBG"); p.dbg_flags = de ? atoi(de) : 0; }   // timing experiments only
+#endif
       } else if (o.kind == OP_CHAIN) {
         ChainParams& p = o.cp;
         memset(&p, 0, sizeof p);
         p.nstages = o.ch.nstages;
         p.B = B; p.L = o.ch.L; p.C = o.ch.C;
         p.tiles_per_batch = (o.ch.L + 127) / 128;
+#ifdef DV_DEBUG_HOOKS
         { const char* de = getenv("DV_CHAIN_DBG"); p.dbg_flags = de ? atoi(de) : 0; }
+#endif
         int na = 0, nw = 0;
         for (int i = 0; i < o.ch.nstages; ++i) {
           const ChainStageDesc& sd = o.ch.st[i];
@@ -861,7 +870,11 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
   } while (0)
 
 int& skip_kinds_mask() {
+#ifdef DV_DEBUG_HOOKS
   static int mask = [] { const char* e = getenv("DV_SKIP_KINDS"); return e ? atoi(e) : 0; }();
+#else
+  static int mask = 0;   // product build: every op is always launched (dv_debug_skip_kinds exists only in the debug library)
+#endif
   return mask;
 }
 

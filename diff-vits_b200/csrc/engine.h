@@ -112,6 +112,7 @@ struct Plan {
   long long p_freqs = -1, p_w1 = -1, p_b1 = -1, p_w2 = -1, p_b2 = -1, p_wall = -1, p_ball = -1;
 
   // bound state
+  int device = -1;           // CUDA device of the workspace (dv_plan_bind); every entry point runs there
   uint8_t* ws = nullptr;
   const uint8_t* params = nullptr;
   bool bound = false, prompt_ready = false, has_aug = false, has_kvlen = false;

@@ -50,11 +50,13 @@ struct SmemLayout {
 
 // debug timeline (enabled only when p.trace != nullptr): CTA 0, one lane per role
 __device__ __forceinline__ void trace_ev(const GemmParams& p, int role, int tile, int ev) {
+#ifdef DV_DEBUG_HOOKS
   if (p.trace && blockIdx.x == 0) {
     const unsigned long long i = atomicAdd(p.trace, 1ULL);
     if (i < 4000) p.trace[1 + i] = (static_cast<unsigned long long>(role) << 60) | (static_cast<unsigned long long>(tile & 0xFFFF) << 44) |
                                    (static_cast<unsigned long long>(ev & 0xF) << 40) | (clock64() & 0xFFFFFFFFFFULL);
   }
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -75,7 +77,7 @@ __device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + e.srow;
-    rv[i] = (lq + r < p.L && !(p.dbg_flags & 16)) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
+    rv[i] = (lq + r < p.L && !DV_DBG(p, 16)) ? *reinterpret_cast<const uint4*>(res + (rowbase + lq + r) * p.ld_res + gcol + e.spiece * 8)
                            : make_uint4(0, 0, 0, 0);
   }
 }
@@ -146,7 +148,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
   for (int i = 0; i < 4; ++i) {
     const int rrow = i * 8 + e.srow;
     const bool keep = !(TRIM && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
-    if (lq + rrow < p.L && keep && !(p.dbg_flags & 8))
+    if (lq + rrow < p.L && keep && !DV_DBG(p, 8))
       *reinterpret_cast<uint4*>(out + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
           lds128(e.coal + i * 8 * EPI_PITCH);
   }
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int pre = 0;                                        // stages whose expect_tx + W loads are already issued
-      if (!(p.dbg_flags & (4 | 64))) {
+      if (!DV_DBG(p, 4 | 64)) {
         const int n0 = (blockIdx.x % n_tiles_n) * BN;
         pre = total_panels < STAGES ? total_panels : STAGES;
         for (int st = 0; st < pre; ++st) {
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
               continue;
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (p.dbg_flags & 4) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+            if (DV_DBG(p, 4)) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
             mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
             tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
             // the W map's box is 64 x 64 rows: a BN-wide tile takes BN / 64 boxes, stacked contiguously
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + SL::A_BYTES);
-          if (!(p.dbg_flags & 2))
+          if (!DV_DBG(p, 2))
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       const size_t obase = TRIM ? static_cast<size_t>(b) * p.out_bs : rowbase * p.ld_out;
       uint4 rv[4];
       bool preloaded = false;
-      if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && part * 32 < BN && n0 + part * 32 < p.N && !(p.dbg_flags & (1 | 32))) {
+      if (p.out_mode == GEMM_OUT_BF16 && p.res != nullptr && part * 32 < BN && n0 + part * 32 < p.N && !DV_DBG(p, 1 | 32)) {
         epi_load_res(p, e, n0 + part * 32, lq, rowbase, rv);
         preloaded = true;
       }
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 1);
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
-      if (p.dbg_flags & 1) {
+      if (DV_DBG(p, 1)) {
         tc_fence_before();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       } else if (p.out_mode == GEMM_OUT_GEGLU) {

@@ -10,6 +10,14 @@
 
 namespace dv {
 
+// Timing-ablation switches and CTA timelines inside the kernels exist only in the debug build (-DDV_DEBUG_HOOKS,
+// libdiffvits_b200_dbg.so); the product library compiles them out.
+#ifdef DV_DEBUG_HOOKS
+#define DV_DBG(p, mask) ((p).dbg_flags & (mask))
+#else
+#define DV_DBG(p, mask) 0
+#endif
+
 // Launch with the programmatic-stream-serialization attribute (PDL): consecutive kernels of the denoiser overlap
 // their prologue / launch latency with the previous kernel's tail. Disabled with DV_NO_PDL=1 in the environment.
 bool pdl_enabled();

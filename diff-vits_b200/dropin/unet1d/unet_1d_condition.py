@@ -8,6 +8,8 @@ Not kept: a PyTorch execution path. `forward` requires a CUDA sm_100a device and
 """
 from __future__ import annotations
 
+import collections
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Tuple, Union
 
@@ -211,7 +213,10 @@ class UNet1DConditionModel(nn.Module):
         self.conv_out = nn.Conv1d(boc[0], out_channels, kernel_size=3, padding=1)
 
         self.config = cfg
-        self._engines: Dict[Tuple, Any] = {}
+        # shape -> plan (own workspace), least recently used first; bounded so that a long-running process that sees a new T
+        # per utterance (ddpm / ddim sampling, validation) does not grow GPU memory without limit
+        self._engines: "collections.OrderedDict[Tuple, Any]" = collections.OrderedDict()
+        self._engine_cache_size = int(os.environ.get("DV_PLAN_CACHE", "4"))
         self._params_cache: Optional[Tuple[Tuple, torch.Tensor]] = None
 
     # ------------------------------------------------------------------------------------------ engine plumbing
@@ -239,6 +244,8 @@ class UNet1DConditionModel(nn.Module):
         ver = (str(device),) + self._weights_version()
         if self._params_cache is not None and self._params_cache[0] != ver:
             self._params_cache = None
+            for e in self._engines.values():
+                e.close()
             self._engines.clear()          # plans hold pointers into the old blob
         key = (B, T, Tp, x_channels, lanes)
         eng = None if private else self._engines.get(key)
@@ -249,10 +256,39 @@ class UNet1DConditionModel(nn.Module):
                 self._params_cache = (ver, eng.params)
             if not private:
                 self._engines[key] = eng
+                while len(self._engines) > max(1, self._engine_cache_size):
+                    _, old = self._engines.popitem(last=False)      # least recently used plan: destroy it, free its workspace
+                    old.close()
+        elif not private:
+            self._engines.move_to_end(key)
         return eng
 
+    def native_denoiser(self, cond: torch.Tensor, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None,
+                        aug: Optional[torch.Tensor] = None):
+        """A `NativeDenoiser` for this batch, re-using (rebinding) the cached one of the same shape: plan, workspace and the
+        captured loop graph survive from one `solver.sample()` call to the next (tts_infer.py calls it once per utterance)."""
+        from diffvits_b200.native import NativeDenoiser
+        B, Cc, T = cond.shape
+        key = ("denoiser", B, T, ehs.shape[1], Cc)
+        ver = (str(self.device),) + self._weights_version()
+        if self._params_cache is not None and self._params_cache[0] != ver:
+            self._params_cache = None
+            for e in self._engines.values():
+                e.close()
+            self._engines.clear()
+        nd = self._engines.get(key)
+        if nd is None:
+            nd = NativeDenoiser(self, cond, ehs, kv_len, aug)
+            self._engines[key] = nd
+            while len(self._engines) > max(1, self._engine_cache_size):
+                _, old = self._engines.popitem(last=False)
+                old.close()
+        else:
+            self._engines.move_to_end(key)
+            nd.rebind(cond, ehs, kv_len, aug)
+        return nd
+
     # ------------------------------------------------------------------------------------------ forward
-    @torch.no_grad()
     def forward(self, sample: torch.FloatTensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor, class_labels: Optional[torch.Tensor] = None,
                 timestep_cond: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
@@ -273,6 +309,13 @@ class UNet1DConditionModel(nn.Module):
                           ("mid_block_additional_residual", mid_block_additional_residual)):
             if val is not None and not (isinstance(val, dict) and not val):
                 raise NotImplementedError(f"`{name}` is not used by the Diff-VITS denoiser and not implemented natively")
+        # Inference only: the native path has no backward. Running it where autograd expects a graph (the reference's
+        # train.py / model3 training forward) would silently cut the denoiser out of the loss, so refuse instead.
+        if torch.is_grad_enabled() and (self.training or sample.requires_grad or encoder_hidden_states.requires_grad):
+            raise RuntimeError(
+                "diffvits_b200 UNet1DConditionModel.forward is inference-only (no autograd through the native kernels): "
+                "put the module in eval() mode and call it under torch.no_grad() (model3.py:1120 does), or use the reference "
+                "unet1d package for training")
         if sample.dim() != 3 or encoder_hidden_states.dim() != 3:
             raise ValueError("expected sample [B, C, T] and encoder_hidden_states [B, Tp, D]")
         B, _, T = sample.shape
@@ -282,7 +325,8 @@ class UNet1DConditionModel(nn.Module):
         kv_len = None
         if encoder_attention_mask is not None:
             kv_len = mask_to_lengths(encoder_attention_mask, Tp)
-        eng.prepare_prompt(encoder_hidden_states.to(dev), kv_len)
+        with torch.no_grad():
+            eng.prepare_prompt(encoder_hidden_states.to(dev), kv_len)
         if not torch.is_tensor(timestep):
             t = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
         else:

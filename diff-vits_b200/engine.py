@@ -202,13 +202,20 @@ class DenoiserEngine:
             check(self.lib.dv_plan_bind(self._plan, _ptr(self.workspace), _ptr(self.params), _stream(self.device)))
         self._keep: list = []
 
+    def close(self) -> None:
+        """Destroy the plan (its graph, streams, events) and drop the workspace. Idempotent."""
+        if getattr(self, "_plan", None) is not None and self._plan.value:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            self.lib.dv_plan_destroy(self._plan)
+            self._plan = C.c_void_p()
+        self.workspace = None
+        self._keep = []
+        self._keep_cond = None
+
     def __del__(self):
         try:
-            if getattr(self, "_plan", None) is not None and self._plan.value:
-                if self.device.type == "cuda":
-                    torch.cuda.synchronize(self.device)
-                self.lib.dv_plan_destroy(self._plan)
-                self._plan = C.c_void_p()
+            self.close()
         except Exception:
             pass
 
@@ -218,13 +225,15 @@ class DenoiserEngine:
         """ehs: encoder_hidden_states [B, Tp, D]; kv_len: [B] valid prompt rows (None = no mask); aug: optional
         precomputed text-time embedding [B, 512] (default: computed here with the module's TextTimeEmbedding)."""
         assert ehs.shape == (self.B, self.Tp, self.cfg.cross_attention_dim), ehs.shape
+        # The C library runs every plan call on the plan's device (api.cu DevGuard); the torch ops here (casts, the hoisted
+        # TextTimeEmbedding) follow their tensors' device, and streams are looked up for self.device explicitly.
         ehs = ehs.to(self.device, torch.float32).contiguous()
         add = getattr(self.unet, "add_embedding", None)
         if aug is not None:
             aug = aug.to(self.device, torch.float32).contiguous()
             assert aug.shape == (self.B, 4 * self.cfg.block_out_channels[0])
         elif add is not None:
-            with torch.no_grad():
+            with torch.no_grad(), torch.cuda.device(self.device):
                 aug = add(ehs).to(torch.float32).contiguous()      # hoisted: prompt-only (unet_1d_condition.py:869)
         if kv_len is not None:
             kv_len = kv_len.to(self.device, torch.int32).contiguous()
@@ -353,6 +362,10 @@ class DenoiserGroup:
     @property
     def lanes(self) -> int:
         return len(self.engines)
+
+    def close(self) -> None:
+        for e in self.engines:
+            e.close()
 
     def _slices(self, t: Optional[torch.Tensor]):
         if t is None:

@@ -45,6 +45,9 @@ class NativeDenoiser:
         self.calls += 1
         return self.engine.forward(x, t_input, x_only=True)
 
+    def close(self) -> None:
+        self.engine.close()
+
 
 def find_native(model, model_kwargs) -> Optional[NativeDenoiser]:
     """Locate a native denoiser behind the `model` callable given to model_wrapper.
@@ -81,7 +84,9 @@ def find_native(model, model_kwargs) -> Optional[NativeDenoiser]:
         enc = diff.prompt_encoder(prompt, prompt_lengths) * mask.unsqueeze(1).to(prompt.dtype)
         ehs = enc.transpose(1, 2).contiguous()
         kv_len = prompt_lengths.clamp(max=Tp).to(torch.int32)
-    native = NativeDenoiser(unet, cond, ehs, kv_len)
+    # cached per shape on the module and rebound: plan, workspace and the captured loop graph are re-used by the next
+    # solver.sample() of the same (B, T, Tp) instead of being rebuilt per call (bounded LRU, DV_PLAN_CACHE plans)
+    native = unet.native_denoiser(cond, ehs, kv_len)
     native.progress_owner = owner
     return native
 

@@ -137,29 +137,17 @@ DV_API int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_onl
  * `bs` elements between batch items (0 = L * ld) */
 typedef struct dv_gemm_src { const void* ptr; int L; int C; int ld; long long bs; } dv_gemm_src;
 typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; } dv_gemm_seg;
+/* Optional per-call settings of dv_gemm (NULL = defaults): bn = force the N tile (64 / 128 / 192 / 256, 0 = heuristic);
+ * stats != NULL = the epilogue also emits GroupNorm partial sums [B][ceil(L/128)*4][n/16][2] of the stored tensor (what
+ * the engine's GroupNorm consumes instead of re-reading it); out_bs = elements between batch items of `out` (0 = dense
+ * L_out * ld_out); trim_col > 0 = columns >= trim_col of the last row are neither stored nor counted in the partials.
+ * out_bs + trim_col are how the folded nearest-resize conv writes 2L - 1 rows (resnet.py:138-173). */
+typedef struct dv_gemm_opts { int bn; float* stats; long long out_bs; int trim_col; } dv_gemm_opts;
 /* out_mode: 0 bf16 NTC, 1 fp32 NCT, 2 GEGLU bf16. impl: 0 = tcgen05 kernel, 1 = CUDA-core reference (writes raw
  * fp32 [B, L, n_pad] accumulators + bias into `out`). Replaces F.conv1d (unet1d/lora.py:102) / nn.Linear. */
 DV_API int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,
             int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
-            int L_out, int impl, void* stream);
-/* Test hooks for the next dv_gemm calls of this thread: force the N tile (128 / 256, 0 = heuristic) and let the
- * epilogue emit GroupNorm partials [B][ceil(L/128)*4][n/16][2] into `stats` (NULL = off). */
-DV_API void dv_gemm_test_options(int bn, float* stats);
-/* Debug: device buffer of >= 4001 uint64; CTA 0 of the next dv_gemm launches appends (role<<60 | tile<<44 | event<<40 |
- * clock) records, buf[0] = count. roles: 0 TMA producer, 1 MMA issuer, 2 first epilogue warp. NULL = off. */
-DV_API void dv_gemm_test_trace(unsigned long long* buf);
-/* Debug: bit 0 skip the epilogue body, bit 1 skip the MMA issue, bit 2 skip the TMA loads (results are garbage;
- * used to time the three pipelines of the kernel separately). */
-DV_API void dv_gemm_test_flags(int flags);
-/* Test hook for the next dv_gemm calls of this thread (bf16 output mode): `out_bs` = elements between batch items of
- * `out` (0 = dense L_out * ld_out); `trim_col` > 0 = columns >= trim_col of the last row are neither stored nor counted in
- * the GroupNorm partials. This is how the folded nearest-resize conv writes 2L - 1 rows (resnet.py:138-173). */
-DV_API void dv_gemm_test_layout(long long out_bs, int trim_col);
-/* Measurement hook (bench.py): bit k set = the denoiser ops of kernel class k (0 gemm, 2 groupnorm apply, 3 layernorm,
- * 4 attention, 5 chained gemm; dv_plan_op_info's `kind`) are NOT launched by later dv_unet_forward / dv_sample calls, so
- * the difference in step time is that class's cost inside the captured loop. Results are garbage while any bit is set.
- * Initial value: environment variable DV_SKIP_KINDS (default 0). Returns the previous mask. */
-DV_API int dv_debug_skip_kinds(int mask);
+            int L_out, int impl, const dv_gemm_opts* opts, void* stream);
 /* F.scaled_dot_product_attention (attention_processor.py:1032); bf16 q/k/v/o with element strides. */
 DV_API int dv_attention(const void* q, const void* k, const void* v, void* o, int ld_q, int ld_k, int ld_v, int ld_o,
                  long long bs_q, long long bs_k, long long bs_v, long long bs_o, int B, int H, int Lq, int Lk, int D,

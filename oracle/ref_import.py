@@ -48,7 +48,11 @@ def load_unet_module():
         return importlib.import_module("_ref_unet1d.unet_1d_condition")
 
 
-from diffvits_b200.synthetic import UNET_KW  # noqa: E402,F401  (model3.py:887-896 with config.json:40-46)
+# Diffusion_Encoder's UNet constructor arguments (model3.py:887-896 with config.json:40-46). The oracle owns its copy of
+# the constants; tests/test_host.py checks that the product's workload definition (diffvits_b200.synthetic) agrees.
+UNET_KW = dict(in_channels=228, out_channels=100, block_out_channels=(128, 256, 384, 512), norm_num_groups=8,
+               cross_attention_dim=128, attention_head_dim=8, addition_embed_type="text",
+               resnet_time_scale_shift="scale_shift")
 
 
 def build_ref_unet(seed: int = 1234):

@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from diffvits_b200 import _lib
-from diffvits_b200._lib import GemmSeg, GemmSrc, check
+from diffvits_b200._lib import GemmOpts, GemmSeg, GemmSrc, check
 
 
 def vp(t: Optional[torch.Tensor]):
@@ -36,7 +36,7 @@ def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]]
          stats: bool = False, layout: Optional[Tuple[int, int]] = None):
     """srcs: bf16 [B, L, C] tensors; segs: (src, row_off, c0, channels); w: bf16 [n_pad, k_tot].
     views: optional (L_view, C_view) per source (the stride-2 conv reads [L/2, 2C]).
-    layout: optional (out_bs, trim_col) of dv_gemm_test_layout; the result is then the flat [B, out_bs] buffer."""
+    layout: optional (out_bs, trim_col) of dv_gemm_opts; the result is then the flat [B, out_bs] buffer."""
     lib = _lib.load()
     B = srcs[0].shape[0]
     n_pad, k_tot = w.shape
@@ -66,15 +66,11 @@ def gemm(srcs: Sequence[torch.Tensor], segs: Sequence[Tuple[int, int, int, int]]
     st = None
     if stats:
         st = torch.full((B, (L_out + 127) // 128 * 4, n // 16, 2), float("nan"), dtype=torch.float32, device=dev)
-    lib.dv_gemm_test_options(bn, vp(st))
-    if layout is not None:
-        lib.dv_gemm_test_layout(int(layout[0]), int(layout[1]))
-    try:
-        check(lib.dv_gemm(S, len(srcs), G, len(segs), vp(w), k_tot, n, n_pad, vp(bias), vp(res),
-                          0 if res is None else res.shape[-1], vp(out), ld_out, out_mode, B, L_out, impl, stream()))
-    finally:
-        lib.dv_gemm_test_options(0, None)
-        lib.dv_gemm_test_layout(0, 0)
+    opts = GemmOpts(bn, None if st is None else st.data_ptr(), 0 if layout is None else int(layout[0]),
+                    0 if layout is None else int(layout[1]))
+    check(lib.dv_gemm(S, len(srcs), G, len(segs), vp(w), k_tot, n, n_pad, vp(bias), vp(res),
+                      0 if res is None else res.shape[-1], vp(out), ld_out, out_mode, B, L_out, impl, C.byref(opts),
+                      stream()))
     return (out, st) if stats else out
 
 

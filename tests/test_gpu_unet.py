@@ -299,7 +299,7 @@ def test_batch_consistency_at_bench_size(env):
     for b in (0, 17, 31):
         one = diffvits_b200.NativeDenoiser(unet, cond[b:b + 1].cuda(), ehs[b:b + 1].cuda(), aug=aug[b:b + 1])
         o1 = one(x_T[b:b + 1].cuda(), t)
-        assert U.rel_l2(out[b:b + 1], o1) < 1e-6, b    # fp64 atomics in GN stats may reorder: not bit exact
+        assert U.rel_l2(out[b:b + 1], o1) < 1e-6, b    # the hoisted cuBLAS op aside, reductions are fixed-order (no atomics)
     emu = env["uo"].unet_forward(env["sd"], torch.cat([x_T[:2], cond[:2]], 1).cuda(), t, ehs[:2].cuda(),
                                  emulate_bf16=True)
     print(f"B=32,T=1000 rows 0-1 vs emulating oracle: rel {U.rel_l2(out[:2], emu):.3e}")

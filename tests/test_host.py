@@ -36,6 +36,19 @@ def test_abi_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name)
     assert lib.dv_version() == 100
+    # measurement hooks live in their own header and only in the debug build: the product library must not export them
+    dbg = open(os.path.join(ROOT, "include", "diffvits_b200_debug.h")).read()
+    dbg_declared = set(re.findall(r"DV_API[^;]*?\b(dv_[a-z0-9_]+)\s*\(", dbg))
+    assert dbg_declared == set(_lib.DEBUG_SIGNATURES)
+    if not _lib.DEBUG_LIB:
+        for name in dbg_declared:
+            assert not hasattr(lib, name), name
+
+
+def test_oracle_and_product_agree_on_the_workload_definition():
+    from diffvits_b200 import synthetic
+    from oracle import ref_import
+    assert ref_import.UNET_KW == synthetic.UNET_KW
 
 
 def test_compute_entry_points_fail_loudly_without_gpu(lib):
@@ -72,6 +85,9 @@ def test_plan_manifest_and_errors(lib, seeded_unet):
     assert lib.dv_plan_create(C.byref(cfg), 1, 15, 50, C.byref(q)) == -1 and b"too short" in lib.dv_last_error()
     bad = _cfg(boc=(128, 200, 384, 512))
     assert lib.dv_plan_create(C.byref(bad), 1, 200, 50, C.byref(q)) == -4
+    bad = _cfg(boc=(128, 256, 384, 512))
+    bad.norm_num_groups = 16                       # 128 / 16 = 8 channels per group: statistics blocks are 16 wide
+    assert lib.dv_plan_create(C.byref(bad), 1, 200, 50, C.byref(q)) == -4 and b"16 * norm_num_groups" in lib.dv_last_error()
     bad = _cfg(heads=32)
     assert lib.dv_plan_create(C.byref(bad), 1, 200, 50, C.byref(q)) < 0
     assert lib.dv_plan_create(C.byref(cfg), 0, 200, 50, C.byref(q)) == -1
@@ -245,6 +261,15 @@ def test_unet_shell_api(dropin, seeded_unet):
     # no CPU execution path: forward refuses instead of falling back to PyTorch
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         seeded_unet(torch.zeros(1, 228, 8), 1.0, torch.zeros(1, 4, 128))
+    # inference only: a training-mode call with autograd on must not silently return a detached result
+    seeded_unet.train()
+    try:
+        with pytest.raises(RuntimeError, match="inference-only"):
+            seeded_unet(torch.zeros(1, 228, 8), 1.0, torch.zeros(1, 4, 128))
+    finally:
+        seeded_unet.eval()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        seeded_unet(torch.zeros(1, 228, 8, requires_grad=True), 1.0, torch.zeros(1, 4, 128))
     # state_dict round trip (what tts_infer.py:78 does)
     m2 = U.UNet1DConditionModel(**{k: seeded_unet.config[k] for k in
                                    ("in_channels", "out_channels", "block_out_channels", "norm_num_groups",

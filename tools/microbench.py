@@ -16,7 +16,7 @@ import torch  # noqa: E402
 
 import gpu_util as U  # noqa: E402
 from diffvits_b200 import _lib  # noqa: E402
-from diffvits_b200._lib import GemmSeg, GemmSrc, check  # noqa: E402
+from diffvits_b200._lib import GemmOpts, GemmSeg, GemmSrc, check  # noqa: E402
 
 ITERS = 20
 
@@ -61,7 +61,8 @@ def main():
     B = a.B
     levels = [(a.T, 128), (a.T // 2, 256), (a.T // 4, 384), (a.T // 8, 512)]
     if "gemm" in only:
-        lib.dv_gemm_test_flags(a.flags)
+        if a.flags:
+            lib.dv_gemm_test_flags(a.flags)      # debug library only (DV_DEBUG_LIB=1)
         print(f"# GEMM (dbg flags {a.flags}): tag, us, TFLOP/s, algorithmic MB")
         for li, (L, Cc) in enumerate(levels):
             cases = [
@@ -90,16 +91,17 @@ def main():
                         continue
 
                     def fn(st):
-                        lib.dv_gemm_test_options(bn, U.vp(stt))
+                        opts = GemmOpts(bn, None if stt is None else stt.data_ptr(), 0, 0)
                         check(lib.dv_gemm(S, 1, G, len(segs), U.vp(w), ktot, N, N, U.vp(bias), U.vp(res),
-                                          0 if res is None else N, U.vp(out), out.shape[-1], mode, B, L, 0, st))
+                                          0 if res is None else N, U.vp(out), out.shape[-1], mode, B, L, 0,
+                                          C.byref(opts), st))
                     us = timeit(fn)
                     fl = 2.0 * B * L * N * ktot
                     mb = (B * L * K1 * 2 + N * ktot * 2 + out.numel() * 2 + (B * L * N * 2 if withres else 0)) / 1e6
                     print(f"L{li} {tag:24s} bn={bn} M={B * L:6d} N={N:5d} K={ktot:5d}  {us:8.2f} us  "
                           f"{fl / us / 1e6:7.1f} TF/s  {mb:7.2f} MB")
-        lib.dv_gemm_test_options(0, None)
-        lib.dv_gemm_test_flags(0)
+        if a.flags:
+            lib.dv_gemm_test_flags(0)
     if "attn" in only:
         print("# attention: tag, us, TFLOP/s, Gexp/s")
         for li, (L, Cc) in enumerate(levels):
