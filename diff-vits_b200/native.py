@@ -99,8 +99,15 @@ def _cell_ok(cell) -> bool:
         return False
 
 
+# how many whole sampling loops the drop-in solvers have run natively in this process (tests read it to prove that the
+# reference's own call sequence reached the native path rather than the generic per-step loop)
+NATIVE_LOOPS = 0
+
+
 def tick_progress(native: NativeDenoiser, n: int) -> None:
     """Advance the reference's tqdm bar (model3.py:1133, 1167) by the number of model evaluations done natively."""
+    global NATIVE_LOOPS
+    NATIVE_LOOPS += 1
     owner = getattr(native, "progress_owner", None)
     bar = getattr(owner, "bar", None) if owner is not None else None
     if bar is not None and hasattr(bar, "update"):

@@ -30,3 +30,9 @@ def ragged_mask(B: int, Tp: int, step: int = 100):
     lens = torch.tensor([max(1, Tp - i * step) for i in range(B)], dtype=torch.int32)
     mask = torch.arange(Tp)[None, :] < lens[:, None]
     return lens, mask
+
+
+def make_prompt(B: int, Tp: int, seed: int = 0, n_mels: int = 100) -> torch.Tensor:
+    """Speech-prompt mel [B, 100, Tp] ~ N(0,1): the PromptEncoder's input (model3.py:906), for the arms that run it."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    return torch.randn(B, n_mels, Tp, generator=g)

@@ -1,5 +1,5 @@
 """ORACLE helper (test infrastructure): import the *reference* implementation from /root/reference (read-only,
-present only in the build container) under private module names, without disturbing the drop-in `unet1d` /
+present only in the build container) or from its snapshot oracle/_ref/ under private module names, without disturbing the drop-in `unet1d` /
 `sampler` packages. Used by oracle/make_golden.py and by the tests that pin the oracle against the live reference.
 """
 from __future__ import annotations
@@ -11,7 +11,16 @@ import sys
 import types
 import warnings
 
-REF_ROOT = os.environ.get("DIFFVITS_REFERENCE", "/root/reference")
+def _root() -> str:
+    """The reference checkout (build container) or its snapshot oracle/_ref/ (travels to the GPU box)."""
+    from oracle import ref_snapshot
+    for cand in (os.environ.get("DIFFVITS_REFERENCE", "/root/reference"), ref_snapshot.SNAPSHOT):
+        if os.path.isfile(os.path.join(cand, "unet1d", "unet_1d_condition.py")):
+            return cand
+    return os.environ.get("DIFFVITS_REFERENCE", "/root/reference")
+
+
+REF_ROOT = _root()
 
 
 def available() -> bool:

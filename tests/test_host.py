@@ -330,10 +330,12 @@ def test_reference_model3_builds_on_the_dropin():
 
 def test_reference_arm_of_bench_runs_on_cpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
-                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                          "--steps", "1", "--warmup", "0", "--cpu-target", "2"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert len(out.stdout.strip().splitlines()) == 1          # stdout carries exactly the JSON line
+    line = json.loads(out.stdout.strip())
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
+    assert "PromptEncoder" in line["cpu_baseline"]["sample"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0
 
 
