@@ -37,8 +37,15 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 // out[b, l, n] = epi( sum over K panels  A_seg[b, l + row_off, c0 + 64*p : +64] . W[n, k_run : +64] )
 // A sources are channel-last bf16 tensors [B, L, C] behind 3-D TMA maps (zero fill outside [0, L) gives the
 // conv padding); W is bf16 [N_pad, K_tot] K-major behind a 2-D TMA map.
-constexpr int GEMM_MAX_SRC = 3;
-constexpr int GEMM_MAX_SEG = 6;
+// Precision modes. BF16 (default): activations and weights are single bf16 tensors. SPLIT ("fp32x3"): every bf16 tensor has
+// a second "lo" plane holding bf16(x - float(hi)) (hi + lo carries 16 mantissa bits) and every contraction is
+// a_hi.w_hi + a_hi.w_lo + a_lo.w_hi in the fp32 accumulator - for the tap-GEMM simply three K segments per logical
+// segment, over two A maps (hi / lo plane) and two W maps. Epilogues write both planes; norms, layout kernels and the
+// attention core read hi + lo and write both planes.
+constexpr int GEMM_MAX_LSRC = 3;                   // logical sources (torch.cat inputs / pair views)
+constexpr int GEMM_MAX_LSEG = 6;                   // logical K segments (conv taps, shortcut sources)
+constexpr int GEMM_MAX_SRC = 2 * GEMM_MAX_LSRC;    // maps in the kernel parameters (hi and lo plane of each source)
+constexpr int GEMM_MAX_SEG = 3 * GEMM_MAX_LSEG;
 
 enum GemmOut : int {
   GEMM_OUT_BF16 = 0,     // out bf16 [B, L, ld_out], columns [0, N)
@@ -51,11 +58,14 @@ struct GemmSeg {
   int16_t row_off;  // row offset added to the tile's first row (-1, 0, +1 for the three conv taps)
   int16_t c0;       // first channel of the segment in the source tensor
   int16_t npanels;  // number of 64-channel panels
+  int16_t wsel;     // weight matrix: 0 = mapW (hi plane), 1 = mapW2 (lo plane)
+  int16_t wk0;      // first 64-wide K panel of the segment inside that weight matrix
 };
 
 struct alignas(64) GemmParams {
   CUtensorMap mapA[GEMM_MAX_SRC];
   CUtensorMap mapW;
+  CUtensorMap mapW2;    // split precision: lo plane of the weights (aliases mapW otherwise)
   GemmSeg seg[GEMM_MAX_SEG];
   int nseg;
   int B, L, N;          // L = output rows per batch item, N = real output columns
@@ -64,8 +74,10 @@ struct alignas(64) GemmParams {
   int out_mode;
   const float* bias;    // [n_pad] or nullptr
   const void* res;      // bf16 [B, L, ld_res] residual added before the store, or nullptr
+  const void* res_lo;   // split precision: lo plane of the residual
   int ld_res;
   void* out;
+  void* out_lo;         // split precision: lo plane of the output (non-null selects the split epilogue)
   int ld_out;
   long long out_bs;     // GEMM_OUT_BF16: elements between batch items of `out` (0 = L * ld_out, dense)
   int trim_col;         // GEMM_OUT_BF16: if > 0, columns >= trim_col of the LAST row (l = L - 1) are neither stored nor counted in
@@ -142,6 +154,8 @@ struct alignas(64) AttnParams {
   float scale;                                             // D^-0.5
   unsigned long long* trace;   // debug: CTA (0,0,0) appends (role, tile, event, clock) records; [0] = record count
   const int* kv_len;   // per-batch number of un-masked keys (keys >= kv_len[b] get the -10000 bias), or nullptr
+  // split precision: lo planes (same strides); q_lo != nullptr selects the FP32 CUDA-core kernel (csrc/attention_split.cu)
+  const void* q_lo; const void* k_lo; const void* v_lo; void* o_lo;
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);          // tcgen05 kernel (csrc/attention_tc.cu)
 cudaError_t attention_tc_init();                                            // kernel attributes (call outside graph capture)
@@ -150,6 +164,7 @@ cudaError_t attention_tc_init();                                            // k
 bool attention_tc_prepare(AttnParams& p, const char** err);
 cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st);
 cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st);   // mma.sync kernel (csrc/attention.cu)
+cudaError_t launch_attention_split(const AttnParams& p, cudaStream_t st);    // hi + lo operands, fp32 math (csrc/attention_split.cu)
 
 // ------------------------------------------------------------------ norms
 // Partial statistics layout (written by the GEMM epilogue or by gn_stats): float [B][chunks][nblk][2] holding the
@@ -172,20 +187,23 @@ struct GnParams {
   const float* scale_shift; int ss_ld;     // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + C + c]
   float eps; int silu;
   void* out;                   // bf16 [B, L, c0 + c1]
+  const void* x0_lo; const void* x1_lo; void* out_lo;   // split precision: lo planes (out_lo != nullptr selects it)
 };
 size_t gn_scratch_floats(int B, int L, int C);
 // standalone statistics pass over (x0 | x1) into `scratch` (same partial layout, one source covering all channels)
 cudaError_t launch_gn_stats(const GnParams& p, float* scratch, cudaStream_t st);
 cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st);
+// x_lo / out_lo: lo planes in split precision (both null otherwise)
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
-                             float eps, cudaStream_t st);
+                             float eps, cudaStream_t st, const void* x_lo = nullptr, void* out_lo = nullptr);
 
 // ------------------------------------------------------------------ elementwise / small
 // [B, Csrc, T] fp32 -> channel-last bf16 [B, T, ld_dst]; channel c goes to column c + (c >= split ? shift : 0).
+// dst_lo != nullptr (split precision): the lo plane bf16(x - float(hi)) goes there.
 cudaError_t launch_nct_to_ntc(const float* src, void* dst, int B, int Csrc, int T, int ld_dst, int col0, int split,
-                              int shift, cudaStream_t st);
+                              int shift, cudaStream_t st, void* dst_lo = nullptr);
 // [B, T, C] fp32 -> bf16 (same layout)
-cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st, void* dst_lo = nullptr);
 
 struct TembParams {
   const float* t; int t_stride;          // model time per batch item (t_stride 0 = broadcast)

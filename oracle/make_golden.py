@@ -55,11 +55,13 @@ def main():
     # 4. full sampling loops at C1 with the reference samplers wired like model3.py:1143-1158 / 1177-1192
     rdpm, runi = ref_import.load_samplers()
     betas = inputs.betas_linear()
-    step_outs = []
+    step_outs, step_x, step_t = [], [], []
 
     def model(x, t, **kw):
         out = unet(torch.cat([x, cond], dim=1), t, ehs).sample
         step_outs.append(out)
+        step_x.append(x.clone())          # the denoiser INPUT of every call: teacher-forced per-step parity needs x_k
+        step_t.append(t.clone())
         return out
 
     ns = rdpm.NoiseScheduleVP("discrete", betas=betas)
@@ -67,16 +69,22 @@ def main():
     lat_dpm = rdpm.DPM_Solver(fn, ns, algorithm_type="dpmsolver++").sample(
         x_T.clone(), steps=50, order=2, skip_type="time_uniform", method="multistep")
     dpm_steps = torch.stack([step_outs[i] for i in (0, 1, 25, 49)]).numpy()
+    dpm_x = torch.stack([step_x[i] for i in (0, 1, 25, 49)]).numpy()
+    dpm_t = torch.stack([step_t[i].reshape(-1)[0] for i in (0, 1, 25, 49)]).numpy()
     assert len(step_outs) == 50
-    step_outs.clear()
+    step_outs.clear(); step_x.clear(); step_t.clear()
     ns2 = runi.NoiseScheduleVP("discrete", betas=betas)
     fn2 = runi.model_wrapper(model, ns2, model_type="x_start", model_kwargs={})
     lat_uni = runi.UniPC(fn2, ns2, variant="bh2").sample(
         x_T.clone(), steps=10, order=2, skip_type="time_uniform", method="multistep")
     assert len(step_outs) == 10
     uni_steps = torch.stack([step_outs[i] for i in (0, 1, 9)]).numpy()
+    uni_x = torch.stack([step_x[i] for i in (0, 1, 9)]).numpy()
+    uni_t = torch.stack([step_t[i].reshape(-1)[0] for i in (0, 1, 9)]).numpy()
     np.savez_compressed(os.path.join(GOLD, "sampler_c1.npz"), dpm50=lat_dpm.numpy(), dpm_steps=dpm_steps,
                         unipc10=lat_uni.numpy(), uni_steps=uni_steps)
+    # denoiser inputs (x_k, model time) at the same trajectory points, fp16-free fp32: ~0.6 MB
+    np.savez_compressed(os.path.join(GOLD, "sampler_c1_inputs.npz"), dpm_x=dpm_x, dpm_t=dpm_t, uni_x=uni_x, uni_t=uni_t)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

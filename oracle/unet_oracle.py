@@ -189,11 +189,16 @@ def upsample(c: _Ctx, x: Tensor, size: int, key: str) -> Tensor:
 @torch.no_grad()
 def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, ehs: Tensor,
                  mask: Optional[Tensor] = None, cfg: Optional[dict] = None, emulate_bf16: bool = False,
-                 trace: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                 trace: Optional[Dict[str, Tensor]] = None, teacher: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """UNet1DConditionModel.forward (unet_1d_condition.py:743-1037).
 
     sample [B, Cin, T] fp32; timestep [B] (or [1]) float; ehs [B, Tp, Dc]; mask: bool [B, Tp] keep-mask or None.
-    Returns [B, out_channels, T] fp32."""
+    Returns [B, out_channels, T] fp32.
+
+    trace: filled with every block output (reference module path -> [B, C, L]).
+    teacher: block outputs of ANOTHER evaluation (the CUDA engine's, same names, [B, C, L]). Each block's own output still
+    goes to `trace`, but everything downstream of a block consumes the teacher's tensor instead: block k is evaluated on
+    the engine's input of block k, so its error does not accumulate with depth (teacher-forced per-block parity)."""
     cfg = cfg or default_cfg()
     c = _Ctx(sd, cfg, emulate_bf16)
     boc = tuple(cfg["block_out_channels"])
@@ -212,6 +217,8 @@ def unet_forward(sd: Dict[str, Tensor], sample: Tensor, timestep: Tensor, ehs: T
     def tr(name, v):
         if trace is not None:
             trace[name] = v
+        if teacher is not None:
+            return teacher[name].to(v.dtype)
         return v
 
     h = tr("conv_in", c.r(conv(c, c.r(sample), "conv_in")))                            # :943

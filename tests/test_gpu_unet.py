@@ -51,7 +51,7 @@ def test_forward_c1_vs_reference_golden_and_emulated_oracle(env):
               f"emulation vs fp32 rel {U.rel_l2(emu, ref):.3e}")
         assert torch.isfinite(out).all()
         assert U.rel_l2(out, emu) < 1.5e-2
-        assert U.rel_l2(out, ref) < 1.5e-2 and U.max_abs(out, ref) < 4e-2
+        assert U.rel_l2(out, ref) < 1.2e-2 and U.max_abs(out, ref) < 2e-2
 
 
 def test_forward_ragged_prompt_mask(env):
@@ -64,7 +64,7 @@ def test_forward_ragged_prompt_mask(env):
                encoder_attention_mask=mask.cuda()).sample
     ref = torch.from_numpy(g["out"]).cuda()
     print(f"ragged: rel {U.rel_l2(out, ref):.3e} max {U.max_abs(out, ref):.3e}")
-    assert U.rel_l2(out, ref) < 1.5e-2 and U.max_abs(out, ref) < 4e-2
+    assert U.rel_l2(out, ref) < 1.2e-2 and U.max_abs(out, ref) < 2e-2
 
 
 @pytest.mark.parametrize("T,seed", [(203, 3), (198, 4)])
@@ -85,7 +85,7 @@ def test_forward_odd_lengths_vs_reference_golden(env, T, seed):
           f"vs bf16-emulating oracle rel {U.rel_l2(out, emu):.3e}")
     assert out.shape == ref.shape and torch.isfinite(out).all()
     assert U.rel_l2(out, emu) < 1.5e-2
-    assert U.rel_l2(out, ref) < 1.5e-2 and U.max_abs(out, ref) < 4e-2
+    assert U.rel_l2(out, ref) < 1.2e-2 and U.max_abs(out, ref) < 2e-2
     # batch of 3 at the same odd length: every sample equals its single-sample evaluation (batch strides, trimmed rows).
     # The hoisted torch op (add_embedding, cuBLAS) is shared: it picks batch-size dependent kernels.
     import diffvits_b200
@@ -177,6 +177,65 @@ def test_depth_profile_vs_emulating_oracle(env):
     assert rels["down_blocks.0.attentions.0"] < 8e-3     # + GN, 9 GEMMs, 2 attentions, 3 LNs
     assert rels["down_blocks.0.downsamplers.0.conv"] < 1e-2
     assert max(rels.values()) < 2e-2                     # never worse than the BF16 floor anywhere in the network
+
+
+def test_teacher_forced_per_block_parity(env):
+    """Every block of the network on its own: the emulating oracle evaluates block k on the ENGINE's input of block k (the
+    named tensors the engine leaves in its workspace), so a block's error does not compound with depth and the gate can be
+    two orders of magnitude below the end-to-end BF16 floor. This is what proves the kernel logic at depth: conv taps and
+    padding at every level, stride-2 / folded-upsample packing, two-source GroupNorm + shortcut over the never-materialised
+    concat, time scale/shift rows, attention + key padding, GEGLU, residual epilogues - for all 45 block outputs and
+    the final conv_out. What remains is accumulation order and 1-ulp flips of the BF16 intermediates INSIDE one block."""
+    U, unet, uo = env["U"], env["unet"], env["uo"]
+    import diffvits_b200
+    x_T, cond, ehs = env["inputs"].make_inputs(2, 200, 282, seed=21)
+    lens, mask = env["inputs"].ragged_mask(2, 282)
+    ehs = ehs * mask[:, :, None]
+    native = diffvits_b200.NativeDenoiser(unet, cond.cuda(), ehs.cuda(), kv_len=lens.cuda())
+    t = torch.tensor([731.5], device="cuda")
+    out = native(x_T.cuda(), t).clone()
+    torch.cuda.synchronize()
+    got = {k: v.float().transpose(1, 2).contiguous() for k, v in native.engine.named_tensors().items()}
+    assert len(got) == 45
+    trace = {}
+    final = uo.unet_forward(env["sd"], torch.cat([x_T, cond], 1).cuda(), t, ehs.cuda(), mask=mask.cuda(), emulate_bf16=True,
+                            trace=trace, teacher=got)
+    rels = {k: U.rel_l2(got[k], trace[k]) for k in trace}
+    rels["conv_out"] = U.rel_l2(out, final)
+    worst = sorted(rels.items(), key=lambda kv: -kv[1])
+    for k, v in worst[:8]:
+        print(f"  {k:40s} rel {v:.3e}")
+    res = [v for k, v in rels.items() if ".resnets." in k]
+    att = [v for k, v in rels.items() if ".attentions." in k]
+    print(f"teacher-forced per-block: {len(rels)} tensors, resnets max {max(res):.2e}, transformers max {max(att):.2e}, "
+          f"conv_in {rels['conv_in']:.2e}, conv_out {rels['conv_out']:.2e}")
+    # measured (B200, r2a): conv_in 5.6e-5, conv_out 5.1e-4, resnets <= 2.5e-3, transformer blocks <= 2.6e-3 - the BF16
+    # rounding flips of the 4 (resnet) / ~20 (transformer) intermediate tensors inside ONE block, 3-4x below the end-to-end
+    # floor. The FP32-class mode runs the same test at 1e-4 (tests/test_gpu_precision.py).
+    assert rels["conv_in"] < 1e-3 and rels["conv_out"] < 2e-3
+    for k, v in rels.items():
+        assert v < 3.5e-3, (k, v)
+
+
+def test_teacher_forced_per_step_parity(env):
+    """Denoiser outputs at the REFERENCE's own trajectory points (steps 0 / 1 / 25 / 49 of the 50-step DPM-Solver++ loop,
+    0 / 1 / 9 of the 10-step UniPC loop): the engine is fed the reference's x_k (tests/golden/sampler_c1_inputs.npz) and
+    compared with the reference's output of that call, so late steps (small t, structured x) are covered without the
+    trajectory drift of a free-running loop."""
+    U, unet = env["U"], env["unet"]
+    import diffvits_b200
+    g = np.load(os.path.join(GOLD, "sampler_c1.npz"))
+    gi = np.load(os.path.join(GOLD, "sampler_c1_inputs.npz"))
+    x_T, cond, ehs = env["inputs"].make_inputs(1, 200, 282)
+    native = diffvits_b200.NativeDenoiser(unet, cond.cuda(), ehs.cuda())
+    for name, xs, ts, refs in (("dpm", gi["dpm_x"], gi["dpm_t"], g["dpm_steps"]), ("unipc", gi["uni_x"], gi["uni_t"], g["uni_steps"])):
+        for x, t, ref in zip(xs, ts, refs):
+            out = native(torch.from_numpy(x).cuda(), torch.tensor([float(t)], device="cuda"))
+            ref = torch.from_numpy(ref).cuda()
+            rel, mx = U.rel_l2(out, ref), U.max_abs(out, ref)
+            print(f"{name} t_in={float(t):8.3f}: teacher-forced denoiser output vs reference rel {rel:.3e} max {mx:.3e}")
+            assert torch.isfinite(out).all()
+            assert mx < 2e-2 and rel < 1.2e-2      # north_star max-abs gate; rel-L2 = measured BF16 floor (8-9e-3) + margin
 
 
 def test_loop_control_bit_exact(env):

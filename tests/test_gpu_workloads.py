@@ -135,6 +135,12 @@ def test_c5_long_form_call_and_loop(env):
     # the first sight of a loop runs eagerly, the second one is captured: this one is the graph replay
     c = diffvits_b200.sample_native(unet, x_T, cond, ehs, sampler="unipc", steps=25, betas=betas, native=native)
     assert torch.equal(a, c)
+    # the same 25-step loop by the ORACLE's UniPC restatement (pinned to the reference's sampler in tests/test_oracle.py)
+    # driving the native denoiser: checks the loop control and coefficient tables at the C5 step count
+    want = env["so"].unipc_bh2(lambda xx, ti: native(xx, ti.to("cuda")).clone(), betas, x_T.clone(), 25)
+    rel = U.rel_l2(a, want)
+    print(f"C5 25-step UniPC loop (T=4000): native loop vs oracle loop over the native denoiser rel {rel:.3e}")
+    assert rel < 4e-2
 
 
 def test_eager_pytorch_bar_on_same_gpu(env):
