@@ -34,6 +34,7 @@ class UnetCfg(C.Structure):
         ("num_heads", C.c_int),
         ("norm_eps", C.c_float),
         ("x_channels", C.c_int),
+        ("precision", C.c_int),
     ]
 
 

@@ -194,7 +194,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
             int n_pad, const float* bias, const void* res, int ld_res, void* out, int ld_out, int out_mode, int B,
             int L_out, int impl, const dv_gemm_opts* opts, void* stream) {
   if (!srcs || !segs || !w || !out) return fail(DV_ERR_INVALID, "null argument");
-  if (nsrc < 1 || nsrc > dv::GEMM_MAX_SRC || nseg < 1 || nseg > dv::GEMM_MAX_SEG) return fail(DV_ERR_INVALID, "bad nsrc/nseg");
+  if (nsrc < 1 || nsrc > dv::GEMM_MAX_LSRC || nseg < 1 || nseg > dv::GEMM_MAX_LSEG) return fail(DV_ERR_INVALID, "bad nsrc/nseg");
   if (n_pad % 128 || k_tot % 64) return fail(DV_ERR_INVALID, "n_pad must be a multiple of 128 and k_tot of 64");
   int rc = require_device();
   if (rc != DV_OK) return rc;
@@ -210,6 +210,7 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
     rs[i] = dv::GemmRefSrc{s.ptr, s.L, s.C, s.ld};
   }
   if (!dv::make_tmap_2d(&p.mapW, w, k_tot, n_pad, 64, err)) return fail(DV_ERR_CUDA, err);
+  p.mapW2 = p.mapW;
   int ksum = 0;
   for (int i = 0; i < nseg; ++i) {
     if (segs[i].src < 0 || segs[i].src >= nsrc) return fail(DV_ERR_INVALID, "segment source out of range");
@@ -217,6 +218,8 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
     p.seg[i].row_off = static_cast<int16_t>(segs[i].row_off);
     p.seg[i].c0 = static_cast<int16_t>(segs[i].c0);
     p.seg[i].npanels = static_cast<int16_t>(segs[i].npanels);
+    p.seg[i].wsel = 0;
+    p.seg[i].wk0 = static_cast<int16_t>(ksum / 64);
     ksum += segs[i].npanels * 64;
   }
   if (ksum != k_tot) return fail(DV_ERR_INVALID, "segments do not add up to k_tot");

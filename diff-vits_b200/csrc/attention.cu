@@ -490,6 +490,7 @@ cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st) {
 // the whole step is not faster (219.8 vs 217.7 ms), so the mma.sync kernel stays the default for every head dim.
 // DV_ATTN=tc|legacy forces one kernel.
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
+  if (p.q_lo != nullptr) return launch_attention_split(p, st);     // FP32-class precision mode (hi + lo planes)
   // read per launch (launches are captured into a graph on the hot path): tests flip it between calls
   const char* e = getenv("DV_ATTN");
   if (e && e[0] == 't') return launch_attention_tc(p, st);          // tcgen05 kernel

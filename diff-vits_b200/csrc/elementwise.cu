@@ -14,7 +14,8 @@ namespace {
 
 // ------------------------------------------------------------------ layout
 __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                         int Csrc, int T, int ld_dst, int col0, int split, int shift) {
+                                                         int Csrc, int T, int ld_dst, int col0, int split, int shift,
+                                                         __nv_bfloat16* __restrict__ dst_lo) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float tile[32][33];
@@ -30,13 +31,15 @@ __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict
     const int t = t0 + k, c = c0 + tx;
     if (t < T && c < Csrc) {
       const int col = col0 + c + (c >= split ? shift : 0);
-      dst[(static_cast<size_t>(b) * T + t) * ld_dst + col] = __float2bfloat16_rn(tile[tx][k]);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(tile[tx][k]);
+      dst[(static_cast<size_t>(b) * T + t) * ld_dst + col] = hi;
+      if (dst_lo) dst_lo[(static_cast<size_t>(b) * T + t) * ld_dst + col] = __float2bfloat16_rn(tile[tx][k] - __bfloat162float(hi));
     }
   }
 }
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                          size_t n) {
+                                                          size_t n, __nv_bfloat16* __restrict__ dst_lo) {
   pdl_launch_dependents();
   pdl_wait();
   const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -46,8 +49,18 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
     w.x = pack_bf16(v.x, v.y);
     w.y = pack_bf16(v.z, v.w);
     *reinterpret_cast<uint2*>(dst + i4) = w;
+    if (dst_lo) {
+      uint2 wl;
+      wl.x = pack_bf16(v.x - bf16_lo(w.x), v.y - bf16_hi(w.x));
+      wl.y = pack_bf16(v.z - bf16_lo(w.y), v.w - bf16_hi(w.y));
+      *reinterpret_cast<uint2*>(dst_lo + i4) = wl;
+    }
   } else {
-    for (size_t i = i4; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+    for (size_t i = i4; i < n; ++i) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(src[i]);
+      dst[i] = hi;
+      if (dst_lo) dst_lo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(hi));
+    }
   }
 }
 
@@ -241,13 +254,15 @@ bool pdl_enabled() {
 }
 
 cudaError_t launch_nct_to_ntc(const float* src, void* dst, int B, int Csrc, int T, int ld_dst, int col0, int split,
-                              int shift, cudaStream_t st) {
+                              int shift, cudaStream_t st, void* dst_lo) {
   dim3 grid((T + 31) / 32, (Csrc + 31) / 32, B);
-  return launch_k(nct_to_ntc_kernel, grid, dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), Csrc, T, ld_dst, col0, split, shift);
+  return launch_k(nct_to_ntc_kernel, grid, dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), Csrc, T, ld_dst, col0, split, shift,
+                  reinterpret_cast<__nv_bfloat16*>(dst_lo));
 }
-cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
+cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st, void* dst_lo) {
   const size_t blocks = (n / 4 + 256) / 256;
-  return launch_k(f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return launch_k(f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), n,
+                  reinterpret_cast<__nv_bfloat16*>(dst_lo));
 }
 cudaError_t launch_temb(const TembParams& p, cudaStream_t st) {
   if (p.emb_dim != 512 || p.sin_dim > 256 || p.sin_dim % 2) return cudaErrorInvalidValue;

@@ -88,10 +88,12 @@ struct Builder {
     ws_cur = o + bytes;
     return o;
   }
+  // bf16 tensors are followed by their lo plane in split precision (Plan::plane)
+  size_t tensor_bytes(int L, int C) const { return static_cast<size_t>(P.B) * L * C * 2 * (P.split ? 2 : 1); }
   TRef act(int L, int C) {
     TRef t;
     t.L = L; t.C = C;
-    t.off = ws_alloc(static_cast<size_t>(P.B) * L * C * 2);
+    t.off = ws_alloc(tensor_bytes(L, C));
     return t;
   }
   // scratch tensors: lifetime = one block; offsets are relative to the scratch arena until finalize()
@@ -100,7 +102,7 @@ struct Builder {
     TRef t;
     t.L = L; t.C = C;
     size_t o = align_up(scratch_cur, 1024);
-    scratch_cur = o + static_cast<size_t>(P.B) * L * C * 2;
+    scratch_cur = o + tensor_bytes(L, C);
     if (scratch_cur > scratch_max) scratch_max = scratch_cur;
     t.off = SCRATCH_TAG | o;
     return t;
@@ -113,7 +115,8 @@ struct Builder {
     s.name = name; s.recipe = recipe; s.keys = std::move(keys); s.dtype = dtype; s.shape = std::move(shape);
     size_t n = 1;
     for (int d : s.shape) n *= static_cast<size_t>(d);
-    s.bytes = n * (dtype == "bf16" ? 2 : 4);
+    if (dtype == "bf16" && P.split) s.dtype = "bf16x2";     // hi matrix followed by the lo matrix
+    s.bytes = n * (s.dtype == "bf16" ? 2 : 4);
     s.off = align_up(P.param_bytes, 256);
     P.param_bytes = s.off + s.bytes;
     P.slots.push_back(s);
@@ -215,7 +218,7 @@ struct Builder {
     g.n = N; g.n_pad = round_up(N, 128);
     long long wo = slot(tag + ".W", "conv3", wk, "bf16", {g.n_pad, g.k_tot});
     P.slots.back().shape.push_back(cin_real);  // [n_pad, k_tot, cin_real]: packer pads each tap from cin_real to a.C
-    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2;
+    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.split ? 2 : 1);
     g.w_off = wo;
     g.bias_off = slot(tag + ".b", "vec_sum", bk, "f32", {g.n_pad});
     g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
@@ -255,7 +258,7 @@ struct Builder {
   }
 
   TRef transformer(const std::string& pfx, TRef y) {
-    if (P.fuse && y.C % 128 == 0 && y.C <= 384 && y.C <= P.fuse_max_c) return transformer_fused(pfx, y);
+    if (P.fuse && !P.split && y.C % 128 == 0 && y.C <= 384 && y.C <= P.fuse_max_c) return transformer_fused(pfx, y);
     scratch_reset();
     const int L = y.L, C = y.C, H = P.cfg.num_heads, D = C / H;
     const std::string tb = pfx + ".transformer_blocks.0";
@@ -267,7 +270,7 @@ struct Builder {
     TRef ao = tmp(L, C);
     // A projection whose output row fits one CTA's TMEM accumulator (C <= 384) takes the LayerNorm that follows it
     // along as a one-stage chain (csrc/chain_tc.cu, CH_ROW with a global LayerNorm output): one launch instead of two.
-    const bool ln_fused = P.fuse_ln && C % 128 == 0 && C <= 384;
+    const bool ln_fused = P.fuse_ln && !P.split && C % 128 == 0 && C <= 384;
     auto proj_ln = [&](const std::string& tag, TRef a, const std::string& wkey, const std::string& bkey, TRef res,
                        const std::string& lnkey) {
       if (!ln_fused) {
@@ -303,11 +306,12 @@ struct Builder {
     // --- cross attention to the prompt (K/V hoisted into prep_ops)
     TRef kv;
     kv.L = P.Tp; kv.C = 2 * C;
-    kv.off = ws_alloc(static_cast<size_t>(P.B) * P.Tp * 2 * C * 2);
+    kv.off = ws_alloc(tensor_bytes(P.Tp, 2 * C));
     linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
            2 * C, TRef(), kv, GEMM_OUT_BF16);
     TRef q = qkv;  // reuse the first C columns' storage as a dense [L, C] tensor
     q.C = C;
+    if (P.split) q = tmp(L, C);   // (an alias would put its lo plane inside qkv's hi plane: keep the two-plane rule simple)
     linear(P.ops, tb + ".attn2.to_q", nrm, "linear", {tb + ".attn2.to_q.weight"}, "", C, TRef(), q, GEMM_OUT_BF16);
     {
       Op o;
@@ -394,7 +398,7 @@ struct Builder {
     }
     TRef kv;
     kv.L = P.Tp; kv.C = 2 * C;
-    kv.off = ws_alloc(static_cast<size_t>(P.B) * P.Tp * 2 * C * 2);
+    kv.off = ws_alloc(tensor_bytes(P.Tp, 2 * C));
     linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
            2 * C, TRef(), kv, GEMM_OUT_BF16);
     TRef q = qkv;  // the first [L, C] worth of the qkv scratch, dense
@@ -465,7 +469,7 @@ struct Builder {
     g.n = C; g.n_pad = round_up(C, 128);
     g.w_off = slot(key + ".W", "conv3", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
     P.slots.back().shape.push_back(C);
-    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2;
+    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.split ? 2 : 1);
     g.bias_off = slot(key + ".b", "vec_sum", {key + ".bias"}, "f32", {g.n_pad});
     g.out = out; g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
     attach_stats(g, out);
@@ -545,6 +549,8 @@ int Plan::build(std::string& err) {
   if (c.cross_attention_dim % 64 != 0) { err = "cross_attention_dim must be a multiple of 64"; return DV_ERR_UNSUPPORTED; }
   if (c.x_channels < 1 || c.x_channels > c.in_channels) { err = "x_channels out of range"; return DV_ERR_INVALID; }
   if (c.out_channels > 128) { err = "out_channels > 128 not supported"; return DV_ERR_UNSUPPORTED; }
+  if (c.precision != DV_PRECISION_BF16 && c.precision != DV_PRECISION_FP32X3) { err = "unknown precision"; return DV_ERR_INVALID; }
+  split = c.precision == DV_PRECISION_FP32X3;
   emb_dim = 4 * c.block_out_channels[0];
   if (emb_dim != 512) { err = "time_embed_dim must be 512 (block_out_channels[0] == 128)"; return DV_ERR_UNSUPPORTED; }
   cin_pad = round_up(c.in_channels, 64);
@@ -560,9 +566,9 @@ int Plan::build(std::string& err) {
   const int C0 = c.block_out_channels[0];
 
   // ---- persistent regions
-  off_xin = b.ws_alloc(static_cast<size_t>(B) * T * cin_pad * 2);
+  off_xin = b.ws_alloc(b.tensor_bytes(T, cin_pad));
   b.ehs_bf16.L = Tp; b.ehs_bf16.C = c.cross_attention_dim;
-  b.ehs_bf16.off = b.ws_alloc(static_cast<size_t>(B) * Tp * c.cross_attention_dim * 2);
+  b.ehs_bf16.off = b.ws_alloc(b.tensor_bytes(Tp, c.cross_attention_dim));
   off_ehs = b.ehs_bf16.off;
   off_aug = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4);
   off_embact = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4 * 2);          // two time-table slots
@@ -761,23 +767,48 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         GemmDesc& g = o.g;
         GemmParams& p = o.gp;
         memset(&p, 0, sizeof p);
+        // kernel map 2 * s = hi plane of logical source s, 2 * s + 1 = its lo plane (split precision only)
         for (int i = 0; i < GEMM_MAX_SRC; ++i) {
-          const int s = i < g.nsrc ? i : 0;  // unused maps alias source 0 so prefetch.tensormap stays valid
+          const int s = (i >> 1) < g.nsrc ? (i >> 1) : 0;  // unused maps alias source 0 so prefetch.tensormap stays valid
           const TRef& t = g.src[s];
-          if (!make_tmap_3d(&p.mapA[i], ws + t.off, g.view_c[s], g.view_c[s], g.view_l[s], B,
+          const size_t lo = (split && (i & 1)) ? plane(t) : 0;
+          if (!make_tmap_3d(&p.mapA[i], ws + t.off + lo, g.view_c[s], g.view_c[s], g.view_l[s], B,
                             static_cast<size_t>(t.L) * t.C, err))
             return false;
         }
         if (!make_tmap_2d(&p.mapW, params + g.w_off, g.k_tot, g.n_pad, 64, err)) return false;
-        for (int i = 0; i < g.nseg; ++i) p.seg[i] = g.seg[i];
-        p.nseg = g.nseg;
+        p.mapW2 = p.mapW;
+        if (split && !make_tmap_2d(&p.mapW2, params + g.w_off + static_cast<size_t>(g.n_pad) * g.k_tot * 2, g.k_tot, g.n_pad, 64, err))
+          return false;
+        // logical segment -> kernel segments: a.w (BF16) or a_hi.w_hi + a_hi.w_lo + a_lo.w_hi (split: three K segments
+        // over the same weight panels of the hi / lo matrix)
+        p.nseg = 0;
+        int wk = 0;
+        for (int i = 0; i < g.nseg; ++i) {
+          GemmSeg sg = g.seg[i];
+          const int lsrc = sg.src;
+          sg.wk0 = static_cast<int16_t>(wk);
+          sg.wsel = 0;
+          sg.src = static_cast<int16_t>(2 * lsrc);
+          p.seg[p.nseg++] = sg;
+          if (split) {
+            sg.wsel = 1;
+            p.seg[p.nseg++] = sg;                         // a_hi . w_lo
+            sg.wsel = 0;
+            sg.src = static_cast<int16_t>(2 * lsrc + 1);
+            p.seg[p.nseg++] = sg;                         // a_lo . w_hi
+          }
+          wk += sg.npanels;
+        }
         p.B = B; p.L = g.l_out; p.N = g.n; p.n_pad = g.n_pad;
         p.tiles_per_batch = (g.l_out + 127) / 128;
         p.out_mode = g.out_mode;
         p.bias = pf(g.bias_off);
         p.res = g.res.valid() ? ws + g.res.off : nullptr;
+        p.res_lo = (split && g.res.valid()) ? ws + g.res.off + plane(g.res) : nullptr;
         p.ld_res = g.res.valid() ? g.res.C : 0;
         p.out = g.out_dynamic ? nullptr : ws + g.out.off;
+        p.out_lo = (split && !g.out_dynamic && g.out_mode != GEMM_OUT_F32_NCL) ? ws + g.out.off + plane(g.out) : nullptr;
         p.ld_out = g.ld_out;
         p.out_bs = g.out_bs;
         p.trim_col = g.trim_col;
@@ -835,15 +866,33 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         o.gn.x0 = ws + o.gno.x0;
         o.gn.x1 = o.gn.c1 ? ws + o.gno.x1 : nullptr;
         o.gn.out = ws + o.gno.out;
+        o.gn.x0_lo = o.gn.x1_lo = nullptr; o.gn.out_lo = nullptr;
+        if (split) {
+          const size_t rows = static_cast<size_t>(B) * o.gn.L * 2;
+          o.gn.x0_lo = ws + o.gno.x0 + rows * o.gn.c0;
+          if (o.gn.c1) o.gn.x1_lo = ws + o.gno.x1 + rows * o.gn.c1;
+          o.gn.out_lo = ws + o.gno.out + rows * (o.gn.c0 + o.gn.c1);
+        }
         for (int i = 0; i < o.gn.nst; ++i) o.gn.st[i].ptr = reinterpret_cast<const float*>(ws + off_stats + o.gno.st[i]);
         o.gn.gamma = pf(o.gno.gamma);
         o.gn.beta = pf(o.gno.beta);
         o.gn.scale_shift = o.gno.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + o.gno.ss;
       } else if (o.kind == OP_LN) {
         o.ln.x = ws + o.lno.x; o.ln.out = ws + o.lno.out;
+        o.ln.x_lo = nullptr; o.ln.out_lo = nullptr;
+        if (split) {
+          const size_t pl = static_cast<size_t>(o.ln.rows) * o.ln.C * 2;
+          o.ln.x_lo = ws + o.lno.x + pl; o.ln.out_lo = ws + o.lno.out + pl;
+        }
         o.ln.gamma = pf(o.lno.gamma); o.ln.beta = pf(o.lno.beta);
       } else if (o.kind == OP_ATTN) {
         o.at.q = ws + o.ato.q; o.at.k = ws + o.ato.k; o.at.v = ws + o.ato.v; o.at.o = ws + o.ato.o;
+        if (split) {   // lo plane of the tensor each operand lives in: + B * (batch stride) bf16 elements
+          o.at.q_lo = ws + o.ato.q + static_cast<size_t>(B) * o.at.bs_q * 2;
+          o.at.k_lo = ws + o.ato.k + static_cast<size_t>(B) * o.at.bs_k * 2;
+          o.at.v_lo = ws + o.ato.v + static_cast<size_t>(B) * o.at.bs_v * 2;
+          o.at.o_lo = ws + o.ato.o + static_cast<size_t>(B) * o.at.bs_o * 2;
+        }
         o.at.kv_len = nullptr;  // set in prompt_prepare
         const char* ae = nullptr;
         if (!attention_tc_prepare(o.at, &ae)) { err = std::string("attention_tc_prepare: ") + (ae ? ae : "?"); return false; }
@@ -908,7 +957,9 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
           e = launch_gn_apply(o.gn, st);
         }
         break;
-      case OP_LN: e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st); break;
+      case OP_LN:
+        e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st, o.ln.x_lo, o.ln.out_lo);
+        break;
       case OP_ATTN: {
         AttnParams a = o.at;
         if (o.ato.cross && has_kvlen) a.kv_len = reinterpret_cast<const int*>(ws + off_kvlen);
@@ -929,7 +980,7 @@ int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_l
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!ehs) { err = "ehs is null"; return DV_ERR_INVALID; }
   const size_t n = static_cast<size_t>(B) * Tp * cfg.cross_attention_dim;
-  DV_CK(launch_f32_to_bf16(ehs, ws + off_ehs, n, st));
+  DV_CK(launch_f32_to_bf16(ehs, ws + off_ehs, n, st, split ? ws + off_ehs + n * 2 : nullptr));
   // The captured loop reads the prompt-side tensors at fixed workspace addresses, so a new batch of the same shape
   // keeps the graph; only a change of WHICH optional inputs exist (their pointers are baked into the launches) drops it.
   const bool topo_changed = prompt_ready && (has_aug != (aug != nullptr) || has_kvlen != (kv_len != nullptr));
@@ -951,7 +1002,8 @@ int Plan::set_cond(const float* cond, cudaStream_t st, std::string& err) {
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   const int cc = cfg.in_channels - cfg.x_channels;
   if (cc <= 0) return DV_OK;
-  DV_CK(launch_nct_to_ntc(cond, ws + off_xin, B, cc, T, cin_pad, cfg.x_channels, 1 << 30, 0, st));
+  DV_CK(launch_nct_to_ntc(cond, ws + off_xin, B, cc, T, cin_pad, cfg.x_channels, 1 << 30, 0, st,
+                          split ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
   return DV_OK;
 }
 
@@ -1011,7 +1063,8 @@ int Plan::forward(const float* sample, int x_only, const float* t, int t_stride,
                   std::string& err, int* launches, cudaEvent_t* events, int tables_slot) {
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
-  DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st));
+  DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st,
+                          split ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
   if (tables_slot < 0) {
     int rc = enqueue_time_tables(t, t_stride, 0, st, err);
     if (rc != DV_OK) return rc;

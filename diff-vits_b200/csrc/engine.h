@@ -31,12 +31,12 @@ struct ParamSlot {
 enum OpKind { OP_GEMM = 0, OP_GN_APPLY = 2, OP_LN = 3, OP_ATTN = 4, OP_CHAIN = 5 };
 int& skip_kinds_mask();   // measurement hook (dv_debug_skip_kinds): op kinds that are not launched
 
-struct GemmDesc {
+struct GemmDesc {   // logical description: bind() expands it to the kernel's maps / segments (x3 in split precision)
   int nsrc = 0;
-  TRef src[GEMM_MAX_SRC];
-  int view_l[GEMM_MAX_SRC], view_c[GEMM_MAX_SRC];  // TMA view (stride-2 conv reads [L/2, 2C])
+  TRef src[GEMM_MAX_LSRC];
+  int view_l[GEMM_MAX_LSRC], view_c[GEMM_MAX_LSRC];  // TMA view (stride-2 conv reads [L/2, 2C])
   int nseg = 0;
-  GemmSeg seg[GEMM_MAX_SEG];
+  GemmSeg seg[GEMM_MAX_LSEG];
   size_t w_off = 0; int k_tot = 0, n = 0, n_pad = 0;
   long long bias_off = -1;
   TRef res; TRef out;
@@ -77,7 +77,7 @@ struct Op {
   GemmDesc g; GemmParams gp;
   ChainDesc ch; ChainParams cp;
   GnParams gn;
-  struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; } ln;
+  struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; const void* x_lo; void* out_lo; } ln;
   AttnParams at;
   // deferred (offset-based) descriptions resolved in bind()
   struct { size_t x0, x1, out; long long st[2]; long long gamma, beta, ss; } gno;
@@ -89,6 +89,9 @@ struct Plan {
   dv_unet_cfg cfg;
   int B, T, Tp;
   int n_levels, emb_dim, cin_pad;
+  bool split = false;        // cfg.precision == DV_PRECISION_FP32X3: every bf16 tensor [B, L, C] of the workspace is followed by
+                             // its lo plane (same shape, at + B*L*C*2 bytes), every bf16 weight matrix by its lo matrix
+  size_t plane(const TRef& t) const { return static_cast<size_t>(B) * t.L * t.C * 2; }
   // Widest level whose transformer blocks run as chained kernels (DV_FUSE_MAXC). Measured on C2 (B200, 32 x 1000):
   // the chain wins or ties while a level has >= ~1.5 row tiles per SM (C = 128: 250 tiles); deeper levels have too few
   // 128-row tiles (125 / 63) to fill 148 SMs with one CTA per tile, there the one-kernel-per-op program is faster.

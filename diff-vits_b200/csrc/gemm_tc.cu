@@ -72,8 +72,9 @@ struct EpiCtx {
   int lane, srow, spiece;
 };
 
-__device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& e, int gcol, int lq, size_t rowbase, uint4 (&rv)[4]) {
-  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.res);
+__device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& e, int gcol, int lq, size_t rowbase, uint4 (&rv)[4],
+                                             const void* plane = nullptr) {
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(plane ? plane : p.res);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + e.srow;
@@ -83,7 +84,7 @@ __device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& 
 }
 
 // One 32-row x 32-column chunk of a bf16 output tile: (+bias) (+residual) -> bf16, GroupNorm partials, coalesced store.
-template <bool HAS_RES, bool HAS_STATS, bool TRIM>
+template <bool HAS_RES, bool HAS_STATS, bool TRIM, bool SPLIT>
 __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx& e, uint32_t taddr_c, int gcol, int lq,
                                               size_t rowbase, size_t obase, bool valid, size_t stat_chunk, bool last,
                                               uint64_t* empty_bar, uint4 (&rv)[4], bool preloaded) {
@@ -103,6 +104,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     if (e.lane == 0) mbar_arrive(empty_bar);
   }
   uint32_t rr[16];
+  uint32_t rrl[SPLIT ? 16 : 1];
   if (HAS_RES) {
     __syncwarp();
 #pragma unroll
@@ -110,8 +112,23 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
       const uint4 t = lds128(e.mine + j * 16);
       rr[4 * j] = t.x; rr[4 * j + 1] = t.y; rr[4 * j + 2] = t.z; rr[4 * j + 3] = t.w;
     }
+    if (SPLIT) {                                          // lo plane of the residual, staged the same way
+      uint4 rl[4];
+      epi_load_res(p, e, gcol, lq, rowbase, rl, p.res_lo);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts128(e.coal + i * 8 * EPI_PITCH, rl[i]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 t = lds128(e.mine + j * 16);
+        rrl[4 * j] = t.x; rrl[4 * j + 1] = t.y; rrl[4 * j + 2] = t.z; rrl[4 * j + 3] = t.w;
+      }
+      __syncwarp();
+    }
   }
   uint32_t packed[16];
+  uint32_t packed_lo[SPLIT ? 16 : 1];
   float2 s0 = make_float2(0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {                      // 4 columns per iteration: one broadcast LDS.128 of bias
@@ -123,7 +140,9 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
       float2 v = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
       v = add_f32x2(v, h ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y));
       if (HAS_RES) v = add_f32x2(v, make_float2(bf16_lo(rr[j >> 1]), bf16_hi(rr[j >> 1])));
+      if (HAS_RES && SPLIT) v = add_f32x2(v, make_float2(bf16_lo(rrl[j >> 1]), bf16_hi(rrl[j >> 1])));
       packed[j >> 1] = pack_bf16(v.x, v.y);
+      if (SPLIT) packed_lo[j >> 1] = pack_bf16(v.x - bf16_lo(packed[j >> 1]), v.y - bf16_hi(packed[j >> 1]));
       if (HAS_STATS) {
         if (j < 16) { s0 = add_f32x2(s0, v); q0 = fma_f32x2(v, v, q0); }
         else        { s1 = add_f32x2(s1, v); q1 = fma_f32x2(v, v, q1); }
@@ -141,22 +160,27 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
       *reinterpret_cast<float4*>(p.stats + (stat_chunk * p.stats_nblk + (gcol >> 4)) * 2) = make_float4(a0, b0, a1, b1);
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    sts128(e.mine + j * 16, make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]));
-  __syncwarp();
+  for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
+    const uint32_t* pk = (SPLIT && pl) ? packed_lo : packed;
+    __nv_bfloat16* o = (SPLIT && pl) ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) : out;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rrow = i * 8 + e.srow;
-    const bool keep = !(TRIM && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
-    if (lq + rrow < p.L && keep && !DV_DBG(p, 8))
-      *reinterpret_cast<uint4*>(out + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
-          lds128(e.coal + i * 8 * EPI_PITCH);
+    for (int j = 0; j < 4; ++j)
+      sts128(e.mine + j * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rrow = i * 8 + e.srow;
+      const bool keep = !(TRIM && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
+      if (lq + rrow < p.L && keep && !DV_DBG(p, 8))
+        *reinterpret_cast<uint4*>(o + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
+            lds128(e.coal + i * 8 * EPI_PITCH);
+    }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // TRIM: instantiation for the odd-length folded upsample conv (output batch stride != L * ld_out, last half row absent)
-template <int BN, int EW, bool TRIM>
+template <int BN, int EW, bool TRIM, bool SPLIT = false>
 __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using SL = SmemLayout<BN, EW>;
   constexpr int PARTS = EW / 4;                       // epilogue warps per TMEM lane quarter
@@ -181,6 +205,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < GEMM_MAX_SRC; ++s) tma_prefetch_desc(&p.mapA[s]);
     tma_prefetch_desc(&p.mapW);
+    tma_prefetch_desc(&p.mapW2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -211,12 +236,17 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       if (!DV_DBG(p, 4 | 64)) {
         const int n0 = (blockIdx.x % n_tiles_n) * BN;
         pre = total_panels < STAGES ? total_panels : STAGES;
-        for (int st = 0; st < pre; ++st) {
-          uint8_t* sb = smem + st * SL::STAGE_BYTES + SL::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[st], SL::STAGE_BYTES);
+        int st = 0;
+        for (int sgi = 0; sgi < p.nseg && st < pre; ++sgi) {
+          const GemmSeg sg = p.seg[sgi];
+          const CUtensorMap* mw = sg.wsel ? &p.mapW2 : &p.mapW;
+          for (int q = 0; q < sg.npanels && st < pre; ++q, ++st) {
+            uint8_t* sb = smem + st * SL::STAGE_BYTES + SL::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[st], SL::STAGE_BYTES);
 #pragma unroll
-          for (int h = 0; h < BN / 64; ++h)
-            tma_load_2d(sb + h * (64 * BK * 2), &p.mapW, &full_bar[st], st * BK, n0 + h * 64);
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sb + h * (64 * BK * 2), mw, &full_bar[st], (sg.wk0 + q) * BK, n0 + h * 64);
+          }
         }
       }
       pdl_wait();
@@ -233,6 +263,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
         for (int s = 0; s < p.nseg; ++s) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* ma = &p.mapA[sg.src];
+          const CUtensorMap* mw = sg.wsel ? &p.mapW2 : &p.mapW;
           for (int q = 0; q < sg.npanels; ++q, ++kp, ++issued) {
             uint8_t* sa = smem + stage * SL::STAGE_BYTES;
             uint8_t* sb = sa + SL::A_BYTES;
@@ -248,7 +279,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
             // the W map's box is 64 x 64 rows: a BN-wide tile takes BN / 64 boxes, stacked contiguously
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h)
-              tma_load_2d(sb + h * (64 * BK * 2), &p.mapW, &full_bar[stage], kp * BK, n0 + h * 64);
+              tma_load_2d(sb + h * (64 * BK * 2), mw, &full_bar[stage], (sg.wk0 + q) * BK, n0 + h * 64);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -350,6 +381,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
           uint32_t packed[8];
+          uint32_t packed_lo[SPLIT ? 8 : 1];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bg = bu;
@@ -362,20 +394,34 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
             const float2 ub = add_f32x2(make_float2(__uint_as_float(u[j + 2]), __uint_as_float(u[j + 3])), make_float2(bu.z, bu.w));
             const float2 ga = add_f32x2(make_float2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), make_float2(bg.x, bg.y));
             const float2 gb = add_f32x2(make_float2(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), make_float2(bg.z, bg.w));
-            packed[2 * j4] = pack_bf16(ua.x * gelu_fast_f(ga.x), ua.y * gelu_fast_f(ga.y));
-            packed[2 * j4 + 1] = pack_bf16(ub.x * gelu_fast_f(gb.x), ub.y * gelu_fast_f(gb.y));
+            if (SPLIT) {                                     // FP32-class mode: exact erf GELU, hi + lo planes
+              const float h0 = ua.x * gelu_erf_f(ga.x), h1 = ua.y * gelu_erf_f(ga.y);
+              const float h2 = ub.x * gelu_erf_f(gb.x), h3 = ub.y * gelu_erf_f(gb.y);
+              packed[2 * j4] = pack_bf16(h0, h1);
+              packed[2 * j4 + 1] = pack_bf16(h2, h3);
+              packed_lo[2 * j4] = pack_bf16(h0 - bf16_lo(packed[2 * j4]), h1 - bf16_hi(packed[2 * j4]));
+              packed_lo[2 * j4 + 1] = pack_bf16(h2 - bf16_lo(packed[2 * j4 + 1]), h3 - bf16_hi(packed[2 * j4 + 1]));
+            } else {
+              packed[2 * j4] = pack_bf16(ua.x * gelu_fast_f(ga.x), ua.y * gelu_fast_f(ga.y));
+              packed[2 * j4 + 1] = pack_bf16(ub.x * gelu_fast_f(gb.x), ub.y * gelu_fast_f(gb.y));
+            }
           }
-          sts128(e.mine, make_uint4(packed[0], packed[1], packed[2], packed[3]));
-          sts128(e.mine + 16, make_uint4(packed[4], packed[5], packed[6], packed[7]));
-          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int r = i * 16 + orow;
-            if (lq + r < p.L)
-              *reinterpret_cast<uint4*>(out + (rowbase + lq + r) * p.ld_out + ocol + opiece * 8) =
-                  lds128(slab + r * EPI_PITCH + opiece * 16);
+          for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
+            const uint32_t* pk = (SPLIT && pl) ? packed_lo : packed;
+            __nv_bfloat16* o = (SPLIT && pl) ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) : out;
+            sts128(e.mine, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            sts128(e.mine + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r = i * 16 + orow;
+              if (lq + r < p.L)
+                *reinterpret_cast<uint4*>(o + (rowbase + lq + r) * p.ld_out + ocol + opiece * 8) =
+                    lds128(slab + r * EPI_PITCH + opiece * 16);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       } else if (p.out_mode == GEMM_OUT_F32_NCL) {
         float* out = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.N * p.L + (valid ? l : 0);
@@ -415,11 +461,11 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           arrived |= last;
           const uint32_t tc = taddr + ch * 32;
           if (has_res) {
-            if (has_stats) epi_chunk_bf16<true, true, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
-            else           epi_chunk_bf16<true, false, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            if (has_stats) epi_chunk_bf16<true, true, TRIM, SPLIT>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<true, false, TRIM, SPLIT>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           } else {
-            if (has_stats) epi_chunk_bf16<false, true, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
-            else           epi_chunk_bf16<false, false, TRIM>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            if (has_stats) epi_chunk_bf16<false, true, TRIM, SPLIT>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
+            else           epi_chunk_bf16<false, false, TRIM, SPLIT>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
           }
         }
         if (!arrived) {                                   // this warp's columns were all padding
@@ -469,13 +515,13 @@ __global__ void gemm_ref_kernel(GemmParams p, GemmRefSrc s0, GemmRefSrc s1, Gemm
 int g_num_sms = 0;
 int g_force_ew = 0;   // DV_GEMM_EW: 8 / 16 force the CTA shape of the 128-wide tile kernel (0 = heuristic)
 
-template <int BN, int EW, bool TRIM = false>
+template <int BN, int EW, bool TRIM = false, bool SPLIT = false>
 cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
   using SL = SmemLayout<BN, EW>;
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / BN);
   const int slots = g_num_sms * (EW == 8 ? 2 : 1);
   const int grid = tiles < slots ? tiles : slots;
-  return launch_k(gemm_tc_kernel<BN, EW, TRIM>, dim3(grid), dim3(64 + EW * 32), SL::dyn_bytes(p.n_pad), st, p);
+  return launch_k(gemm_tc_kernel<BN, EW, TRIM, SPLIT>, dim3(grid), dim3(64 + EW * 32), SL::dyn_bytes(p.n_pad), st, p);
 }
 
 }  // namespace
@@ -522,6 +568,12 @@ cudaError_t gemm_tc_init() {
   e = cudaFuncSetAttribute(gemm_tc_kernel<256, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(gemm_tc_kernel<256, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
 }
@@ -536,8 +588,16 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   }
   if (p.n_pad % 128 != 0 || p.n_pad > MAX_NPAD || p.nseg < 1 || p.nseg > GEMM_MAX_SEG) return cudaErrorInvalidValue;
   if (p.out_mode == GEMM_OUT_GEGLU && p.n_pad % 128 != 0) return cudaErrorInvalidValue;
-  const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
   const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
+  if (p.out_lo != nullptr) {                             // split precision: one tile shape (128 x 128, 16 epilogue warps)
+    if (p.res != nullptr && p.res_lo == nullptr) return cudaErrorInvalidValue;
+    if (p.trim_col > 0 || !dense) {
+      if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
+      return launch_bn<128, 16, true, true>(p, st);
+    }
+    return launch_bn<128, 16, false, true>(p, st);
+  }
+  const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
   if (p.trim_col > 0 || !dense) {                        // odd-length folded upsample conv: its own instantiations
     if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
     if (bn == 256 && p.n_pad % 256 == 0) return launch_bn<256, 16, true>(p, st);

@@ -20,11 +20,11 @@ namespace {
 
 constexpr int NT = 256;
 
-__device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, int c) {
+__device__ __forceinline__ const uint4* gn_src(const GnParams& p, int b, int l, int c, bool lo = false) {
   if (c < p.c0)
-    return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x0) +
+    return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(lo ? p.x0_lo : p.x0) +
                                           (static_cast<size_t>(b) * p.L + l) * p.c0 + c);
-  return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x1) +
+  return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(lo ? p.x1_lo : p.x1) +
                                         (static_cast<size_t>(b) * p.L + l) * p.c1 + (c - p.c0));
 }
 
@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const GnParams p, float* _
   }
 }
 
+// SPLIT: FP32-class mode - the input is hi + lo, the result is written as hi and lo planes.
+template <bool SPLIT>
 __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows_per_cta) {
   pdl_launch_dependents();
   __shared__ float s_mean[32], s_rstd[32];
@@ -97,11 +99,13 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
   const int lbeg = blockIdx.x * rows_per_cta;
   const int lend = min(lbeg + rows_per_cta, p.L);
   uint4 v[UNR];
+  uint4 vl[SPLIT ? UNR : 1];
   if (r < R) {
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int l = lbeg + r + u * R;
       v[u] = l < lend ? __ldg(gn_src(p, b, l, cbase)) : make_uint4(0, 0, 0, 0);
+      if (SPLIT) vl[u] = l < lend ? __ldg(gn_src(p, b, l, cbase, true)) : make_uint4(0, 0, 0, 0);
     }
   }
   // ---- group statistics: one warp per group; the (block, chunk, fold) index space is flattened over the lanes so
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
       for (int u = 0; u < UNR; ++u) {
         const int l = l0 + u * R;
         v[u] = l < lend ? __ldg(gn_src(p, b, l, cbase)) : make_uint4(0, 0, 0, 0);
+        if (SPLIT) vl[u] = l < lend ? __ldg(gn_src(p, b, l, cbase, true)) : make_uint4(0, 0, 0, 0);
       }
     }
 #pragma unroll
@@ -193,15 +198,25 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
       const int l = l0 + u * R;
       if (l >= lend) continue;
       const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      uint32_t y[4];
+      uint32_t y[4], yl[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float a = fmaf(bf16_lo(w[j]), ca[2 * j], cb[2 * j]);
-        float c = fmaf(bf16_hi(w[j]), ca[2 * j + 1], cb[2 * j + 1]);
+        float xa = bf16_lo(w[j]), xc = bf16_hi(w[j]);
+        if (SPLIT) {
+          const uint32_t wl = j == 0 ? vl[u].x : (j == 1 ? vl[u].y : (j == 2 ? vl[u].z : vl[u].w));
+          xa += bf16_lo(wl);
+          xc += bf16_hi(wl);
+        }
+        float a = fmaf(xa, ca[2 * j], cb[2 * j]);
+        float c = fmaf(xc, ca[2 * j + 1], cb[2 * j + 1]);
         if (p.silu) { a = silu_f(a); c = silu_f(c); }
         y[j] = pack_bf16(a, c);
+        if (SPLIT) yl[j] = pack_bf16(a - bf16_lo(y[j]), c - bf16_hi(y[j]));
       }
       *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * p.L + l) * C + cbase) = make_uint4(y[0], y[1], y[2], y[3]);
+      if (SPLIT)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + (static_cast<size_t>(b) * p.L + l) * C + cbase) =
+            make_uint4(yl[0], yl[1], yl[2], yl[3]);
     }
   }
 }
@@ -210,10 +225,11 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
 // works on LN_ROWS rows at a time with all of their loads issued up front (memory-level parallelism: at C = 128 a
 // row is only 8 bytes per lane).
 constexpr int LN_WARPS = 8;
-template <int CHUNKS>
+template <int CHUNKS, bool SPLIT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        int rows, float eps) {
+                                                        int rows, float eps, const __nv_bfloat16* __restrict__ x_lo,
+                                                        __nv_bfloat16* __restrict__ out_lo) {
   constexpr int C = CHUNKS * 128;
   constexpr int LN_ROWS = CHUNKS <= 2 ? 4 : 2;
   pdl_launch_dependents();
@@ -228,12 +244,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const int row0 = (blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * LN_ROWS;
   if (row0 >= rows) return;
   uint2 w[LN_ROWS][CHUNKS];
+  uint2 wl[SPLIT ? LN_ROWS : 1][SPLIT ? CHUNKS : 1];
 #pragma unroll
   for (int rr = 0; rr < LN_ROWS; ++rr) {
     const int row = min(row0 + rr, rows - 1);
     const uint2* xr = reinterpret_cast<const uint2*>(x + static_cast<size_t>(row) * C);
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) w[rr][i] = __ldg(xr + lane + 32 * i);
+    if (SPLIT) {
+      const uint2* xl = reinterpret_cast<const uint2*>(x_lo + static_cast<size_t>(row) * C);
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) wl[rr][i] = __ldg(xl + lane + 32 * i);
+    }
   }
 #pragma unroll
   for (int rr = 0; rr < LN_ROWS; ++rr) {
@@ -244,6 +266,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
       v[i][0] = bf16_lo(w[rr][i].x); v[i][1] = bf16_hi(w[rr][i].x); v[i][2] = bf16_lo(w[rr][i].y); v[i][3] = bf16_hi(w[rr][i].y);
+      if (SPLIT) {
+        v[i][0] += bf16_lo(wl[rr][i].x); v[i][1] += bf16_hi(wl[rr][i].x);
+        v[i][2] += bf16_lo(wl[rr][i].y); v[i][3] += bf16_hi(wl[rr][i].y);
+      }
       s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
 #pragma unroll
@@ -260,10 +286,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C);
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
+      const float y0 = (v[i][0] - mean) * rstd * gm[i].x + bt[i].x, y1 = (v[i][1] - mean) * rstd * gm[i].y + bt[i].y;
+      const float y2 = (v[i][2] - mean) * rstd * gm[i].z + bt[i].z, y3 = (v[i][3] - mean) * rstd * gm[i].w + bt[i].w;
       uint2 o;
-      o.x = pack_bf16((v[i][0] - mean) * rstd * gm[i].x + bt[i].x, (v[i][1] - mean) * rstd * gm[i].y + bt[i].y);
-      o.y = pack_bf16((v[i][2] - mean) * rstd * gm[i].z + bt[i].z, (v[i][3] - mean) * rstd * gm[i].w + bt[i].w);
+      o.x = pack_bf16(y0, y1);
+      o.y = pack_bf16(y2, y3);
       orow[lane + 32 * i] = o;
+      if (SPLIT) {
+        uint2 ol;
+        ol.x = pack_bf16(y0 - bf16_lo(o.x), y1 - bf16_hi(o.x));
+        ol.y = pack_bf16(y2 - bf16_lo(o.y), y3 - bf16_hi(o.y));
+        reinterpret_cast<uint2*>(out_lo + static_cast<size_t>(row) * C)[lane + 32 * i] = ol;
+      }
     }
   }
 }
@@ -290,24 +324,36 @@ cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
   int rows = 4 * (NT / (C >> 3));
   if (rows < 4) rows = 4;
   dim3 grid((p.L + rows - 1) / rows, p.B);
-  return launch_k(gn_apply_kernel, grid, dim3(NT), 0, st, p, rows);
+  if (p.out_lo != nullptr) {
+    if (!p.x0_lo || (p.c1 && !p.x1_lo)) return cudaErrorInvalidValue;
+    return launch_k(gn_apply_kernel<true>, grid, dim3(NT), 0, st, p, rows);
+  }
+  return launch_k(gn_apply_kernel<false>, grid, dim3(NT), 0, st, p, rows);
 }
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
-                             float eps, cudaStream_t st) {
+                             float eps, cudaStream_t st, const void* x_lo, void* out_lo) {
   const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* oo = reinterpret_cast<__nv_bfloat16*>(out);
+  const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(x_lo);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
   const int rpc = LN_WARPS * (C <= 256 ? 4 : 2);   // rows per CTA, matches LN_ROWS in the kernel
   dim3 grid((rows + rpc - 1) / rpc);
+  if ((x_lo == nullptr) != (out_lo == nullptr)) return cudaErrorInvalidValue;
+#define DV_LN_CASE(CH)                                                                                                   \
+  case CH * 128:                                                                                                         \
+    return out_lo ? launch_k(layernorm_kernel<CH, true>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps, xl, ol) \
+                  : launch_k(layernorm_kernel<CH, false>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps, xl, ol);
   switch (C) {
-    case 128: return launch_k(layernorm_kernel<1>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
-    case 256: return launch_k(layernorm_kernel<2>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
-    case 384: return launch_k(layernorm_kernel<3>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
-    case 512: return launch_k(layernorm_kernel<4>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
-    case 640: return launch_k(layernorm_kernel<5>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
-    case 768: return launch_k(layernorm_kernel<6>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
-    case 1024: return launch_k(layernorm_kernel<8>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps);
+    DV_LN_CASE(1)
+    DV_LN_CASE(2)
+    DV_LN_CASE(3)
+    DV_LN_CASE(4)
+    DV_LN_CASE(5)
+    DV_LN_CASE(6)
+    DV_LN_CASE(8)
     default: return cudaErrorInvalidValue;
   }
+#undef DV_LN_CASE
 }
 
 }  // namespace dv

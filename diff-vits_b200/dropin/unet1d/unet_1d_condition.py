@@ -218,6 +218,11 @@ class UNet1DConditionModel(nn.Module):
         self._engines: "collections.OrderedDict[Tuple, Any]" = collections.OrderedDict()
         self._engine_cache_size = int(os.environ.get("DV_PLAN_CACHE", "4"))
         self._params_cache: Optional[Tuple[Tuple, torch.Tensor]] = None
+        # arithmetic of the native path: "bf16" (fast path) or "fp32x3" (hi + lo BF16 operand split, FP32-class accuracy:
+        # include/diffvits_b200.h DV_PRECISION_*). Not a constructor argument (the reference's ctor has none): set the
+        # attribute, or DV_PRECISION in the environment, before the first forward / sample.
+        from diffvits_b200.engine import default_precision
+        self.native_precision = default_precision()
 
     # ------------------------------------------------------------------------------------------ engine plumbing
     @property
@@ -241,7 +246,7 @@ class UNet1DConditionModel(nn.Module):
         device = require_cuda(self.device)
         if self.dtype != torch.float32:
             raise RuntimeError("keep UNet1DConditionModel parameters in fp32; the engine packs BF16 operands itself")
-        ver = (str(device),) + self._weights_version()
+        ver = (str(device), self.native_precision) + self._weights_version()
         if self._params_cache is not None and self._params_cache[0] != ver:
             self._params_cache = None
             for e in self._engines.values():
@@ -251,7 +256,8 @@ class UNet1DConditionModel(nn.Module):
         eng = None if private else self._engines.get(key)
         if eng is None:
             blob = None if self._params_cache is None else self._params_cache[1]
-            eng = DenoiserGroup(self, B, T, Tp, device, x_channels=x_channels, params=blob, lanes=lanes)
+            eng = DenoiserGroup(self, B, T, Tp, device, x_channels=x_channels, params=blob, lanes=lanes,
+                                precision=self.native_precision)
             if self._params_cache is None:
                 self._params_cache = (ver, eng.params)
             if not private:
@@ -270,7 +276,7 @@ class UNet1DConditionModel(nn.Module):
         from diffvits_b200.native import NativeDenoiser
         B, Cc, T = cond.shape
         key = ("denoiser", B, T, ehs.shape[1], Cc)
-        ver = (str(self.device),) + self._weights_version()
+        ver = (str(self.device), self.native_precision) + self._weights_version()
         if self._params_cache is not None and self._params_cache[0] != ver:
             self._params_cache = None
             for e in self._engines.values():

@@ -117,6 +117,11 @@ def pack_slot(slot: dict, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
         n_expected *= d
     if out.numel() != n_expected:
         raise ValueError(f"slot {slot['name']}: packed {tuple(out.shape)} does not match manifest shape {shape}")
+    if slot["dtype"] == "bf16x2":
+        # FP32-class precision mode: the matrix as two bf16 planes, hi = bf16(w), lo = bf16(w - hi) (w = hi + lo to 16 bits)
+        hi = out.to(torch.bfloat16)
+        lo = (out - hi.to(torch.float32)).to(torch.bfloat16)
+        return torch.cat([hi.reshape(-1), lo.reshape(-1)])
     return out.to(torch.bfloat16 if slot["dtype"] == "bf16" else torch.float32).reshape(-1)
 
 
@@ -131,7 +136,19 @@ def pack_params(manifest: List[dict], sd: Dict[str, torch.Tensor], nbytes: int) 
     return blob
 
 
-def unet_cfg_from_config(config: dict, x_channels: Optional[int] = None) -> UnetCfg:
+PRECISIONS = {"bf16": 0, "fp32x3": 1}
+
+
+def default_precision() -> str:
+    """DV_PRECISION=bf16 (default, fast path) | fp32x3 (hi + lo BF16 operand split, FP32-class accuracy)."""
+    import os
+    p = os.environ.get("DV_PRECISION", "bf16").lower()
+    if p not in PRECISIONS:
+        raise ValueError(f"DV_PRECISION={p!r}: expected one of {sorted(PRECISIONS)}")
+    return p
+
+
+def unet_cfg_from_config(config: dict, x_channels: Optional[int] = None, precision: str = "bf16") -> UnetCfg:
     """Translate the reference UNet's config dict (unet_1d_condition.py:560-607) into the C struct; raises
     ValueError for configurations outside the accelerated path."""
     boc = tuple(config["block_out_channels"])
@@ -171,6 +188,7 @@ def unet_cfg_from_config(config: dict, x_channels: Optional[int] = None) -> Unet
     cfg.num_heads = heads
     cfg.norm_eps = config["norm_eps"]
     cfg.x_channels = x_channels if x_channels is not None else min(config["out_channels"], config["in_channels"])
+    cfg.precision = PRECISIONS[precision]
     return cfg
 
 
@@ -179,12 +197,13 @@ class DenoiserEngine:
     """One plan of the native UNet forward / sampling loop at fixed (B, T, Tp) on one CUDA device."""
 
     def __init__(self, unet: torch.nn.Module, B: int, T: int, Tp: int, device, x_channels: Optional[int] = None,
-                 params: Optional[torch.Tensor] = None):
+                 params: Optional[torch.Tensor] = None, precision: str = "bf16"):
         self.device = require_cuda(device)
         self.lib = _lib.load()
         self.unet = unet
         self.B, self.T, self.Tp = int(B), int(T), int(Tp)
-        self.cfg = unet_cfg_from_config(unet.config, x_channels)
+        self.precision = precision
+        self.cfg = unet_cfg_from_config(unet.config, x_channels, precision)
         self.x_channels = self.cfg.x_channels
         self.in_channels, self.out_channels = self.cfg.in_channels, self.cfg.out_channels
         self._plan = C.c_void_p()
@@ -286,8 +305,11 @@ class DenoiserEngine:
         for i in range(self.lib.dv_plan_tensor_count(self._plan)):
             check(self.lib.dv_plan_tensor_info(self._plan, i, buf, 160, C.byref(off), C.byref(L), C.byref(Cc)))
             n = self.B * L.value * Cc.value * 2
-            out[buf.value.decode()] = self.workspace[off.value: off.value + n].view(torch.bfloat16).view(
-                self.B, L.value, Cc.value)
+            t = self.workspace[off.value: off.value + n].view(torch.bfloat16).view(self.B, L.value, Cc.value)
+            if self.precision == "fp32x3":      # hi + lo planes -> the fp32 value they carry
+                lo = self.workspace[off.value + n: off.value + 2 * n].view(torch.bfloat16).view(self.B, L.value, Cc.value)
+                t = t.float() + lo.float()
+            out[buf.value.decode()] = t
         return out
 
     # ---- measurement support
@@ -339,7 +361,8 @@ class DenoiserGroup:
     interface as DenoiserEngine; `sample` captures all lanes into one CUDA graph (dv_sample_group)."""
 
     def __init__(self, unet: torch.nn.Module, B: int, T: int, Tp: int, device, x_channels: Optional[int] = None,
-                 params: Optional[torch.Tensor] = None, lanes: Optional[int] = None):
+                 params: Optional[torch.Tensor] = None, lanes: Optional[int] = None, precision: str = "bf16"):
+        self.precision = precision
         lanes = default_lanes(B) if lanes is None else max(1, min(int(lanes), B))
         base, extra = divmod(B, lanes)
         self.sizes = [base + (1 if i < extra else 0) for i in range(lanes)]
@@ -348,7 +371,7 @@ class DenoiserGroup:
             self.bounds.append(self.bounds[-1] + n)
         self.engines: List[DenoiserEngine] = []
         for n in self.sizes:
-            eng = DenoiserEngine(unet, n, T, Tp, device, x_channels=x_channels, params=params)
+            eng = DenoiserEngine(unet, n, T, Tp, device, x_channels=x_channels, params=params, precision=precision)
             params = eng.params
             self.engines.append(eng)
         e0 = self.engines[0]

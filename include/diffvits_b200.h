@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DV_VERSION 100
+#define DV_VERSION 101
 
 #if defined(__GNUC__)
 #define DV_API __attribute__((visibility("default")))
@@ -54,7 +54,17 @@ typedef struct dv_unet_cfg {
   int num_heads;              /* `attention_head_dim` in the reference ctor (it is the head COUNT): 8 */
   float norm_eps;             /* 1e-5 */
   int x_channels;             /* leading input channels that change every step (the noisy latent): 100 */
+  int precision;              /* DV_PRECISION_BF16 (0) or DV_PRECISION_FP32X3 (1), see below */
 } dv_unet_cfg;
+
+/* Arithmetic of the contractions. The reference computes in FP32 (unet1d/lora.py:99-104, attention_processor.py:1032).
+ *  DV_PRECISION_BF16   : BF16 operands, FP32 accumulation - the fast path (per-call rel-L2 vs the FP32 reference ~8e-3,
+ *                        the same floor as the reference under torch.autocast(bfloat16)).
+ *  DV_PRECISION_FP32X3 : every BF16 operand carries a second "lo" plane (x = hi + lo, 16 mantissa bits) and every product
+ *                        is a_hi.w_hi + a_hi.w_lo + a_lo.w_hi on the same tcgen05 kernel (three K segments per logical
+ *                        segment); norms / SiLU / GELU / attention core in FP32. Meets the FP32 gate (1e-4 rel-L2). */
+#define DV_PRECISION_BF16 0
+#define DV_PRECISION_FP32X3 1
 
 typedef struct dv_plan dv_plan;
 
