@@ -43,11 +43,23 @@ class GemmSrc(C.Structure):
 
 
 class GemmSeg(C.Structure):
-    _fields_ = [("src", C.c_int), ("row_off", C.c_int), ("c0", C.c_int), ("npanels", C.c_int)]
+    _fields_ = [("src", C.c_int), ("row_off", C.c_int), ("c0", C.c_int), ("npanels", C.c_int), ("ntap", C.c_int),
+                ("wk0", C.c_int), ("tap_stride", C.c_int), ("xf", C.c_int), ("xf_c0", C.c_int)]
+
+    def __init__(self, src=0, row_off=0, c0=0, npanels=0, ntap=1, wk0=-1, tap_stride=0, xf=0, xf_c0=0):
+        super().__init__(src, row_off, c0, npanels, ntap, wk0, tap_stride, xf, xf_c0)
+
+
+class GemmNorm(C.Structure):
+    _fields_ = [("stats", C.c_void_p * 2), ("chunks", C.c_int * 2), ("nblk", C.c_int * 2), ("fold", C.c_int * 2),
+                ("cover", C.c_int * 2), ("nst", C.c_int), ("C", C.c_int), ("L", C.c_int), ("G", C.c_int),
+                ("eps", C.c_float), ("silu", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("scale_shift", C.c_void_p), ("ss_ld", C.c_int)]
 
 
 class GemmOpts(C.Structure):
-    _fields_ = [("bn", C.c_int), ("stats", C.c_void_p), ("out_bs", C.c_longlong), ("trim_col", C.c_int)]
+    _fields_ = [("bn", C.c_int), ("stats", C.c_void_p), ("out_bs", C.c_longlong), ("trim_col", C.c_int),
+                ("norm", C.POINTER(GemmNorm))]
 
 
 # name -> (restype, argtypes); mirrors include/diffvits_b200.h one to one

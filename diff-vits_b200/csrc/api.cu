@@ -203,9 +203,13 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   std::string err;
   dv::GemmRefSrc rs[dv::GEMM_MAX_SRC];
   for (int i = 0; i < dv::GEMM_MAX_SRC; ++i) {
-    const dv_gemm_src& s = srcs[i < nsrc ? i : 0];
+    const int si = i < nsrc ? i : 0;
+    const dv_gemm_src& s = srcs[si];
     if (s.C % 64) return fail(DV_ERR_INVALID, "source channels must be a multiple of 64");
-    if (!dv::make_tmap_3d(&p.mapA[i], s.ptr, s.C, s.ld, s.L, B, s.bs > 0 ? static_cast<size_t>(s.bs) : static_cast<size_t>(s.L) * s.ld, err))
+    int rows = 128;                                        // sources read with shared conv taps stage a 136-row box
+    for (int k = 0; k < nseg; ++k) if (segs[k].src == si && segs[k].ntap == 3) rows = 136;
+    p.map_rows[i] = static_cast<int16_t>(rows);
+    if (!dv::make_tmap_3d(&p.mapA[i], s.ptr, s.C, s.ld, s.L, B, s.bs > 0 ? static_cast<size_t>(s.bs) : static_cast<size_t>(s.L) * s.ld, err, rows))
       return fail(DV_ERR_CUDA, err);
     rs[i] = dv::GemmRefSrc{s.ptr, s.L, s.C, s.ld};
   }
@@ -219,8 +223,15 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
     p.seg[i].c0 = static_cast<int16_t>(segs[i].c0);
     p.seg[i].npanels = static_cast<int16_t>(segs[i].npanels);
     p.seg[i].wsel = 0;
-    p.seg[i].wk0 = static_cast<int16_t>(ksum / 64);
-    ksum += segs[i].npanels * 64;
+    const int ntap = segs[i].ntap == 3 ? 3 : 1;
+    if (segs[i].ntap != 0 && segs[i].ntap != 1 && segs[i].ntap != 3) return fail(DV_ERR_INVALID, "ntap must be 1 or 3");
+    p.seg[i].ntap = static_cast<int16_t>(ntap);
+    p.seg[i].wk0 = static_cast<int16_t>(segs[i].wk0 >= 0 ? segs[i].wk0 : ksum / 64);
+    p.seg[i].tap_stride = static_cast<int16_t>(segs[i].tap_stride > 0 ? segs[i].tap_stride : segs[i].npanels);
+    p.seg[i].xf = static_cast<int16_t>(segs[i].xf);
+    p.seg[i].xf_c0 = static_cast<int16_t>(segs[i].xf_c0);
+    if (segs[i].xf && !(opts && opts->norm)) return fail(DV_ERR_INVALID, "xf segment without dv_gemm_opts.norm");
+    ksum += segs[i].npanels * 64 * ntap;
   }
   if (ksum != k_tot) return fail(DV_ERR_INVALID, "segments do not add up to k_tot");
   p.nseg = nseg;
@@ -229,6 +240,16 @@ int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg
   p.out_mode = out_mode;
   p.bias = bias; p.res = res; p.ld_res = ld_res; p.out = out; p.ld_out = ld_out;
   if (opts) { p.out_bs = opts->out_bs; p.trim_col = opts->trim_col; p.stats = opts->stats; p.bn = opts->bn; }
+  if (opts && opts->norm) {
+    const dv_gemm_norm& nm = *opts->norm;
+    if (nm.nst < 1 || nm.nst > 2) return fail(DV_ERR_INVALID, "norm.nst must be 1 or 2");
+    for (int i = 0; i < nm.nst; ++i) {
+      p.xf.st_ptr[i] = nm.stats[i]; p.xf.st_chunks[i] = nm.chunks[i]; p.xf.st_nblk[i] = nm.nblk[i];
+      p.xf.st_fold[i] = nm.fold[i]; p.xf.st_cover[i] = nm.cover[i];
+    }
+    p.xf.nst = nm.nst; p.xf.C = nm.C; p.xf.L = nm.L; p.xf.G = nm.G; p.xf.eps = nm.eps; p.xf.silu = nm.silu;
+    p.xf.gamma = nm.gamma; p.xf.beta = nm.beta; p.xf.scale_shift = nm.scale_shift; p.xf.ss_ld = nm.ss_ld;
+  }
   p.stats_nblk = n / 16;
 #ifdef DV_DEBUG_HOOKS
   p.trace = g_test_trace; p.dbg_flags = g_test_flags;

@@ -26,12 +26,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn(std::string& err) {
 }
 
 bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
-                  std::string& err) {
+                  std::string& err, int box_rows) {
   auto fn = get_encode_fn(err);
   if (!fn) return false;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(view_c), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(batch_stride_elems) * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -169,29 +169,48 @@ struct Builder {
   Op& emit_gemm(std::vector<Op>& list, const std::string& tag) {
     Op o;
     o.kind = OP_GEMM; o.tag = tag;
-    for (int i = 0; i < GEMM_MAX_SRC; ++i) { o.g.view_l[i] = 0; o.g.view_c[i] = 0; }
+    for (int i = 0; i < GEMM_MAX_LSRC; ++i) { o.g.view_l[i] = 0; o.g.view_c[i] = 0; }
     list.push_back(o);
     return list.back();
   }
   static void add_src(GemmDesc& g, TRef t) {
     g.src[g.nsrc] = t; g.view_l[g.nsrc] = t.L; g.view_c[g.nsrc] = t.C; g.nsrc++;
   }
-  static void add_seg(GemmDesc& g, int src, int row_off, int c0, int channels) {
+  // ntap = 3: conv k3 with shared rows (row_off = -1). wk0 < 0: the segment's weights follow the previous segment's in K;
+  // tap_stride 0: the taps of this segment are `channels` apart (single-source conv).
+  static void add_seg(GemmDesc& g, int src, int row_off, int c0, int channels, int ntap = 1, int wk0 = -1, int tap_stride = 0,
+                      bool xf = false, int xf_c0 = 0) {
     GemmSeg s;
+    memset(&s, 0, sizeof s);
     s.src = static_cast<int16_t>(src); s.row_off = static_cast<int16_t>(row_off);
     s.c0 = static_cast<int16_t>(c0); s.npanels = static_cast<int16_t>(channels / 64);
+    s.ntap = static_cast<int16_t>(ntap);
+    s.wk0 = static_cast<int16_t>(wk0 >= 0 ? wk0 : g.k_tot / 64);
+    s.tap_stride = static_cast<int16_t>(tap_stride > 0 ? tap_stride : channels / 64);
+    s.xf = xf ? 1 : 0; s.xf_c0 = static_cast<int16_t>(xf_c0);
     g.seg[g.nseg++] = s;
-    g.k_tot += channels;
+    g.k_tot += channels * ntap;
+  }
+  // GroupNorm parameters of a fused-norm GEMM
+  void set_xf(GemmDesc& g, TRef x0, TRef x1, const std::string& norm_key, float eps, bool silu, long long ss_off) {
+    const int C = x0.C + (x1.valid() ? x1.C : 0);
+    if (x0.st_off < 0 || (x1.valid() && x1.st_off < 0)) { err = "internal: GroupNorm input without statistics: " + norm_key; return; }
+    g.xf.on = true; g.xf.x0 = x0; g.xf.x1 = x1;
+    g.xf.gamma = vec(norm_key + ".weight", C);
+    g.xf.beta = vec(norm_key + ".bias", C);
+    g.xf.ss = ss_off; g.xf.eps = eps; g.xf.silu = silu;
   }
 
-  // Linear / 1x1 conv: out[L, N] = a[L, K] W^T (+bias) (+res)
+  // Linear / 1x1 conv: out[L, N] = a[L, K] W^T (+bias) (+res). norm_key != "": `a` is the RAW input of a GroupNorm (eps,
+  // no SiLU) that is applied on the way into the tensor core.
   void linear(std::vector<Op>& list, const std::string& tag, TRef a, const std::string& recipe,
               std::vector<std::string> wkeys, const std::string& bias_key, int N, TRef res, TRef& out, int out_mode,
-              bool stats = false) {
+              bool stats = false, const std::string& norm_key = "", float norm_eps = 1e-5f) {
     Op& o = emit_gemm(list, tag);
     GemmDesc& g = o.g;
     add_src(g, a);
-    add_seg(g, 0, 0, 0, a.C);
+    add_seg(g, 0, 0, 0, a.C, 1, -1, 0, !norm_key.empty(), 0);
+    if (!norm_key.empty()) set_xf(g, a, TRef(), norm_key, norm_eps, false, -1);
     g.n = N; g.n_pad = round_up(N, 128);
     g.w_off = slot(tag + ".W", recipe, std::move(wkeys), "bf16", {g.n_pad, g.k_tot});
     if (!bias_key.empty())
@@ -200,14 +219,30 @@ struct Builder {
     if (stats) attach_stats(g, out);
   }
 
-  // conv k3 s1 p1 over `a` (+ optional 1x1 shortcut over xs fused as extra K panels) (+ optional identity residual)
-  void conv3(std::vector<Op>& list, const std::string& tag, TRef a, int cin_real, const std::string& wkey,
+  // conv k3 s1 p1 over (a0 | a1) (+ optional 1x1 shortcut over xs fused as extra K panels) (+ optional identity residual).
+  // Each 64-channel panel is staged once (136 rows) and read by the three taps through row-shifted descriptors.
+  // norm_key != "": (a0 | a1) is the RAW input of GroupNorm(norm_key) + SiLU (+ time scale/shift at ss_off), applied in
+  // shared memory on the way into the tensor core; otherwise a0 is the already normalised operand.
+  void conv3(std::vector<Op>& list, const std::string& tag, TRef a0, TRef a1, int cin_real, const std::string& wkey,
              const std::string& bkey, int N, const TRef* sc_src, int n_sc, const std::string& sc_key, TRef res,
-             TRef& out, int out_mode, bool dynamic_out) {
+             TRef& out, int out_mode, bool dynamic_out, const std::string& norm_key = "", long long ss_off = -1) {
     Op& o = emit_gemm(list, tag);
     GemmDesc& g = o.g;
-    add_src(g, a);
-    for (int tap = 0; tap < 3; ++tap) add_seg(g, 0, tap - 1, 0, a.C);
+    const bool xf = !norm_key.empty();
+    const int cin = a0.C + (a1.valid() ? a1.C : 0);
+    const int np = cin / 64;                       // K panels per tap: weights are tap-major over the concatenated channels
+    add_src(g, a0);
+    if (a1.valid()) add_src(g, a1);
+    if (P.gemm2) {
+      add_seg(g, 0, -1, 0, a0.C, 3, 0, np, xf, 0);
+      if (a1.valid()) add_seg(g, 1, -1, 0, a1.C, 3, a0.C / 64, np, xf, a0.C);
+    } else {                                       // one-ring kernel: a segment (= its own A loads) per tap and source
+      for (int tap = 0; tap < 3; ++tap) {
+        add_seg(g, 0, tap - 1, 0, a0.C, 1, tap * np);
+        if (a1.valid()) add_seg(g, 1, tap - 1, 0, a1.C, 1, tap * np + a0.C / 64);
+      }
+    }
+    if (xf) set_xf(g, a0, a1, norm_key, P.cfg.norm_eps, true, ss_off);
     std::vector<std::string> wk = {wkey};
     std::vector<std::string> bk = {bkey};
     for (int i = 0; i < n_sc; ++i) {
@@ -217,11 +252,11 @@ struct Builder {
     if (n_sc) { wk.push_back(sc_key + ".weight"); bk.push_back(sc_key + ".bias"); }
     g.n = N; g.n_pad = round_up(N, 128);
     long long wo = slot(tag + ".W", "conv3", wk, "bf16", {g.n_pad, g.k_tot});
-    P.slots.back().shape.push_back(cin_real);  // [n_pad, k_tot, cin_real]: packer pads each tap from cin_real to a.C
+    P.slots.back().shape.push_back(cin_real);  // [n_pad, k_tot, cin_real]: packer pads each tap from cin_real to cin
     P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.split ? 2 : 1);
     g.w_off = wo;
     g.bias_off = slot(tag + ".b", "vec_sum", bk, "f32", {g.n_pad});
-    g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
+    g.res = res; g.out = out; g.l_out = a0.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
     if (out_mode == GEMM_OUT_BF16) attach_stats(g, out);
   }
 
@@ -230,28 +265,38 @@ struct Builder {
     const int L = x0.L;
     const int cin = x0.C + (x1.valid() ? x1.C : 0);
     const float eps = P.cfg.norm_eps;
-    TRef a = tmp(L, cin);
-    emit_gn(P.ops, pfx + ".norm1", x0, x1, pfx + ".norm1", eps, true, -1, a);
     TRef u = tmp(L, cout);
-    conv3(P.ops, pfx + ".conv1", a, cin, pfx + ".conv1.weight", pfx + ".conv1.bias", cout, nullptr, 0, "", TRef(), u,
-          GEMM_OUT_BF16, false);
+    if (P.fuse_gn) {
+      conv3(P.ops, pfx + ".conv1", x0, x1, cin, pfx + ".conv1.weight", pfx + ".conv1.bias", cout, nullptr, 0, "", TRef(), u,
+            GEMM_OUT_BF16, false, pfx + ".norm1", -1);
+    } else {
+      TRef a = tmp(L, cin);
+      emit_gn(P.ops, pfx + ".norm1", x0, x1, pfx + ".norm1", eps, true, -1, a);
+      conv3(P.ops, pfx + ".conv1", a, TRef(), cin, pfx + ".conv1.weight", pfx + ".conv1.bias", cout, nullptr, 0, "", TRef(), u,
+            GEMM_OUT_BF16, false);
+    }
     // time scale/shift: rows [ss_cur, ss_cur + 2*cout) of the stacked time_emb_proj
     wall_keys.push_back(pfx + ".time_emb_proj.weight");
     ball_keys.push_back(pfx + ".time_emb_proj.bias");
     const long long ss_off = ss_cur;
     ss_cur += 2 * cout;
-    TRef v = tmp(L, cout);
-    emit_gn(P.ops, pfx + ".norm2", u, TRef(), pfx + ".norm2", eps, true, ss_off, v);
+    TRef v = u;
+    std::string n2 = pfx + ".norm2";
+    if (!P.fuse_gn) {
+      v = tmp(L, cout);
+      emit_gn(P.ops, pfx + ".norm2", u, TRef(), pfx + ".norm2", eps, true, ss_off, v);
+      n2.clear();
+    }
     TRef y = act(L, cout);
     if (cin != cout) {
       TRef sc[2] = {x0, x1};
-      conv3(P.ops, pfx + ".conv2", v, cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, sc, x1.valid() ? 2 : 1,
-            pfx + ".conv_shortcut", TRef(), y, GEMM_OUT_BF16, false);
+      conv3(P.ops, pfx + ".conv2", v, TRef(), cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, sc, x1.valid() ? 2 : 1,
+            pfx + ".conv_shortcut", TRef(), y, GEMM_OUT_BF16, false, n2, ss_off);
       P.named.emplace_back(pfx, y);
     } else {
       if (x1.valid()) { err = "identity shortcut over a channel concat is not supported"; return y; }
-      conv3(P.ops, pfx + ".conv2", v, cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, nullptr, 0, "", x0, y,
-            GEMM_OUT_BF16, false);
+      conv3(P.ops, pfx + ".conv2", v, TRef(), cout, pfx + ".conv2.weight", pfx + ".conv2.bias", cout, nullptr, 0, "", x0, y,
+            GEMM_OUT_BF16, false, n2, ss_off);
       P.named.emplace_back(pfx, y);
     }
     return y;
@@ -262,19 +307,26 @@ struct Builder {
     scratch_reset();
     const int L = y.L, C = y.C, H = P.cfg.num_heads, D = C / H;
     const std::string tb = pfx + ".transformer_blocks.0";
-    TRef g = tmp(L, C);
-    emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
+    const bool ln_fused = P.fuse_ln && !P.split && C % 128 == 0 && C <= 384;
+    const bool gn_in_gemm = P.fuse_gn && !ln_fused;   // (the one-stage chain of DV_FUSE_LN has no operand transform)
+    TRef g = y;                                  // fused: proj_in reads the raw block input and normalises it in flight
+    std::string gn_key = pfx + ".norm";
+    if (!gn_in_gemm) {
+      g = tmp(L, C);
+      emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
+      gn_key.clear();
+    }
     TRef z = tmp(L, C);
     TRef nrm = tmp(L, C);
     TRef qkv = tmp(L, 3 * C);
     TRef ao = tmp(L, C);
     // A projection whose output row fits one CTA's TMEM accumulator (C <= 384) takes the LayerNorm that follows it
     // along as a one-stage chain (csrc/chain_tc.cu, CH_ROW with a global LayerNorm output): one launch instead of two.
-    const bool ln_fused = P.fuse_ln && !P.split && C % 128 == 0 && C <= 384;
     auto proj_ln = [&](const std::string& tag, TRef a, const std::string& wkey, const std::string& bkey, TRef res,
                        const std::string& lnkey) {
       if (!ln_fused) {
-        linear(P.ops, tag, a, "linear", {wkey}, bkey, C, res, z, GEMM_OUT_BF16);
+        linear(P.ops, tag, a, "linear", {wkey}, bkey, C, res, z, GEMM_OUT_BF16, false,
+               (tag == pfx + ".proj_in") ? gn_key : std::string(), 1e-6f);
         emit_ln(P.ops, lnkey, z, lnkey, nrm);
         return;
       }
@@ -494,14 +546,20 @@ struct Builder {
     GemmDesc& g = o.g;
     const bool odd = (Ls & 1) != 0;
     add_src(g, x);
-    add_seg(g, 0, -1, 0, C);
-    add_seg(g, 0, 0, 0, C);
-    if (odd) {
+    if (!odd && P.gemm2) {
+      add_seg(g, 0, -1, 0, C, 3);                 // (x, -1) (x, 0) (x, +1): one staged box, three row-shifted reads
+    } else if (!odd) {
+      add_seg(g, 0, -1, 0, C);
+      add_seg(g, 0, 0, 0, C);
+      add_seg(g, 0, 1, 0, C);
+    } else {
+      add_seg(g, 0, -1, 0, C);
+      add_seg(g, 0, 0, 0, C);
       add_src(g, x);
       g.view_l[1] = x.L - 1;
       add_seg(g, 1, 0, 0, C);
+      add_seg(g, 0, 1, 0, C);
     }
-    add_seg(g, 0, 1, 0, C);
     g.n = 2 * C; g.n_pad = round_up(2 * C, 128);
     // both packings live in the parameter blob so that its layout does not depend on (B, T, Tp): one packed blob per
     // module serves every plan (engine.py: DenoiserGroup shares it)
@@ -561,6 +619,10 @@ int Plan::build(std::string& err) {
     { const char* fl = getenv("DV_FUSE_LN"); fuse_ln = fl && fl[0] == '1'; }
     const char* fm = getenv("DV_FUSE_MAXC");
     fuse_max_c = fm ? atoi(fm) : 128;
+    const char* fg = getenv("DV_FUSE_GN");
+    fuse_gn = !split && fg && fg[0] == '1';
+    const char* g2 = getenv("DV_GEMM2");
+    gemm2 = fuse_gn || (g2 && g2[0] == '1');
   }
   Builder b(*this);
   const int C0 = c.block_out_channels[0];
@@ -594,7 +656,7 @@ int Plan::build(std::string& err) {
   xin.off = off_xin; xin.L = T; xin.C = cin_pad;
   std::vector<TRef> skips;
   TRef h = b.act(T, C0);
-  b.conv3(ops, "conv_in", xin, c.in_channels, "conv_in.weight", "conv_in.bias", C0, nullptr, 0, "", TRef(), h,
+  b.conv3(ops, "conv_in", xin, TRef(), c.in_channels, "conv_in.weight", "conv_in.bias", C0, nullptr, 0, "", TRef(), h,
           GEMM_OUT_BF16, false);
   named.emplace_back("conv_in", h);
   skips.push_back(h);
@@ -633,12 +695,17 @@ int Plan::build(std::string& err) {
   if (!b.err.empty()) { err = b.err; return DV_ERR_UNSUPPORTED; }
   {
     b.scratch_reset();
-    TRef a = b.tmp(T, C0);
-    b.emit_gn(ops, "conv_norm_out", h, TRef(), "conv_norm_out", c.norm_eps, true, -1, a);
     TRef dummy;
     dummy.L = T; dummy.C = c.out_channels;
-    b.conv3(ops, "conv_out", a, C0, "conv_out.weight", "conv_out.bias", c.out_channels, nullptr, 0, "", TRef(), dummy,
-            GEMM_OUT_F32_NCL, true);
+    if (fuse_gn) {
+      b.conv3(ops, "conv_out", h, TRef(), C0, "conv_out.weight", "conv_out.bias", c.out_channels, nullptr, 0, "", TRef(), dummy,
+              GEMM_OUT_F32_NCL, true, "conv_norm_out", -1);
+    } else {
+      TRef a = b.tmp(T, C0);
+      b.emit_gn(ops, "conv_norm_out", h, TRef(), "conv_norm_out", c.norm_eps, true, -1, a);
+      b.conv3(ops, "conv_out", a, TRef(), C0, "conv_out.weight", "conv_out.bias", c.out_channels, nullptr, 0, "", TRef(), dummy,
+              GEMM_OUT_F32_NCL, true);
+    }
   }
 
   // ---- stacked time_emb_proj
@@ -659,6 +726,7 @@ int Plan::build(std::string& err) {
           for (int i = 0; i < o.g.nsrc; ++i) fix(o.g.src[i].off);
           if (o.g.res.valid()) fix(o.g.res.off);
           fix(o.g.out.off);
+          if (o.g.xf.on) { fix(o.g.xf.x0.off); if (o.g.xf.x1.valid()) fix(o.g.xf.x1.off); }
           break;
         case OP_GN_APPLY:
           fix(o.gno.x0); fix(o.gno.x1); fix(o.gno.out);
@@ -772,8 +840,11 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
           const int s = (i >> 1) < g.nsrc ? (i >> 1) : 0;  // unused maps alias source 0 so prefetch.tensormap stays valid
           const TRef& t = g.src[s];
           const size_t lo = (split && (i & 1)) ? plane(t) : 0;
+          int rows = 128;                                  // sources read with shared conv taps stage a 136-row box
+          for (int k = 0; k < g.nseg; ++k) if (g.seg[k].src == s && g.seg[k].ntap == 3) rows = 136;
+          p.map_rows[i] = static_cast<int16_t>(rows);
           if (!make_tmap_3d(&p.mapA[i], ws + t.off + lo, g.view_c[s], g.view_c[s], g.view_l[s], B,
-                            static_cast<size_t>(t.L) * t.C, err))
+                            static_cast<size_t>(t.L) * t.C, err, rows))
             return false;
         }
         if (!make_tmap_2d(&p.mapW, params + g.w_off, g.k_tot, g.n_pad, 64, err)) return false;
@@ -783,11 +854,9 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         // logical segment -> kernel segments: a.w (BF16) or a_hi.w_hi + a_hi.w_lo + a_lo.w_hi (split: three K segments
         // over the same weight panels of the hi / lo matrix)
         p.nseg = 0;
-        int wk = 0;
         for (int i = 0; i < g.nseg; ++i) {
           GemmSeg sg = g.seg[i];
           const int lsrc = sg.src;
-          sg.wk0 = static_cast<int16_t>(wk);
           sg.wsel = 0;
           sg.src = static_cast<int16_t>(2 * lsrc);
           p.seg[p.nseg++] = sg;
@@ -798,7 +867,21 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
             sg.src = static_cast<int16_t>(2 * lsrc + 1);
             p.seg[p.nseg++] = sg;                         // a_lo . w_hi
           }
-          wk += sg.npanels;
+        }
+        if (g.xf.on) {                                    // GroupNorm fused into the operand path
+          GemmXf& x = p.xf;
+          const TRef* xs[2] = {&g.xf.x0, &g.xf.x1};
+          x.nst = g.xf.x1.valid() ? 2 : 1;
+          for (int i = 0; i < x.nst; ++i) {
+            x.st_ptr[i] = reinterpret_cast<const float*>(ws + off_stats + xs[i]->st_off);
+            x.st_chunks[i] = xs[i]->st_chunks; x.st_nblk[i] = xs[i]->st_nblk; x.st_fold[i] = xs[i]->st_fold;
+            x.st_cover[i] = xs[i]->C;
+          }
+          x.C = g.xf.x0.C + (g.xf.x1.valid() ? g.xf.x1.C : 0);
+          x.L = g.xf.x0.L; x.G = cfg.norm_num_groups; x.eps = g.xf.eps; x.silu = g.xf.silu ? 1 : 0;
+          x.gamma = pf(g.xf.gamma); x.beta = pf(g.xf.beta);
+          x.scale_shift = g.xf.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + g.xf.ss;
+          x.ss_ld = n_all;
         }
         p.B = B; p.L = g.l_out; p.N = g.n; p.n_pad = g.n_pad;
         p.tiles_per_batch = (g.l_out + 127) / 128;
@@ -939,9 +1022,10 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
     if (skip_kinds & (1 << o.kind)) { if (launches) ++*launches; continue; }
     switch (o.kind) {
       case OP_GEMM:
-        if (o.g.out_dynamic) {
+        if (o.g.out_dynamic || (ss_slot && o.gp.xf.scale_shift)) {
           GemmParams p = o.gp;
-          p.out = dyn_out;
+          if (o.g.out_dynamic) p.out = dyn_out;
+          if (ss_slot && p.xf.scale_shift) p.xf.scale_shift += static_cast<size_t>(ss_slot) * B * n_all;
           e = launch_gemm_tc(p, st);
         } else {
           e = launch_gemm_tc(o.gp, st);

@@ -31,6 +31,15 @@ struct ParamSlot {
 enum OpKind { OP_GEMM = 0, OP_GN_APPLY = 2, OP_LN = 3, OP_ATTN = 4, OP_CHAIN = 5 };
 int& skip_kinds_mask();   // measurement hook (dv_debug_skip_kinds): op kinds that are not launched
 
+// GroupNorm fused into a GEMM's operand path (GemmSeg::xf): the normalised tensor is (x0 | x1), never materialised
+struct XfDesc {
+  bool on = false;
+  TRef x0, x1;
+  long long gamma = -1, beta = -1, ss = -1;   // parameter slots / column offset into the time scale-shift table
+  float eps = 1e-5f;
+  bool silu = false;
+};
+
 struct GemmDesc {   // logical description: bind() expands it to the kernel's maps / segments (x3 in split precision)
   int nsrc = 0;
   TRef src[GEMM_MAX_LSRC];
@@ -47,6 +56,7 @@ struct GemmDesc {   // logical description: bind() expands it to the kernel's ma
   bool out_dynamic = false;  // conv_out: destination supplied per call
   long long stats_off = -1;  // >= 0: emit GroupNorm partials of the output
   int stats_nblk = 0;
+  XfDesc xf;
 };
 
 // One stage of a chained-GEMM launch (kernels.h: ChainStage), offsets instead of pointers until bind()
@@ -100,6 +110,10 @@ struct Plan {
                              // slower on C2 (4.62 vs 4.34 ms per call: one 128-row tile per CTA with a three-pass epilogue loses to
                              // an N-split GEMM + a streaming LayerNorm), so it is off; kept parity-tested for wider-N shapes.
   bool fuse = true;          // transformer sections as chained-GEMM kernels (DV_FUSE=0 selects the one-kernel-per-op program)
+  bool gemm2 = false;        // DV_GEMM2=1: k=3 convs as ONE shared-tap segment on the two-ring kernel (csrc/gemm_tc2.cu) instead of
+                             // three single-tap segments on the one-ring kernel (measured 4 % slower per C2 step: off)
+  bool fuse_gn = false;      // DV_FUSE_GN=1 (implies gemm2): GroupNorm (+SiLU, +scale/shift) applied inside the consuming conv / 1x1 GEMM (operand transform in
+                             // shared memory) instead of a stand-alone gn_apply pass. Parity-tested; measured 13 % slower per C2 step (gemm_tc2.cu header): off
   std::vector<ParamSlot> slots;
   size_t param_bytes = 0, ws_bytes = 0;
   std::vector<Op> ops;       // one denoiser call
@@ -160,7 +174,7 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
                  float* const* x, int flags, cudaStream_t st, std::string& err);
 
 bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
-                  std::string& err);
+                  std::string& err, int box_rows = 128);
 bool make_tmap_2d(CUtensorMap* m, const void* base, int k_tot, int rows, int box_rows, std::string& err);
 
 }  // namespace dv

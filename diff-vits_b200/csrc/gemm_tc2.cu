@@ -1,21 +1,14 @@
-// Tap-GEMM on the 5th-gen tensor cores: implicit-GEMM conv1d (k=3, stride 1 or 2, nearest-2x upsample folded
-// into the weight packing), 1x1 conv and Linear, all as   D[128 x BN] += A_panel[128 x 64] . W_panel[BN x 64]^T.
-//
-// Persistent, warp-specialised kernel: one CTA per SM loops over output tiles (static round-robin schedule).
-//   warp 0    : TMA producer  - one elected lane issues cp.async.bulk.tensor loads (A: 3-D [C, L, B] box 64x128x1,
-//                               W: 2-D [K, N] box 64xBN), 128-byte swizzle, completion on the stage's "full" mbarrier.
-//                               Conv taps are the same box shifted by -1/0/+1 rows; rows outside [0, L) are zero
-//                               filled by TMA, which is exactly the conv padding. torch.cat inputs are extra A maps.
-//   warp 1    : MMA issuer    - lane 0 issues tcgen05.mma.cta_group::1.kind::f16 (BF16 x BF16 -> FP32 in TMEM),
-//                               4 x (K=16) per 64-wide panel; tcgen05.commit releases the smem stage / hands the
-//                               accumulator to the epilogue. Two TMEM accumulators (2 x BN columns) ping-pong, so
-//                               the epilogue of tile i overlaps the main loop of tile i+1.
-//   warps 2-9 : epilogue      - tcgen05.ld 32 lanes x 32 columns -> registers -> (+bias) (+residual) (GEGLU) -> bf16,
-//                               staged through a per-warp smem slab so that global loads/stores are row-contiguous
-//                               (64-byte segments, 8 rows per instruction) instead of one row per thread; optional
-//                               per-(32-row chunk, 16-channel block) sum / sum-of-squares of the stored values for the
-//                               GroupNorm that consumes this tensor (deterministic shuffle tree, no atomics);
-//                               conv_out stores fp32 [B, N, L] directly (lanes = consecutive frames).
+// Tap-GEMM, second pipeline shape (opt-in: DV_GEMM2=1 / DV_FUSE_GN=1, or any segment with shared taps / a fused norm).
+// Same contract, same epilogue and same tcgen05 / TMEM / TMA machinery as csrc/gemm_tc.cu, but:
+//   * TWO rings instead of one (A slots of 136 rows, W slots), each with its own producer warp: a k=3 conv stages ONE
+//     136-row activation box per channel panel and its three taps read it through row-shifted UMMA descriptors
+//     (profiles/r2b_umma_row_shift_probe.txt): a third of the activation traffic;
+//   * optional operand-transform warps: GroupNorm (+time scale/shift, +SiLU) of the resnet / transformer input applied to
+//     the staged box IN SHARED MEMORY between the TMA load and the MMA, so the normalised tensor never exists in HBM.
+// Measured on C2 (B200, profiles/r2d_*): convs run as fast as in the one-ring kernel, but 1x1 / Linear GEMMs lose 20-40 %
+// (the single MMA-issuing thread pays two barrier waits per 64-wide panel instead of one), and the fused norm is redone
+// N / BN times (every column tile of a row block transforms the same rows) on 4 warps that are MUFU / issue bound:
+// the whole step is 4 % (two rings) / 13 % (fused GroupNorm) slower, so the engine's default program does not use it.
 #include <cstdio>
 #include <cstdlib>
 
@@ -35,17 +28,25 @@ constexpr int EPI_PITCH = 80;                       // bytes per staged row: 32 
 constexpr int EPI_SLAB = 32 * EPI_PITCH;            // per epilogue warp
 constexpr int MAX_NPAD = 4096;                      // bias vector kept in shared memory for the whole kernel
 
+constexpr int A_ROWS_MAX = 136;                     // conv k3 with shared taps: 128 + 2 halo rows, padded to whole 8-row atoms
+constexpr int XF_MAXC = 1024;                       // widest normalised tensor (level-3 concat: 512 + 512 channels)
+constexpr int XF_WARPS = 4;
+
 template <int BN, int EW>
 struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = EW == 8 ? 2 : (BN == 64 ? 6 : (BN == 128 ? 5 : (BN == 192 ? 4 : 3)));
-  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + EW * EPI_SLAB;
-  static constexpr int BIAS_OFF = BAR_OFF + 256;       // barriers + tmem slot, then the bias vector (n_pad floats)
+  static constexpr int A_SLOT = A_ROWS_MAX * BK * 2;              // 17408 B = 17 swizzle atoms
+  static constexpr int W_SLOT = BN * BK * 2;
+  static constexpr int NA = EW == 8 ? 2 : (BN <= 128 ? 4 : 3);
+  static constexpr int NW = EW == 8 ? 3 : (BN == 64 ? 8 : (BN == 128 ? 5 : (BN == 192 ? 4 : 3)));
+  static constexpr int W_OFF = NA * A_SLOT;
+  static constexpr int EPI_OFF = W_OFF + NW * W_SLOT;
+  static constexpr int XF_OFF = EPI_OFF + EW * EPI_SLAB;          // coefficient table [2][XF_MAXC] floats + group stats
+  static constexpr int XF_BYTES = 2 * XF_MAXC * 4 + 256;
+  static constexpr int BAR_OFF = XF_OFF + (EW == 8 ? 0 : XF_BYTES);
+  static constexpr int BIAS_OFF = BAR_OFF + 512;       // barriers + tmem slot, then the bias vector (n_pad floats)
   static constexpr int dyn_bytes(int n_pad) { return BIAS_OFF + n_pad * 4 + 1024; }   // + slack for 1024-byte alignment
-  static_assert(dyn_bytes(MAX_NPAD) <= (EW == 8 ? 116224 : 232448), "exceeds the shared memory budget");
+  static constexpr int max_bytes = EW == 8 ? 116224 : 232448;
+  static_assert(dyn_bytes(EW == 8 ? 1024 : MAX_NPAD) <= max_bytes, "exceeds the shared memory budget");
 };
 
 // debug timeline (enabled only when p.trace != nullptr): CTA 0, one lane per role
@@ -179,36 +180,119 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
   }
 }
 
+// GroupNorm coefficients of one batch item for the operand transform: table[c] = a_c, table[XF_MAXC + c] = b_c with
+// y = SiLU?(a_c x + b_c). Statistics: the same partial sums, in the same fixed order, as gn_apply (csrc/norm.cu): one warp
+// per group, (block, chunk, fold) flattened over the lanes, fp64 accumulation, fixed shuffle tree.
+__device__ __forceinline__ void xf_coefficients(const GemmXf& x, int b, float* table, float* gstat, int xw, int lane, int xtid) {
+  const int cpg = x.C / x.G;
+  for (int g = xw; g < x.G; g += XF_WARPS) {
+    double sum = 0.0, sumsq = 0.0;
+    const int kb0 = (g * cpg) >> 4, nkb = cpg >> 4;
+    int cov0 = 0;
+    for (int si = 0; si < x.nst; ++si) {
+      const int lo = max(kb0, cov0 >> 4), hi = min(kb0 + nkb, (cov0 + x.st_cover[si]) >> 4);
+      if (hi > lo) {
+        const int nf = x.st_fold[si] ? 2 : 1;
+        const int per_blk = x.st_chunks[si] * nf;
+        const int items = (hi - lo) * per_blk;
+        const int nblk = x.st_nblk[si];
+        const float* base = x.st_ptr[si] + static_cast<size_t>(b) * x.st_chunks[si] * nblk * 2;
+        for (int i0 = 0; i0 < items; i0 += 128) {
+          float2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            v[u] = make_float2(0.f, 0.f);
+            if (i < items) {
+              const int kl = lo - (cov0 >> 4) + i / per_blk;
+              const int rem = i % per_blk;
+              const int ch = rem / nf, f = rem % nf;
+              v[u] = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(ch) * nblk + kl + f * (nblk >> 1)) * 2));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { sum += static_cast<double>(v[u].x); sumsq += static_cast<double>(v[u].y); }
+        }
+      }
+      cov0 += x.st_cover[si];
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, m);
+      sumsq += __shfl_xor_sync(0xffffffffu, sumsq, m);
+    }
+    if (lane == 0) {
+      const double n = static_cast<double>(x.L) * cpg;
+      const double mean = sum / n;
+      double var = sumsq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gstat[2 * g] = static_cast<float>(mean);
+      gstat[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(x.eps)));
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(XF_WARPS * 32) : "memory");
+  for (int c = xtid; c < x.C; c += XF_WARPS * 32) {
+    const int g = c / cpg;
+    float a = gstat[2 * g + 1] * __ldg(x.gamma + c);
+    float bb = __ldg(x.beta + c) - gstat[2 * g] * a;
+    if (x.scale_shift) {
+      const float s1 = 1.0f + __ldg(x.scale_shift + static_cast<size_t>(b) * x.ss_ld + c);
+      a *= s1;
+      bb = bb * s1 + __ldg(x.scale_shift + static_cast<size_t>(b) * x.ss_ld + x.C + c);
+    }
+    table[c] = a;
+    table[XF_MAXC + c] = bb;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(XF_WARPS * 32) : "memory");
+}
+
 // TRIM: instantiation for the odd-length folded upsample conv (output batch stride != L * ld_out, last half row absent)
-template <int BN, int EW, bool TRIM, bool SPLIT = false>
-__global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+// SPLIT: FP32-class precision (hi + lo planes); XF: operand-transform warps present (GroupNorm fused into the consumer)
+template <int BN, int EW, bool TRIM, bool SPLIT = false, bool XF = false>
+__global__ void __launch_bounds__(96 + EW * 32 + (XF ? XF_WARPS * 32 : 0), EW == 8 ? 2 : 1)
+gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
   using SL = SmemLayout<BN, EW>;
   constexpr int PARTS = EW / 4;                       // epilogue warps per TMEM lane quarter
-  constexpr int STAGES = SL::STAGES;
+  constexpr int NA = SL::NA, NW = SL::NW;
+  static_assert(!(XF && EW == 8), "the transform warps exist only in the one-CTA-per-SM shape");
+  constexpr int WPROD = 2 + EW + (XF ? XF_WARPS : 0);   // last warp: weight producer
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  // A-slot barriers. A raw panel: TMA -> a_full -> MMA. A normalised (xf) panel: TMA -> x_full -> transform warps -> a_ready
+  // -> MMA. The two kinds complete DIFFERENT barriers of a slot, so each barrier's phases count only its own kind of use and
+  // every waiter (which keeps one phase bit per slot and kind) stays exactly in step with it - the transform warps never
+  // have to observe, or skip over, the raw panels.
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* x_full = a_full + NA;
+  uint64_t* a_ready = x_full + NA;
+  uint64_t* a_empty = a_ready + NA;
+  uint64_t* w_full = a_empty + NA;
+  uint64_t* w_empty = w_full + NW;
+  uint64_t* tmem_full_bar = w_empty + NW;         // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  static_assert((4 * NA + 2 * NW + 4) * 8 + 4 <= 512, "barrier region");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int n_tiles_n = p.n_pad / BN;
   const int num_tiles = p.tiles_per_batch * p.B * n_tiles_n;
-  int total_panels = 0;
-  for (int s = 0; s < p.nseg; ++s) total_panels += p.seg[s].npanels;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < GEMM_MAX_SRC; ++s) tma_prefetch_desc(&p.mapA[s]);
     tma_prefetch_desc(&p.mapW);
     tma_prefetch_desc(&p.mapW2);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&x_full[s], 1);
+      mbar_init(&a_ready[s], XF_WARPS * 32);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NW; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -218,7 +302,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   }
   constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;   // power of two >= the two accumulators
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  if (warp >= 2 && p.bias) {                         // bias vector -> shared memory, once per CTA
+  if (warp >= 2 && warp < 2 + EW && p.bias) {        // bias vector -> shared memory, once per CTA
     float* sb = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
     for (int i = threadIdx.x - 64; i < p.n_pad; i += EW * 32) sb[i] = __ldg(p.bias + i);
   }
@@ -227,65 +311,67 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only static data (weights, descriptors); activations of earlier kernels are read only after
-  // griddepcontrol.wait. The producer first puts the W panels of its first ring of stages in flight (weights are static):
+  // griddepcontrol.wait. The producer first puts the W panels of its first ring of slots in flight (weights are static):
   // with PDL that load latency overlaps the previous kernel's tail instead of following it.
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer, activations (A ring)
+    pdl_wait();
     if (lane == 0) {
-      int pre = 0;                                        // stages whose expect_tx + W loads are already issued
-      if (!DV_DBG(p, 4 | 64)) {
-        const int n0 = (blockIdx.x % n_tiles_n) * BN;
-        pre = total_panels < STAGES ? total_panels : STAGES;
-        int st = 0;
-        for (int sgi = 0; sgi < p.nseg && st < pre; ++sgi) {
-          const GemmSeg sg = p.seg[sgi];
-          const CUtensorMap* mw = sg.wsel ? &p.mapW2 : &p.mapW;
-          for (int q = 0; q < sg.npanels && st < pre; ++q, ++st) {
-            uint8_t* sb = smem + st * SL::STAGE_BYTES + SL::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[st], SL::STAGE_BYTES);
-#pragma unroll
-            for (int h = 0; h < BN / 64; ++h)
-              tma_load_2d(sb + h * (64 * BK * 2), mw, &full_bar[st], (sg.wk0 + q) * BK, n0 + h * 64);
-          }
-        }
-      }
-      pdl_wait();
-      int stage = 0;
-      uint32_t phase = 0;
-      int issued = 0;                                     // panels issued by this CTA so far (across tiles)
+      int as = 0;
+      uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mi = tile / n_tiles_n;
-        const int n0 = (tile % n_tiles_n) * BN;
         const int b = mi / p.tiles_per_batch;
         const int l0 = (mi % p.tiles_per_batch) * BM;
-        int kp = 0;
         trace_ev(p, 0, tile, 0);
         for (int s = 0; s < p.nseg; ++s) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* ma = &p.mapA[sg.src];
-          const CUtensorMap* mw = sg.wsel ? &p.mapW2 : &p.mapW;
-          for (int q = 0; q < sg.npanels; ++q, ++kp, ++issued) {
-            uint8_t* sa = smem + stage * SL::STAGE_BYTES;
-            uint8_t* sb = sa + SL::A_BYTES;
-            if (issued < pre) {                           // first ring: barrier armed and W already in flight
-              tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-              continue;
+          const uint32_t a_bytes = static_cast<uint32_t>(p.map_rows[sg.src]) * (BK * 2);
+          for (int q = 0; q < sg.npanels; ++q) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            uint64_t* landed = (XF && sg.xf) ? &x_full[as] : &a_full[as];
+            if (DV_DBG(p, 4)) {
+              mbar_arrive(landed);
+            } else {
+              mbar_arrive_expect_tx(landed, a_bytes);
+              tma_load_3d(smem + as * SL::A_SLOT, ma, landed, sg.c0 + q * BK, l0 + sg.row_off, b);
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (DV_DBG(p, 4)) { mbar_arrive(&full_bar[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
-            mbar_arrive_expect_tx(&full_bar[stage], SL::STAGE_BYTES);
-            tma_load_3d(sa, ma, &full_bar[stage], sg.c0 + q * BK, l0 + sg.row_off, b);
-            // the W map's box is 64 x 64 rows: a BN-wide tile takes BN / 64 boxes, stacked contiguously
-#pragma unroll
-            for (int h = 0; h < BN / 64; ++h)
-              tma_load_2d(sb + h * (64 * BK * 2), mw, &full_bar[stage], (sg.wk0 + q) * BK, n0 + h * 64);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++as == NA) { as = 0; aph ^= 1; }
           }
         }
       }
-    } else {
-      pdl_wait();
+    }
+    __syncwarp();
+  } else if (warp == WPROD) {
+    // ------------------------------------------------------------------ TMA producer, weights (W ring). Weights are static
+    // data: this warp never waits on the previous kernel (no griddepcontrol.wait), so with PDL its first ring of panels is in
+    // flight while the previous kernel drains, and it is never held up by the A ring (its own warp, its own barriers).
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * BN;
+        for (int s = 0; s < p.nseg; ++s) {
+          const GemmSeg sg = p.seg[s];
+          const CUtensorMap* mw = sg.wsel ? &p.mapW2 : &p.mapW;
+          for (int q = 0; q < sg.npanels; ++q)
+            for (int t = 0; t < sg.ntap; ++t) {
+              mbar_wait(&w_empty[ws], wph ^ 1);
+              if (DV_DBG(p, 4)) {
+                mbar_arrive(&w_full[ws]);
+              } else {
+                uint8_t* sb = smem + SL::W_OFF + ws * SL::W_SLOT;
+                mbar_arrive_expect_tx(&w_full[ws], SL::W_SLOT);
+                // the W map's box is 64 x 64 rows: a BN-wide tile takes BN / 64 boxes, stacked contiguously
+#pragma unroll
+                for (int h = 0; h < BN / 64; ++h)
+                  tma_load_2d(sb + h * (64 * BK * 2), mw, &w_full[ws], (sg.wk0 + t * sg.tap_stride + q) * BK, n0 + h * 64);
+              }
+              if (++ws == NW) { ws = 0; wph ^= 1; }
+            }
+        }
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -293,8 +379,8 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, ws = 0;
+      uint32_t full_ph = 0, ready_ph = 0, wph = 0;        // per-slot phase bits of a_full / a_ready (bit = slot)
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -303,20 +389,40 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
         tc_fence_after();
         trace_ev(p, 1, tile, 1);
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kp = 0; kp < total_panels; ++kp) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + SL::A_BYTES);
-          if (!DV_DBG(p, 2))
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const GemmSeg sg = p.seg[s];
+          for (int q = 0; q < sg.npanels; ++q) {
+            if (XF && sg.xf) {
+              mbar_wait(&a_ready[as], (ready_ph >> as) & 1);
+              ready_ph ^= 1u << as;
+            } else {
+              mbar_wait(&a_full[as], (full_ph >> as) & 1);
+              full_ph ^= 1u << as;
+            }
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + as * SL::A_SLOT);
+            for (int t = 0; t < sg.ntap; ++t) {
+              mbar_wait(&w_full[ws], wph);
+              tc_fence_after();
+              // tap t reads rows t .. t + 127 of the slot: start address + t * 128 B (the 128-byte swizzle is a function of
+              // the absolute shared-memory address, so a row-shifted start needs nothing else: r2b_umma_row_shift_probe)
+              const uint64_t adesc = umma_desc_sw128(sa + t * (BK * 2));
+              const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + SL::W_OFF + ws * SL::W_SLOT));
+              if (!DV_DBG(p, 2)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kp | k) != 0);
+                for (int k = 0; k < BK / 16; ++k) {
+                  // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                  umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(&w_empty[ws]);
+              if (++ws == NW) { ws = 0; wph ^= 1; }
+            }
+            umma_commit(&a_empty[as]);
+            if (++as == NA) as = 0;
           }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
         trace_ev(p, 1, tile, 2);
@@ -324,6 +430,61 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
       }
     }
     __syncwarp();
+  } else if (XF && warp >= 2 + EW && warp < WPROD) {
+    // ------------------------------------------------------------------ operand transform: GroupNorm (+SiLU) in shared memory
+    pdl_wait();                                          // the statistics partials come from the producing kernels
+    const int xw = warp - (2 + EW), xtid = threadIdx.x - (2 + EW) * 32;
+    float* table = reinterpret_cast<float*>(smem + SL::XF_OFF);
+    float* gstat = table + 2 * XF_MAXC;
+    int as = 0;
+    uint32_t xph = 0;                                    // per-slot phase bits of x_full
+    int cur_b = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mi = tile / n_tiles_n;
+      const int b = mi / p.tiles_per_batch;
+      const int l0 = (mi % p.tiles_per_batch) * BM;
+      if (b != cur_b && !(DV_DBG(p, 256) && cur_b >= 0)) {   // dbg 256: coefficients once per CTA (timing only)
+        xf_coefficients(p.xf, b, table, gstat, xw, lane, xtid);
+        cur_b = b;
+      }
+      for (int s = 0; s < p.nseg; ++s) {
+        const GemmSeg sg = p.seg[s];
+        const int rows = p.map_rows[sg.src];
+        for (int q = 0; q < sg.npanels; ++q) {
+          if (sg.xf) {
+            mbar_wait(&x_full[as], (xph >> as) & 1);
+            xph ^= 1u << as;
+            const uint32_t slot = smem_u32(smem + as * SL::A_SLOT);
+            const int cbase = sg.xf_c0 + q * BK;
+            // 16-byte pieces: piece jp of row r holds channels 8 * (jp ^ (r & 7)) .. + 8 of the panel (128-byte swizzle)
+            for (int i = xtid; i < rows * 8; i += XF_WARPS * 32) {
+              const int r = i >> 3, jp = i & 7;
+              const int l = l0 + sg.row_off + r;
+              if (l < 0 || l >= p.xf.L) continue;         // rows outside the tensor stay zero: the conv padding
+              const int c = cbase + ((jp ^ (r & 7)) << 3);
+              const uint32_t addr = slot + r * (BK * 2) + jp * 16;
+              const uint4 v = lds128(addr);
+              const float4 a0 = *reinterpret_cast<const float4*>(table + c), a1 = *reinterpret_cast<const float4*>(table + c + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(table + XF_MAXC + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(table + XF_MAXC + c + 4);
+              float y[8];
+              y[0] = fmaf(bf16_lo(v.x), a0.x, b0.x); y[1] = fmaf(bf16_hi(v.x), a0.y, b0.y);
+              y[2] = fmaf(bf16_lo(v.y), a0.z, b0.z); y[3] = fmaf(bf16_hi(v.y), a0.w, b0.w);
+              y[4] = fmaf(bf16_lo(v.z), a1.x, b1.x); y[5] = fmaf(bf16_hi(v.z), a1.y, b1.y);
+              y[6] = fmaf(bf16_lo(v.w), a1.z, b1.z); y[7] = fmaf(bf16_hi(v.w), a1.w, b1.w);
+              if (p.xf.silu && !DV_DBG(p, 128)) {           // dbg 128: no SiLU (timing only)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+              }
+              sts128(addr, make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7])));
+            }
+            fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core's async proxy
+            mbar_arrive(&a_ready[as]);
+          }
+          if (++as == NA) as = 0;
+        }
+      }
+    }
   } else {
     pdl_wait();
     // ------------------------------------------------------------------ epilogue: warps 2..17
@@ -485,66 +646,31 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   }
 }
 
-// ---------------------------------------------------------------- CUDA-core reference of the same contract
-__global__ void gemm_ref_kernel(GemmParams p, GemmRefSrc s0, GemmRefSrc s1, GemmRefSrc s2, const __nv_bfloat16* W,
-                                int k_tot) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;   // packed output column
-  const int l = blockIdx.y;
-  const int b = blockIdx.z;
-  if (n >= p.n_pad) return;
-  GemmRefSrc srcs[3] = {s0, s1, s2};
-  float acc = 0.f;
-  for (int s = 0; s < p.nseg; ++s) {
-    const GemmSeg sg = p.seg[s];
-    const GemmRefSrc& src = srcs[sg.src];
-    for (int t = 0; t < sg.ntap; ++t) {
-      const int ls = l + sg.row_off + t;
-      for (int c = 0; c < sg.npanels * BK; ++c) {
-        const int cs = sg.c0 + c;
-        const int k = (sg.wk0 + t * sg.tap_stride) * BK + c;
-        float a = 0.f;
-        if (ls >= 0 && ls < src.L && cs < src.C)
-          a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src.ptr)[(static_cast<size_t>(b) * src.L + ls) * src.ld + cs]);
-        acc += a * __bfloat162float(W[static_cast<size_t>(n) * k_tot + k]);
-      }
-    }
-  }
-  if (p.bias) acc += p.bias[n];
-  // out is a dense fp32 [B, L, n_pad] scratch in the reference (raw accumulator + bias)
-  reinterpret_cast<float*>(p.out)[(static_cast<size_t>(b) * p.L + l) * p.n_pad + n] = acc;
-}
-
 int g_num_sms = 0;
 int g_force_ew = 0;   // DV_GEMM_EW: 8 / 16 force the CTA shape of the 128-wide tile kernel (0 = heuristic)
 
-template <int BN, int EW, bool TRIM = false, bool SPLIT = false>
+template <int BN, int EW, bool TRIM = false, bool SPLIT = false, bool XF = false>
 cudaError_t launch_bn(const GemmParams& p, cudaStream_t st) {
   using SL = SmemLayout<BN, EW>;
+  if (SL::dyn_bytes(p.n_pad) > SL::max_bytes) return cudaErrorInvalidValue;
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / BN);
   const int slots = g_num_sms * (EW == 8 ? 2 : 1);
   const int grid = tiles < slots ? tiles : slots;
-  return launch_k(gemm_tc_kernel<BN, EW, TRIM, SPLIT>, dim3(grid), dim3(64 + EW * 32), SL::dyn_bytes(p.n_pad), st, p);
+  return launch_k(gemm_tc2_kernel<BN, EW, TRIM, SPLIT, XF>, dim3(grid), dim3(96 + EW * 32 + (XF ? XF_WARPS * 32 : 0)),
+                  SL::dyn_bytes(p.n_pad), st, p);
+}
+
+template <int BN, int EW, bool TRIM = false, bool SPLIT = false, bool XF = false>
+cudaError_t set_smem_attr() {
+  using SL = SmemLayout<BN, EW>;
+  const int want = SL::dyn_bytes(MAX_NPAD);
+  return cudaFuncSetAttribute(gemm_tc2_kernel<BN, EW, TRIM, SPLIT, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              want < SL::max_bytes ? want : SL::max_bytes);
 }
 
 }  // namespace
 
-int gemm_pick_bn(int m_tiles, int n_pad) {
-  if (g_num_sms == 0) return 128;
-  // small problems (a handful of row tiles: batch 1-4): 64-wide tiles put twice as many SMs to work and halve the W bytes
-  // each CTA streams; the main loop of a lone CTA is bound by what one SM can pull from L2 (~0.3 us per 32 KB panel)
-  if (m_tiles * (n_pad / 128) <= g_num_sms / 4 && !getenv("DV_GEMM_NO64")) return 64;
-  // N = 384 (level 2): 2 x 64 tiles of 128 x 128 rows would be 192 tiles = 1.3 waves; 192-wide tiles make it one wave
-  if (n_pad == 384 && m_tiles * 2 <= g_num_sms && !getenv("DV_GEMM_NO192")) return 192;
-  if (n_pad % 256 != 0) return 128;
-  // wide tiles halve the A traffic and the shared-memory bandwidth per FLOP, but only pay when they still fill the GPU
-  return (m_tiles * (n_pad / 256) >= (g_num_sms * 4) / 5) ? 256 : 128;
-}
-
-cudaError_t gemm_tc_init() {
-  {
-    cudaError_t e2 = gemm_tc2_init();
-    if (e2 != cudaSuccess) return e2;
-  }
+cudaError_t gemm_tc2_init() {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -552,55 +678,43 @@ cudaError_t gemm_tc_init() {
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
   }
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<128, 8>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
   {
     const char* ev = getenv("DV_GEMM_EW");
     if (ev) g_force_ew = atoi(ev);
   }
-  e = cudaFuncSetAttribute(gemm_tc_kernel<192, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<192, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<64, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<64, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<256, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemm_tc_kernel<256, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
+  cudaError_t e;
+#define DV_SET(...) if ((e = set_smem_attr<__VA_ARGS__>()) != cudaSuccess) return e;
+  DV_SET(128, 16) DV_SET(128, 8) DV_SET(192, 16) DV_SET(64, 16) DV_SET(256, 16)
+  DV_SET(128, 16, true) DV_SET(256, 16, true)
+  DV_SET(128, 16, false, true) DV_SET(128, 16, true, true)
+  DV_SET(64, 16, false, false, true) DV_SET(128, 16, false, false, true) DV_SET(192, 16, false, false, true)
+  DV_SET(256, 16, false, false, true)
+#undef DV_SET
+  return cudaSuccess;
 }
 
-cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
+cudaError_t launch_gemm_tc2(const GemmParams& p_in, cudaStream_t st) {
   GemmParams p = p_in;
   if (p.out_bs == 0) p.out_bs = static_cast<long long>(p.L) * p.ld_out;
   if (p.trim_col % 32 != 0) return cudaErrorInvalidValue;
   if (g_num_sms == 0) {
-    cudaError_t e = gemm_tc_init();
+    cudaError_t e = gemm_tc2_init();
     if (e != cudaSuccess) return e;
   }
   if (p.n_pad % 128 != 0 || p.n_pad > MAX_NPAD || p.nseg < 1 || p.nseg > GEMM_MAX_SEG) return cudaErrorInvalidValue;
   if (p.out_mode == GEMM_OUT_GEGLU && p.n_pad % 128 != 0) return cudaErrorInvalidValue;
-  // shared conv taps / a GroupNorm fused into the operand path are features of the two-ring kernel (csrc/gemm_tc2.cu)
-  for (int i = 0; i < p.nseg; ++i)
-    if (p.seg[i].ntap != 1 || p.seg[i].xf != 0) return launch_gemm_tc2(p_in, st);
-  for (int i = 0; i < GEMM_MAX_SRC; ++i)
-    if (p.map_rows[i] != 128) return cudaErrorInvalidValue;
+  bool has_xf = false;
+  for (int i = 0; i < p.nseg; ++i) {
+    const GemmSeg& sg = p.seg[i];
+    if (sg.ntap != 1 && sg.ntap != 3) return cudaErrorInvalidValue;
+    if (p.map_rows[sg.src] < (sg.ntap == 3 ? 130 : 128) || p.map_rows[sg.src] > A_ROWS_MAX) return cudaErrorInvalidValue;
+    has_xf |= sg.xf != 0;
+  }
+  if (has_xf && (p.xf.C > XF_MAXC || p.xf.C % (16 * p.xf.G) != 0 || p.xf.G > 32 || p.xf.nst < 1 || p.xf.nst > 2))
+    return cudaErrorInvalidValue;
   const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
   if (p.out_lo != nullptr) {                             // split precision: one tile shape (128 x 128, 16 epilogue warps)
+    if (has_xf) return cudaErrorInvalidValue;            // (the FP32-class mode keeps the stand-alone norm kernels)
     if (p.res != nullptr && p.res_lo == nullptr) return cudaErrorInvalidValue;
     if (p.trim_col > 0 || !dense) {
       if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
@@ -610,32 +724,27 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   }
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
   if (p.trim_col > 0 || !dense) {                        // odd-length folded upsample conv: its own instantiations
-    if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
+    if (p.out_mode != GEMM_OUT_BF16 || has_xf) return cudaErrorInvalidValue;
     if (bn == 256 && p.n_pad % 256 == 0) return launch_bn<256, 16, true>(p, st);
     return launch_bn<128, 16, true>(p, st);
   }
   if (bn == 256) {
     if (p.n_pad % 256 != 0) return cudaErrorInvalidValue;
-    return launch_bn<256, 16>(p, st);
+    return has_xf ? launch_bn<256, 16, false, false, true>(p, st) : launch_bn<256, 16>(p, st);
   }
   if (bn == 192) {
     if (p.n_pad % 192 != 0 || p.out_mode == GEMM_OUT_GEGLU) return cudaErrorInvalidValue;
-    return launch_bn<192, 16>(p, st);
+    return has_xf ? launch_bn<192, 16, false, false, true>(p, st) : launch_bn<192, 16>(p, st);
   }
-  if (bn == 64 && p.out_mode != GEMM_OUT_GEGLU) return launch_bn<64, 16>(p, st);   // GEGLU pairs u / gate inside 128 columns
+  if (bn == 64 && p.out_mode != GEMM_OUT_GEGLU)          // GEGLU pairs u / gate inside 128 columns
+    return has_xf ? launch_bn<64, 16, false, false, true>(p, st) : launch_bn<64, 16>(p, st);
+  if (has_xf) return launch_bn<128, 16, false, false, true>(p, st);
   // two small CTAs per SM pay once there is more than one wave of 128-wide tiles (measured on the C2 shapes: 5-10 %
   // faster at levels 0-2, slower for the few long-K tiles of level 3)
   const int tiles = p.tiles_per_batch * p.B * (p.n_pad / 128);
-  const int ew = g_force_ew ? g_force_ew : (tiles >= g_num_sms + g_num_sms / 8 ? 8 : 16);
+  int ew = g_force_ew ? g_force_ew : (tiles >= g_num_sms + g_num_sms / 8 ? 8 : 16);
+  if (ew == 8 && SmemLayout<128, 8>::dyn_bytes(p.n_pad) > SmemLayout<128, 8>::max_bytes) ew = 16;
   return ew == 8 ? launch_bn<128, 8>(p, st) : launch_bn<128, 16>(p, st);
-}
-
-cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const void* W, int k_tot, cudaStream_t st) {
-  for (int i = 0; i < p.nseg; ++i)
-    if (p.seg[i].xf || p.seg[i].wsel || p.seg[i].src >= 3) return cudaErrorInvalidValue;
-  dim3 grid((p.n_pad + 127) / 128, p.L, p.B);
-  gemm_ref_kernel<<<grid, 128, 0, st>>>(p, srcs[0], srcs[1], srcs[2], reinterpret_cast<const __nv_bfloat16*>(W), k_tot);
-  return cudaGetLastError();
 }
 
 }  // namespace dv

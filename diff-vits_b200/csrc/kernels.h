@@ -34,7 +34,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 // ------------------------------------------------------------------ tap-GEMM (conv1d k3 / 1x1 / linear)
-// out[b, l, n] = epi( sum over K panels  A_seg[b, l + row_off, c0 + 64*p : +64] . W[n, k_run : +64] )
+// out[b, l, n] = epi( sum over segments, panels p, taps t   A_seg[b, l + row_off + t, c0 + 64*p : +64] . W[n, panel(t, p)] )
 // A sources are channel-last bf16 tensors [B, L, C] behind 3-D TMA maps (zero fill outside [0, L) gives the
 // conv padding); W is bf16 [N_pad, K_tot] K-major behind a 2-D TMA map.
 // Precision modes. BF16 (default): activations and weights are single bf16 tensors. SPLIT ("fp32x3"): every bf16 tensor has
@@ -53,13 +53,38 @@ enum GemmOut : int {
   GEMM_OUT_GEGLU = 2,    // tile columns [0,64) = u, [64,128) = gate: out bf16 [B, L, ld_out], N/2 columns
 };
 
+// One K segment = `npanels` 64-channel panels of one source. Every panel is ONE staged activation box ("A slot": rows
+// l0 + row_off ... of the source, TMA zero fill outside [0, L) = the conv padding) that feeds `ntap` MMAs:
+//   ntap = 1 : D += A[rows 0..127] . W[panel]                                   (1x1 conv / Linear / one conv tap)
+//   ntap = 3 : conv k3 with SHARED rows: the box holds 136 rows starting at l0 - 1 and tap t reads rows t .. t+127 through
+//              a row-shifted UMMA descriptor (+128 B per row; profiles/r2b_umma_row_shift_probe.txt) against
+//              W[wk0 + t * tap_stride + panel]: the activation tile is loaded (and transformed) once instead of three times.
+// xf != 0: the box is normalised IN SHARED MEMORY before the MMA reads it (GemmXf below): GroupNorm (+scale/shift, +SiLU)
+// of the resnet blocks / transformer input fused into the consuming conv instead of a stand-alone pass over HBM.
 struct GemmSeg {
-  int16_t src;      // index into mapA
-  int16_t row_off;  // row offset added to the tile's first row (-1, 0, +1 for the three conv taps)
-  int16_t c0;       // first channel of the segment in the source tensor
-  int16_t npanels;  // number of 64-channel panels
-  int16_t wsel;     // weight matrix: 0 = mapW (hi plane), 1 = mapW2 (lo plane)
-  int16_t wk0;      // first 64-wide K panel of the segment inside that weight matrix
+  int16_t src;         // index into mapA
+  int16_t row_off;     // first row of the A slot relative to the tile's first output row (-1 for ntap = 3)
+  int16_t c0;          // first channel of the segment in the source tensor
+  int16_t npanels;     // number of 64-channel panels
+  int16_t wsel;        // weight matrix: 0 = mapW (hi plane), 1 = mapW2 (lo plane, split precision)
+  int16_t wk0;         // 64-wide K panel of (tap 0, panel 0) inside that weight matrix
+  int16_t ntap;        // 1 or 3
+  int16_t tap_stride;  // K panels between consecutive taps of the same channel panel
+  int16_t xf;          // 0 = operand as loaded, 1 = GroupNorm affine (+SiLU) applied in shared memory
+  int16_t xf_c0;       // channel of c0 inside the normalised (possibly concatenated) tensor: coefficient index
+};
+
+// GroupNorm fused into the consumer (xf segments): y = SiLU?( ((x - mean_g) rstd_g gamma_c + beta_c) (1 + scale[b,c]) + shift[b,c] ),
+// statistics from the producers' epilogue partials (same layout / reduction order as gn_apply, csrc/norm.cu).
+struct GemmXf {
+  const float* st_ptr[2];            // partial statistics of the (up to two) sources of the normalised tensor
+  int st_chunks[2], st_nblk[2], st_fold[2], st_cover[2];
+  int nst;
+  int C, L, G;                       // channels of the normalised tensor, rows per batch item, groups
+  float eps;
+  int silu;
+  const float* gamma; const float* beta;      // [C]
+  const float* scale_shift; int ss_ld;        // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + C + c]
 };
 
 struct alignas(64) GemmParams {
@@ -68,6 +93,8 @@ struct alignas(64) GemmParams {
   CUtensorMap mapW2;    // split precision: lo plane of the weights (aliases mapW otherwise)
   GemmSeg seg[GEMM_MAX_SEG];
   int nseg;
+  int16_t map_rows[GEMM_MAX_SRC];   // rows of the TMA box of each A map (128, or 136 for sources read with shared taps)
+  GemmXf xf;                        // used when any segment has xf != 0
   int B, L, N;          // L = output rows per batch item, N = real output columns
   int n_pad;            // N rounded up to the N tile
   int tiles_per_batch;  // ceil(L / 128)
@@ -91,7 +118,9 @@ struct alignas(64) GemmParams {
 
 cudaError_t gemm_tc_init();                       // query the device, set kernel attributes (call outside graph capture)
 int gemm_pick_bn(int m_tiles, int n_pad);
-cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st);
+cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st);   // dispatches to launch_gemm_tc2 for shared taps / fused norms
+cudaError_t gemm_tc2_init();
+cudaError_t launch_gemm_tc2(const GemmParams& p, cudaStream_t st);  // two-ring kernel (csrc/gemm_tc2.cu)
 // Debug/reference implementation of exactly the same contract on CUDA cores (plain loads, fp32 FMA).
 // Used by tests to cross-check the tcgen05 kernel; never used by the engine.
 struct GemmRefSrc { const void* ptr; int L, C, ld; };

@@ -146,13 +146,25 @@ DV_API int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_onl
 /* bf16 rows of `ld` elements, `L` rows visible per batch item (rows outside [0, L) read as zero), `C` channels used,
  * `bs` elements between batch items (0 = L * ld) */
 typedef struct dv_gemm_src { const void* ptr; int L; int C; int ld; long long bs; } dv_gemm_src;
-typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; } dv_gemm_seg;
+/* One K segment: `npanels` 64-channel panels of source `src` starting at channel c0. ntap = 1 (or 0): rows l + row_off.
+ * ntap = 3: conv k3 with shared rows - row_off is the first tap's offset (-1) and tap t reads rows l + row_off + t from the
+ * same staged box. wk0 = first 64-wide K panel of (tap 0, panel 0) in `w` (< 0: the running K position), tap_stride = K panels
+ * between taps (0: npanels). xf = 1: the segment's rows are GroupNorm-normalised in shared memory on the way to the tensor
+ * core (dv_gemm_opts.norm), xf_c0 = channel of c0 inside the normalised tensor. */
+typedef struct dv_gemm_seg { int src; int row_off; int c0; int npanels; int ntap; int wk0; int tap_stride; int xf; int xf_c0; } dv_gemm_seg;
+/* GroupNorm fused into the consuming GEMM (nn.GroupNorm + SiLU + (1+scale)*x+shift, resnet.py:591-631): statistics as
+ * partial sums [B][chunks][nblk][2] per source (what dv_groupnorm's scratch / the GEMM epilogue hold). */
+typedef struct dv_gemm_norm {
+  const float* stats[2]; int chunks[2]; int nblk[2]; int fold[2]; int cover[2]; int nst;
+  int C; int L; int G; float eps; int silu;
+  const float* gamma; const float* beta; const float* scale_shift; int ss_ld;
+} dv_gemm_norm;
 /* Optional per-call settings of dv_gemm (NULL = defaults): bn = force the N tile (64 / 128 / 192 / 256, 0 = heuristic);
  * stats != NULL = the epilogue also emits GroupNorm partial sums [B][ceil(L/128)*4][n/16][2] of the stored tensor (what
  * the engine's GroupNorm consumes instead of re-reading it); out_bs = elements between batch items of `out` (0 = dense
  * L_out * ld_out); trim_col > 0 = columns >= trim_col of the last row are neither stored nor counted in the partials.
  * out_bs + trim_col are how the folded nearest-resize conv writes 2L - 1 rows (resnet.py:138-173). */
-typedef struct dv_gemm_opts { int bn; float* stats; long long out_bs; int trim_col; } dv_gemm_opts;
+typedef struct dv_gemm_opts { int bn; float* stats; long long out_bs; int trim_col; const dv_gemm_norm* norm; } dv_gemm_opts;
 /* out_mode: 0 bf16 NTC, 1 fp32 NCT, 2 GEGLU bf16. impl: 0 = tcgen05 kernel, 1 = CUDA-core reference (writes raw
  * fp32 [B, L, n_pad] accumulators + bias into `out`). Replaces F.conv1d (unet1d/lora.py:102) / nn.Linear. */
 DV_API int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,

@@ -111,6 +111,95 @@ def test_gemm_conv3(U, B, L, Cin, Cout):
     _check_bf16(U, got, ref)
 
 
+@pytest.mark.parametrize("B,L,Cin,Cout,bn", [(2, 257, 128, 128, 0), (1, 200, 256, 384, 192), (2, 1000, 384, 128, 64),
+                                             (2, 26, 512, 512, 256), (40, 1000, 128, 128, 0), (1, 1, 64, 128, 0)])
+def test_gemm_conv3_shared_taps(U, B, L, Cin, Cout, bn):
+    """conv1d k3 s1 p1 with ONE staged 136-row box per channel panel and three row-shifted tensor-core reads
+    (profiles/r2b_umma_row_shift_probe.txt) instead of three loads: same contract as three single-tap segments."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = _rand((B, L, Cin), g)
+    w = (torch.randn(Cout, Cin, 3, generator=g, device="cuda") * (3 * Cin) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g, device="cuda")
+    res = _rand((B, L, Cout), g)
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=1).transpose(1, 2) + res.float()
+    wp = w.permute(0, 2, 1).reshape(Cout, 3 * Cin).contiguous()
+    got, st = U.gemm([x], [(0, -1, 0, Cin, 3)], wp, Cout, bias=bias, res=res, bn=bn, stats=True)
+    _check_bf16(U, got, ref)
+    three, st3 = U.gemm([x], [(0, -1, 0, Cin), (0, 0, 0, Cin), (0, 1, 0, Cin)], wp, Cout, bias=bias, res=res, bn=bn, stats=True)
+    assert U.rel_l2(got.float(), three.float()) < 2e-3          # same products, different accumulation order
+    assert U.rel_l2(st, st3) < 1e-3
+
+
+@pytest.mark.parametrize("B,L,C0,C1,N,silu,ss,bn", [(3, 250, 256, 128, 256, True, False, 0), (2, 1000, 128, 0, 128, True, True, 0),
+                                                     (33, 500, 256, 0, 256, True, True, 256), (2, 125, 512, 384, 384, True, False, 192),
+                                                     (2, 26, 512, 512, 512, True, True, 0), (1, 7, 128, 0, 128, False, False, 64)])
+def test_gemm_conv3_with_fused_groupnorm(U, B, L, C0, C1, N, silu, ss, bn):
+    """GroupNorm (+ time scale/shift, + SiLU) of the conv's input applied in shared memory between the TMA load and the
+    MMA (resnet.py:596-600, 625-631 then conv1 / conv2): the normalised tensor is never written. Two sources = the
+    never-materialised torch.cat([h, skip]) with groups that straddle the seam. Reference: torch GroupNorm on the
+    concatenated tensor, operand rounded to bf16 as the kernel stores it, fp32 conv."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    Cc, G = C0 + C1, 8
+    x0 = _rand((B, L, C0), g, 1.7) + 0.3
+    x1 = (_rand((B, L, C1), g, 0.6) - 0.2) if C1 else None
+    gamma = torch.randn(Cc, generator=g, device="cuda") * 0.3 + 1.0
+    beta = torch.randn(Cc, generator=g, device="cuda") * 0.2
+    ssv = (torch.randn(B, 2 * Cc, generator=g, device="cuda") * 0.3) if ss else None
+    w = (torch.randn(N, Cc, 3, generator=g, device="cuda") * (3 * Cc) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    xc = x0.float() if x1 is None else torch.cat([x0, x1], 2).float()
+    y = F.group_norm(xc.transpose(1, 2), G, gamma, beta, 1e-5)
+    if ss:
+        y = y * (1 + ssv[:, :Cc, None]) + ssv[:, Cc:, None]
+    if silu:
+        y = F.silu(y)
+    y = y.to(torch.bfloat16).float()
+    ref = F.conv1d(y, w.float(), bias, padding=1).transpose(1, 2)
+    wp = w.permute(0, 2, 1).reshape(N, 3 * Cc).contiguous()
+    np_ = Cc // 64
+    srcs = [x0] + ([x1] if C1 else [])
+    segs = [(0, -1, 0, C0, 3, 0, np_, 1, 0)] + ([(1, -1, 0, C1, 3, C0 // 64, np_, 1, C0)] if C1 else [])
+    norm = dict(stats=[U.gn_partials(t) for t in srcs], cover=[t.shape[2] for t in srcs], C=Cc, L=L, G=G, eps=1e-5,
+                silu=silu, gamma=gamma, beta=beta, scale_shift=ssv)
+    got = U.gemm(srcs, segs, wp, N, bias=bias, bn=bn, norm=norm)
+    _check_bf16(U, got, ref)
+    # the stand-alone GroupNorm kernel + plain conv give the same operand: results agree to accumulation order
+    a = U.groupnorm(x0, x1, G, gamma, beta, 1e-5, silu, ssv)
+    unf = U.gemm([a], [(0, -1, 0, Cc, 3)], wp, N, bias=bias, bn=bn)
+    assert U.rel_l2(got.float(), unf.float()) < 2e-3
+
+
+@pytest.mark.parametrize("B", [2, 40])
+def test_gemm_linear_with_fused_groupnorm_and_raw_shortcut(U, B):
+    """1x1 GEMM whose operand is GroupNorm(x) without SiLU (transformer_1d.py:256-258 norm + proj_in), and a conv whose
+    normalised operand shares the launch with RAW shortcut sources (resnet conv2 + conv_shortcut over (h | skip)).
+    B = 40: several tiles per persistent CTA, more raw panels per tile than A slots (the normalised and the raw panels
+    complete different barriers of a slot; a transform warp that lost step with the ring would trap here)."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    L, Cc, N, G = 500, 256, 256, 8
+    x = _rand((B, L, Cc), g, 2.0)
+    gamma, beta = torch.randn(Cc, generator=g, device="cuda") * 0.2 + 1, torch.randn(Cc, generator=g, device="cuda") * 0.1
+    w = _rand((N, Cc), g, Cc ** -0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    y = F.group_norm(x.float().transpose(1, 2), G, gamma, beta, 1e-6).to(torch.bfloat16).float().transpose(1, 2)
+    norm = dict(stats=[U.gn_partials(x)], cover=[Cc], C=Cc, L=L, G=G, eps=1e-6, silu=False, gamma=gamma, beta=beta)
+    got = U.gemm([x], [(0, 0, 0, Cc, 1, -1, 0, 1, 0)], w, N, bias=bias, norm=norm)
+    _check_bf16(U, got, y @ w.float().t() + bias)
+    # conv2(SiLU(GN(u))) + shortcut(h | s): segments u (normalised, shared taps), h, s (raw)
+    C1, C2 = 256, 128
+    u, h, s2 = _rand((B, L, Cc), g, 1.5), _rand((B, L, C1), g), _rand((B, L, C2), g)
+    w2 = (torch.randn(N, Cc, 3, generator=g, device="cuda") * (3 * Cc) ** -0.5).to(torch.bfloat16)
+    wsc = (torch.randn(N, C1 + C2, 1, generator=g, device="cuda") * (C1 + C2) ** -0.5).to(torch.bfloat16)
+    v = F.silu(F.group_norm(u.float().transpose(1, 2), G, gamma, beta, 1e-5)).to(torch.bfloat16).float()
+    ref = (F.conv1d(v, w2.float(), None, padding=1)
+           + F.conv1d(torch.cat([h, s2], 2).float().transpose(1, 2), wsc.float(), bias)).transpose(1, 2)
+    wp = torch.cat([w2.permute(0, 2, 1).reshape(N, 3 * Cc), wsc[:, :, 0]], dim=1).contiguous()
+    segs = [(0, -1, 0, Cc, 3, 0, Cc // 64, 1, 0), (1, 0, 0, C1), (2, 0, 0, C2)]
+    norm = dict(stats=[U.gn_partials(u)], cover=[Cc], C=Cc, L=L, G=G, eps=1e-5, silu=True, gamma=gamma, beta=beta)
+    got = U.gemm([u, h, s2], segs, wp, N, bias=bias, norm=norm)
+    _check_bf16(U, got, ref)
+
+
 def test_gemm_conv3_with_fused_shortcut_two_sources(U):
     """conv2 + 1x1 shortcut over torch.cat([h, skip]) as extra K panels from two tensors (resnet.py:634-639)."""
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -374,3 +374,17 @@ def test_sharded_sampling_equals_single_process():
     assert torch.equal(full, want)
     from diffvits_b200.dist import shard_slice
     assert [shard_slice(5, r, 2) for r in range(2)] == [slice(0, 3), slice(3, 5)]
+
+
+def test_serving_front_buckets_requests_faithfully():
+    """Host logic of the batched front (diff-vits_b200/serving.py; reference: tts_infer.py:46-74 is batch 1): requests
+    share a batch only with requests of exactly the same frame count; prompts are padded to 64-row buckets; order kept."""
+    from diffvits_b200.serving import plan_batches, prompt_bucket
+    assert [prompt_bucket(t) for t in (1, 64, 65, 282)] == [64, 64, 128, 320]
+    shapes = [(200, 282), (136, 40), (200, 300), (136, 64), (200, 282), (136, 65), (200, 257)]
+    plan = plan_batches(shapes, max_batch=2)
+    assert plan == [((136, 64), [1, 3]), ((136, 128), [5]), ((200, 320), [0, 2]), ((200, 320), [4, 6])]
+    seen = sorted(i for _, idx in plan for i in idx)
+    assert seen == list(range(len(shapes)))
+    for (T, Tp), idx in plan:
+        assert all(shapes[i][0] == T and shapes[i][1] <= Tp for i in idx) and len(idx) <= 2

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--Tp", type=int, default=282)
     ap.add_argument("--only", default="gemm,attn,gn,ln,samp")
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--taps3", action="store_true", help="conv k3 as three single-tap segments (three A loads per panel)")
     a = ap.parse_args()
     only = set(a.only.split(","))
     lib = _lib.load()
@@ -83,8 +84,13 @@ def main():
                 res = rnd(B, L, N) if withres else None
                 out = torch.zeros(B, L, N // 2 if mode == 2 else N, dtype=torch.bfloat16, device="cuda")
                 S = (GemmSrc * 1)(GemmSrc(src.data_ptr(), L, K1, K1))
-                segs = [(0, t - 1, 0, K1) for t in range(3)] if taps == 3 else [(0, 0, 0, K1)]
-                G = (GemmSeg * len(segs))(*[GemmSeg(s, ro, c0, ch // 64) for (s, ro, c0, ch) in segs])
+                # conv k3: one staged 136-row box read by three row-shifted descriptors (default), or three loads (--taps3)
+                if taps == 3 and not a.taps3:
+                    G = (GemmSeg * 1)(GemmSeg(0, -1, 0, K1 // 64, 3))
+                    segs = [None]
+                else:
+                    segs = [(0, t - 1, 0, K1) for t in range(3)] if taps == 3 else [(0, 0, 0, K1)]
+                    G = (GemmSeg * len(segs))(*[GemmSeg(s, ro, c0, ch // 64) for (s, ro, c0, ch) in segs])
                 stt = torch.zeros(B, (L + 127) // 128 * 4, N // 16, 2, device="cuda") if stats else None
                 for bn in (64, 128, 192, 256):
                     if N % bn or (bn == 192 and (N != 384 or mode == 2)) or (bn == 64 and (mode == 2 or B * L > 4096)):
