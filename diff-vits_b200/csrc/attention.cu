@@ -482,18 +482,24 @@ cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st) {
   }
 }
 
-// Dispatch. Both kernels implement the same contract and both are parity-tested at every head dim. Which one runs
-// is a measured choice (B200, C2, profiles/r1e_attention_ab.txt): stand-alone the tcgen05 kernel wins for d >= 32
-// (L1-L3: 37 vs 41, 15.7 vs 18.7, 6.5 vs 8.7 us) and loses at d = 16 (117 vs 100 us: both are bound by the MUFU pipe
-// and per-tile latency, and the register-resident mma.sync kernel has 8+ CTAs of TLP per SM); inside the captured
-// step loop its heavier CTA prologue (TMEM allocation, barrier init) overlaps less with the neighbouring kernels and
-// the whole step is not faster (219.8 vs 217.7 ms), so the mma.sync kernel stays the default for every head dim.
-// DV_ATTN=tc|legacy forces one kernel.
+// Dispatch. The kernels implement the same contract and all are parity-tested at every head dim. Which one runs is a
+// measured choice (B200, profiles/r2e_attention_dispatch.txt): the tcgen05 kernel (TMEM accumulators, TMA-fed operands,
+// csrc/attention_tc.cu) is the default for head dims >= 32 (levels 1-3: 22 of the 32 attention launches of a call; stand-alone
+// 37 vs 41, 15.7 vs 18.7, 6.5 vs 8.7 us; C2 step 201.6 vs 202.4 ms, C5 step 150.6 vs 156.3 ms); at d = 16 (level 0) a score
+// costs 64 FLOP per exponential, both kernels are bound by the MUFU pipe and per-tile latency, and the register-resident
+// mma.sync kernel with 8+ CTAs of TLP per SM is faster (100 vs 117 us; C2 step 210.9 ms with tcgen05 everywhere).
+// DV_ATTN=tc|legacy forces one kernel, DV_ATTN_TC_MIN_D moves the threshold.
+constexpr int kTcMinD = 32;        // measured choice, see profiles/r2e_attention_dispatch.txt
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
   if (p.q_lo != nullptr) return launch_attention_split(p, st);     // FP32-class precision mode (hi + lo planes)
   // read per launch (launches are captured into a graph on the hot path): tests flip it between calls
   const char* e = getenv("DV_ATTN");
   if (e && e[0] == 't') return launch_attention_tc(p, st);          // tcgen05 kernel
+  {
+    // head dims from which the tcgen05 kernel is the default (it wins stand-alone for d >= 32; DV_ATTN_TC_MIN_D overrides)
+    static const int tc_min_d = [] { const char* m = getenv("DV_ATTN_TC_MIN_D"); return m ? atoi(m) : kTcMinD; }();
+    if (!(e && e[0] == 'l') && p.D >= tc_min_d) return launch_attention_tc(p, st);
+  }
   if (e && e[0] == 'l') return launch_attention_legacy(p, st);      // first mma.sync kernel
   if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
   const char* pj = getenv("DV_ATTN_POLY");                          // accumulator columns (of 8) on the FMA-pipe exp2
