@@ -38,6 +38,11 @@ class UnetCfg(C.Structure):
     ]
 
 
+class PromptCfg(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("hidden", C.c_int), ("n_layers", C.c_int), ("num_heads", C.c_int),
+                ("ffn_kernel", C.c_int), ("ffn_mult", C.c_int)]
+
+
 class GemmSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("L", C.c_int), ("C", C.c_int), ("ld", C.c_int), ("bs", C.c_longlong)]
 
@@ -80,6 +85,13 @@ SIGNATURES = {
     "dv_unet_forward": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dv_sample": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _i, _vp]),
     "dv_sample_group": (_i, [C.POINTER(_vp), _i, _i, _i, C.POINTER(_f), C.POINTER(_f), C.POINTER(_vp), _i, _vp]),
+    "dv_prompt_plan_create": (_i, [C.POINTER(PromptCfg), _i, _i, C.POINTER(_vp)]),
+    "dv_prompt_plan_destroy": (None, [_vp]),
+    "dv_prompt_plan_workspace_bytes": (_sz, [_vp]),
+    "dv_prompt_plan_param_bytes": (_sz, [_vp]),
+    "dv_prompt_plan_manifest_json": (C.c_char_p, [_vp]),
+    "dv_prompt_plan_bind": (_i, [_vp, _vp, _vp, _vp]),
+    "dv_prompt_encode": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "dv_plan_tensor_count": (_i, [_vp]),
     "dv_plan_tensor_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),
     "dv_plan_op_count": (_i, [_vp]),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 DEBUG = os.environ.get("DV_DEBUG", "0") == "1"
 BUILD = os.path.join(HERE, "build_dbg" if DEBUG else "build")
 LIB = os.path.join(HERE, "libdiffvits_b200_dbg.so" if DEBUG else "libdiffvits_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu", "elementwise.cu", "engine.cu", "api.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu", "elementwise.cu", "engine.cu", "prompt_encoder.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -180,6 +180,57 @@ int dv_plan_profile_forward(dv_plan* plan, const float* sample, int x_only, cons
   return rc == DV_OK ? rc : fail(rc, err);
 }
 
+// ------------------------------------------------------------------------------------------ prompt encoder
+}  // extern "C"
+struct dv_prompt_plan {
+  dv::PromptPlan impl;
+};
+extern "C" {
+int dv_prompt_plan_create(const dv_prompt_cfg* cfg, int B, int Tp, dv_prompt_plan** out) {
+  if (!cfg || !out) return fail(DV_ERR_INVALID, "null argument");
+  dv_prompt_plan* p = new (std::nothrow) dv_prompt_plan();
+  if (!p) return fail(DV_ERR_INVALID, "out of host memory");
+  p->impl.cfg = *cfg;
+  p->impl.B = B; p->impl.Tp = Tp;
+  std::string err;
+  int rc = p->impl.build(err);
+  if (rc != DV_OK) {
+    delete p;
+    return fail(rc, err);
+  }
+  *out = p;
+  return DV_OK;
+}
+void dv_prompt_plan_destroy(dv_prompt_plan* plan) { delete plan; }
+size_t dv_prompt_plan_workspace_bytes(const dv_prompt_plan* plan) { return plan ? plan->impl.ws_bytes : 0; }
+size_t dv_prompt_plan_param_bytes(const dv_prompt_plan* plan) { return plan ? plan->impl.param_bytes : 0; }
+const char* dv_prompt_plan_manifest_json(const dv_prompt_plan* plan) { return plan ? plan->impl.manifest.c_str() : ""; }
+int dv_prompt_plan_bind(dv_prompt_plan* plan, void* workspace, const void* params, void* stream) {
+  if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  {
+    cudaPointerAttributes at;
+    cudaError_t pe = cudaPointerGetAttributes(&at, workspace);
+    if (pe != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+      cudaGetLastError();
+      return fail(DV_ERR_INVALID, "workspace is not a device allocation");
+    }
+    plan->impl.device = at.device;
+  }
+  DevGuard guard(plan->impl.device);
+  int rc = require_device();
+  if (rc != DV_OK) return rc;
+  std::string err;
+  rc = plan->impl.bind(workspace, params, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+int dv_prompt_encode(dv_prompt_plan* plan, const float* prompt, const int32_t* lengths, float* ehs_out, void* stream) {
+  if (!plan) return fail(DV_ERR_INVALID, "null plan");
+  DevGuard guard(plan->impl.device);
+  std::string err;
+  int rc = plan->impl.encode(prompt, lengths, ehs_out, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+
 // ------------------------------------------------------------------------------------------ single kernels
 #ifdef DV_DEBUG_HOOKS
 // Debug library only (include/diffvits_b200_debug.h): timing ablations and CTA timelines.

@@ -582,6 +582,23 @@ std::string json_escape(const std::string& s) { return s; }  // keys are [A-Za-z
 
 }  // namespace
 
+std::string manifest_json(const std::vector<ParamSlot>& slots) {
+  std::ostringstream js;
+  js << "[";
+  for (size_t i = 0; i < slots.size(); ++i) {
+    const ParamSlot& s = slots[i];
+    if (i) js << ",";
+    js << "{\"name\":\"" << json_escape(s.name) << "\",\"recipe\":\"" << s.recipe << "\",\"dtype\":\"" << s.dtype
+       << "\",\"offset\":" << s.off << ",\"nbytes\":" << s.bytes << ",\"shape\":[";
+    for (size_t k = 0; k < s.shape.size(); ++k) js << (k ? "," : "") << s.shape[k];
+    js << "],\"keys\":[";
+    for (size_t k = 0; k < s.keys.size(); ++k) js << (k ? "," : "") << "\"" << json_escape(s.keys[k]) << "\"";
+    js << "]}";
+  }
+  js << "]";
+  return js.str();
+}
+
 int Plan::build(std::string& err) {
   const dv_unet_cfg& c = cfg;
   n_levels = c.n_levels;
@@ -788,20 +805,7 @@ int Plan::build(std::string& err) {
   }
 
   // ---- manifest
-  std::ostringstream js;
-  js << "[";
-  for (size_t i = 0; i < slots.size(); ++i) {
-    const ParamSlot& s = slots[i];
-    if (i) js << ",";
-    js << "{\"name\":\"" << json_escape(s.name) << "\",\"recipe\":\"" << s.recipe << "\",\"dtype\":\"" << s.dtype
-       << "\",\"offset\":" << s.off << ",\"nbytes\":" << s.bytes << ",\"shape\":[";
-    for (size_t k = 0; k < s.shape.size(); ++k) js << (k ? "," : "") << s.shape[k];
-    js << "],\"keys\":[";
-    for (size_t k = 0; k < s.keys.size(); ++k) js << (k ? "," : "") << "\"" << json_escape(s.keys[k]) << "\"";
-    js << "]}";
-  }
-  js << "]";
-  manifest = js.str();
+  manifest = manifest_json(slots);
   param_bytes = align_up(param_bytes, 256);
   return DV_OK;
 }

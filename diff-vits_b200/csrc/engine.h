@@ -173,6 +173,37 @@ struct Plan {
 int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float* t_in, const float* coef,
                  float* const* x, int flags, cudaStream_t st, std::string& err);
 
+std::string manifest_json(const std::vector<ParamSlot>& slots);
+
+// PromptEncoder (model3.py:382-433): the speech-prompt encoder that produces encoder_hidden_states, as a plan of the same
+// kernels (csrc/prompt_encoder.cu). Channel-last [B, Tp, 128] throughout = the layout the UNet's cross-attention reads.
+struct PromptPlan {
+  dv_prompt_cfg cfg;
+  int B = 0, Tp = 0, device = -1;
+  std::vector<ParamSlot> slots;
+  std::string manifest;
+  size_t param_bytes = 0, ws_bytes = 0;
+  uint8_t* ws = nullptr;
+  const uint8_t* params = nullptr;
+  bool bound = false;
+  struct Step {
+    int kind = 0;                   // 0 GEMM, 1 LayerNorm (masked variant), 2 attention
+    GemmParams gp; AttnParams at;
+    size_t x = 0, out = 0; long long gamma = -1, beta = -1; LnMaskParams ln;
+    bool ln_f32 = false;
+    // GEMM description resolved at bind
+    size_t a_off = 0; int a_c = 0; int nseg = 0; int row_off[9] = {0}; long long w_off = -1, b_off = -1; int k_tot = 0, n = 0;
+    size_t res_off = 0; bool has_res = false, relu = false, mask_rows = false;
+    size_t q = 0, k = 0, v = 0, o = 0;
+    std::string tag;
+  };
+  std::vector<Step> steps;
+  size_t off_xin = 0, off_len = 0, off_out32 = 0;
+  int build(std::string& err);
+  int bind(void* workspace, const void* params, cudaStream_t st, std::string& err);
+  int encode(const float* prompt, const int32_t* lengths, float* ehs_out, cudaStream_t st, std::string& err);
+};
+
 bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
                   std::string& err, int box_rows = 128);
 bool make_tmap_2d(CUtensorMap* m, const void* base, int k_tot, int rows, int box_rows, std::string& err);

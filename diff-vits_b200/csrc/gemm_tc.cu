@@ -129,6 +129,8 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
   }
   uint32_t packed[16];
   uint32_t packed_lo[SPLIT ? 16 : 1];
+  // this thread's accumulator row is l = lq + lane of batch item rowbase / L: masked rows are stored as zeros
+  const bool row_keep = p.row_len == nullptr || (lq + e.lane) < __ldg(p.row_len + rowbase / p.L);
   float2 s0 = make_float2(0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {                      // 4 columns per iteration: one broadcast LDS.128 of bias
@@ -141,6 +143,8 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
       v = add_f32x2(v, h ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y));
       if (HAS_RES) v = add_f32x2(v, make_float2(bf16_lo(rr[j >> 1]), bf16_hi(rr[j >> 1])));
       if (HAS_RES && SPLIT) v = add_f32x2(v, make_float2(bf16_lo(rrl[j >> 1]), bf16_hi(rrl[j >> 1])));
+      if (p.relu) v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+      if (!row_keep) v = make_float2(0.f, 0.f);
       packed[j >> 1] = pack_bf16(v.x, v.y);
       if (SPLIT) packed_lo[j >> 1] = pack_bf16(v.x - bf16_lo(packed[j >> 1]), v.y - bf16_hi(packed[j >> 1]));
       if (HAS_STATS) {

@@ -43,7 +43,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 // segment, over two A maps (hi / lo plane) and two W maps. Epilogues write both planes; norms, layout kernels and the
 // attention core read hi + lo and write both planes.
 constexpr int GEMM_MAX_LSRC = 3;                   // logical sources (torch.cat inputs / pair views)
-constexpr int GEMM_MAX_LSEG = 6;                   // logical K segments (conv taps, shortcut sources)
+constexpr int GEMM_MAX_LSEG = 9;                   // logical K segments (conv taps, shortcut sources; 9-tap conv-FFN of the prompt encoder)
 constexpr int GEMM_MAX_SRC = 2 * GEMM_MAX_LSRC;    // maps in the kernel parameters (hi and lo plane of each source)
 constexpr int GEMM_MAX_SEG = 3 * GEMM_MAX_LSEG;
 
@@ -109,6 +109,9 @@ struct alignas(64) GemmParams {
   long long out_bs;     // GEMM_OUT_BF16: elements between batch items of `out` (0 = L * ld_out, dense)
   int trim_col;         // GEMM_OUT_BF16: if > 0, columns >= trim_col of the LAST row (l = L - 1) are neither stored nor counted in
                         // the GroupNorm partials (odd-length nearest-2x upsample: that half row does not exist)
+  int relu;             // GEMM_OUT_BF16: max(v, 0) before the store (conv-FFN of the prompt encoder, operations.py:689)
+  const int* row_len;   // GEMM_OUT_BF16: optional [B] valid rows per batch item; rows >= row_len[b] are stored as zeros
+                        // (the reference's `x * (1 - padding_mask)`, operations.py:813, 820; model3.py:421-431)
   float* stats;         // optional GroupNorm partials of the stored tensor: [B][tiles_per_batch*4][stats_nblk][2]
   int stats_nblk;       // 16-channel blocks per row chunk (= N / 16)
   int bn;               // N tile (128 / 256); 0 = choose
@@ -225,6 +228,13 @@ cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st);
 // x_lo / out_lo: lo planes in split precision (both null otherwise)
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
                              float eps, cudaStream_t st, const void* x_lo = nullptr, void* out_lo = nullptr);
+// LayerNorm variants of the prompt encoder (C = 128 columns stored, statistics over the first c_real of them; the rest
+// of the output row is zero): rows >= row_len[row / rows_per_batch] read as zeros when mask_in (masked_fill before the
+// norm, model.py:95-97) and are written as zeros when mask_out (x * (1 - mask) after it, model3.py:429-431);
+// out_f32 != nullptr: the result also goes there in fp32.
+struct LnMaskParams { const int* row_len; int rows_per_batch; int c_real; int mask_in; int mask_out; float* out_f32; };
+cudaError_t launch_layernorm_masked(const void* x, void* out, const float* gamma, const float* beta, int rows, float eps,
+                                    const LnMaskParams& m, cudaStream_t st);
 
 // ------------------------------------------------------------------ elementwise / small
 // [B, Csrc, T] fp32 -> channel-last bf16 [B, T, ld_dst]; channel c goes to column c + (c >= split ? shift : 0).

@@ -302,7 +302,62 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
+// LayerNorm over the first c_real of 128 stored columns with row masks (prompt encoder: LN(100) in front of `pre`, the
+// final LayerNorm with zeroed padding rows). One warp per row.
+__global__ void __launch_bounds__(256) layernorm_masked_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               int rows, float eps, LnMaskParams m) {
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  float g[4], bt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane * 4 + j;
+    g[j] = c < m.c_real ? __ldg(gamma + c) : 0.f;
+    bt[j] = c < m.c_real ? __ldg(beta + c) : 0.f;
+  }
+  pdl_wait();
+  if (row >= rows) return;
+  const bool padded = m.row_len != nullptr && (row % m.rows_per_batch) >= __ldg(m.row_len + row / m.rows_per_batch);
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!(padded && m.mask_in)) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(x + static_cast<size_t>(row) * 128) + lane);
+    v[0] = bf16_lo(w.x); v[1] = bf16_hi(w.x); v[2] = bf16_lo(w.y); v[3] = bf16_hi(w.y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { if (lane * 4 + j >= m.c_real) v[j] = 0.f; s += v[j]; }
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  const float mean = s / m.c_real;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float d = lane * 4 + j < m.c_real ? v[j] - mean : 0.f; q += d * d; }
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
+  const float rstd = rsqrtf(q / m.c_real + eps);
+  float y[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    y[j] = lane * 4 + j < m.c_real ? (v[j] - mean) * rstd * g[j] + bt[j] : 0.f;
+    if (padded && m.mask_out) y[j] = 0.f;
+  }
+  uint2 o;
+  o.x = pack_bf16(y[0], y[1]);
+  o.y = pack_bf16(y[2], y[3]);
+  reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * 128)[lane] = o;
+  if (m.out_f32) reinterpret_cast<float4*>(m.out_f32 + static_cast<size_t>(row) * 128)[lane] = make_float4(y[0], y[1], y[2], y[3]);
+}
+
 }  // namespace
+
+cudaError_t launch_layernorm_masked(const void* x, void* out, const float* gamma, const float* beta, int rows, float eps,
+                                    const LnMaskParams& m, cudaStream_t st) {
+  if (m.c_real < 1 || m.c_real > 128 || rows < 1 || (m.row_len && m.rows_per_batch < 1)) return cudaErrorInvalidValue;
+  return launch_k(layernorm_masked_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x),
+                  reinterpret_cast<__nv_bfloat16*>(out), gamma, beta, rows, eps, m);
+}
 
 static bool gn_ok(const GnParams& p) {
   const int C = p.c0 + p.c1;

@@ -103,6 +103,16 @@ def pack_slot(slot: dict, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
         else:
             even, odd = torch.cat([w0, w1, w2, z], dim=1), torch.cat([z, w0 + w1, z, w2], dim=1)
         out = _pad_rows(torch.cat([even, odd], dim=0), shape[0])
+    elif rec in ("convtbc1", "convtbc1_pad"):
+        # ConvTBC k = 1 (model.py:60-70): weight [1, c_in, c_out] -> Linear layout [c_out, c_in], K zero-padded to the slot
+        m = w[0][0].t().contiguous()
+        out = m.new_zeros(shape[0], shape[1])
+        out[: m.shape[0], : m.shape[1]] = m
+    elif rec == "ffn_taps":
+        # 9-tap conv feed-forward (operations.py:659-684): K = [tap 0 | ... | tap 8], the reference's kernel_size^-1/2 folded in
+        out = _pad_rows(torch.cat(w, dim=1), shape[0]) * (len(w) ** -0.5)
+    elif rec == "vec_ffn_scale":
+        out = _pad_rows(w[0].reshape(-1), shape[0]) * (9 ** -0.5)
     elif rec == "mat_t":
         out = w[0].t().contiguous()
     elif rec == "rows":

@@ -80,10 +80,15 @@ def find_native(model, model_kwargs) -> Optional[NativeDenoiser]:
         return None
     with torch.no_grad():
         Tp = prompt.size(2)
-        mask = (torch.arange(Tp, device=prompt.device)[None, :] < prompt_lengths[:, None])
-        enc = diff.prompt_encoder(prompt, prompt_lengths) * mask.unsqueeze(1).to(prompt.dtype)
-        ehs = enc.transpose(1, 2).contiguous()
         kv_len = prompt_lengths.clamp(max=Tp).to(torch.int32)
+        # the speech-prompt encoder (model3.py:905-906), once per job: natively when the module has the shape Diff-VITS
+        # uses (diffvits_b200.prompt), else by the module itself
+        from .prompt import encode_prompt
+        ehs = encode_prompt(diff.prompt_encoder, prompt, kv_len)
+        if ehs is None:
+            mask = (torch.arange(Tp, device=prompt.device)[None, :] < prompt_lengths[:, None])
+            enc = diff.prompt_encoder(prompt, prompt_lengths) * mask.unsqueeze(1).to(prompt.dtype)
+            ehs = enc.transpose(1, 2).contiguous()
     # cached per shape on the module and rebound: plan, workspace and the captured loop graph are re-used by the next
     # solver.sample() of the same (B, T, Tp) instead of being rebuilt per call (bounded LRU, DV_PLAN_CACHE plans)
     native = unet.native_denoiser(cond, ehs, kv_len)

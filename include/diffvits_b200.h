@@ -126,6 +126,31 @@ DV_API int dv_sample_group(dv_plan* const* plans, int nplans, int sampler, int n
 /* Kernel launches enqueued by the most recent dv_sample / dv_sample_group (reported on plans[0]). */
 DV_API int dv_plan_last_sample_launches(const dv_plan* plan);
 
+/* ---- PromptEncoder (model3.py:382-433; model.py:72-97, 137-171; operations.py:644-714, 784-821) ---------------------------
+ * The speech-prompt encoder whose output is the UNet's encoder_hidden_states: ConvLayer pre (LayerNorm + 1x1), n_layers x
+ * {LayerNorm, 8-head self-attention with key padding, LayerNorm, 9-tap conv feed-forward (ReLU, 9^-1/2)}, ConvLayer out,
+ * final LayerNorm, padding rows zeroed where the reference multiplies by (1 - mask). The reference evaluates it once per
+ * denoiser call (model3.py:906); it depends on the prompt only, so the drop-in evaluates it once per job with this plan. */
+typedef struct dv_prompt_cfg {
+  int in_channels;   /* 100 mel bins */
+  int hidden;        /* 128 (= out channels = cross_attention_dim); only 128 is built */
+  int n_layers;      /* 4 */
+  int num_heads;     /* 8 (head dim 16) */
+  int ffn_kernel;    /* 9 */
+  int ffn_mult;      /* 4: filter size = 4 * hidden */
+} dv_prompt_cfg;
+typedef struct dv_prompt_plan dv_prompt_plan;
+DV_API int dv_prompt_plan_create(const dv_prompt_cfg* cfg, int B, int Tp, dv_prompt_plan** out);
+DV_API void dv_prompt_plan_destroy(dv_prompt_plan* plan);
+DV_API size_t dv_prompt_plan_workspace_bytes(const dv_prompt_plan* plan);
+DV_API size_t dv_prompt_plan_param_bytes(const dv_prompt_plan* plan);
+DV_API const char* dv_prompt_plan_manifest_json(const dv_prompt_plan* plan);
+DV_API int dv_prompt_plan_bind(dv_prompt_plan* plan, void* workspace, const void* params, void* stream);
+/* PromptEncoder.forward(prompt, lengths) * mask, transposed: prompt NCT [B, in_channels, Tp] fp32, lengths [B] int32
+ * (device), ehs_out [B, Tp, hidden] fp32 = the encoder_hidden_states Diffusion_Encoder.forward passes to the UNet
+ * (model3.py:905-912), rows >= lengths[b] zero. */
+DV_API int dv_prompt_encode(dv_prompt_plan* plan, const float* prompt, const int32_t* lengths, float* ehs_out, void* stream);
+
 /* ---- measurement support ------------------------------------------------------------------------------------- */
 /* Block outputs (bf16 [B, L, C] at byte `offset` of the workspace, named by reference module path) that are still
  * intact after dv_unet_forward returns: lets tests compare the network block by block with the oracle. */

@@ -62,3 +62,15 @@ def test_diffusion_encoder_forward_over_dropin_matches_reference_unet(snap):
     for name, m in res.items():
         assert m["finite"], name
         assert m["rel_l2"] < 1.5e-2 and m["max_abs"] < 2e-2, (name, m)
+
+
+def test_native_prompt_encoder_matches_reference_module(snap):
+    """PromptEncoder (model3.py:382-433) on the engine's kernels vs the reference module, ragged lengths. BF16
+    operands through 4 transformer layers: the same per-call floor as the UNet (measured ~4e-3)."""
+    r = snap.run_arm(os.path.join(HELPERS, "prompt_encoder_check.py"), "dropin")
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    print(res)
+    for name, m in res.items():
+        assert m["finite"] and m["pad_rows_zero"], (name, m)
+        assert m["rel_l2"] < 1e-2 and m["max_abs"] < 5e-2, (name, m)

@@ -388,3 +388,50 @@ def test_serving_front_buckets_requests_faithfully():
     assert seen == list(range(len(shapes)))
     for (T, Tp), idx in plan:
         assert all(shapes[i][0] == T and shapes[i][1] <= Tp for i in idx) and len(idx) <= 2
+
+
+def test_prompt_encoder_plan_and_packing(lib):
+    """Plan of the native PromptEncoder (csrc/prompt_encoder.cu): manifest keys = the reference module's state_dict keys
+    (model3.py:382-433), and the 9-tap conv feed-forward packing (tap order incl. the reference's unshifted tap 0,
+    operations.py:678-684, with 9^-1/2 folded in) against the reference's expression evaluated with torch ops."""
+    from diffvits_b200._lib import PromptCfg
+    from diffvits_b200.engine import pack_slot
+    p = C.c_void_p()
+    cfg = PromptCfg(100, 128, 4, 8, 9, 4)
+    assert lib.dv_prompt_plan_create(C.byref(cfg), 3, 200, C.byref(p)) == 0
+    man = json.loads(lib.dv_prompt_plan_manifest_json(p).decode())
+    keys = {k for s in man for k in s["keys"]}
+    want = {"pre.layer_norm.weight", "pre.layer_norm.bias", "pre.conv.weight", "pre.conv.bias", "layer_norm.weight",
+            "layer_norm.bias", "out_proj.layer_norm.weight", "out_proj.layer_norm.bias", "out_proj.conv.weight", "out_proj.conv.bias"}
+    for l in range(4):
+        q = f"layers.{l}.op."
+        want |= {q + "layer_norm1.weight", q + "layer_norm1.bias", q + "layer_norm2.weight", q + "layer_norm2.bias",
+                 q + "self_attn.in_proj_weight", q + "self_attn.out_proj.weight", q + "ffn.ffn_1.0.bias", q + "ffn.ffn_2.weight",
+                 q + "ffn.ffn_2.bias"} | {q + f"ffn.ffn_1.{i}.weight" for i in range(9)}
+    assert keys == want, keys ^ want
+    assert lib.dv_prompt_plan_workspace_bytes(p) > 0 and lib.dv_prompt_plan_param_bytes(p) > 0
+    lib.dv_prompt_plan_destroy(p)
+    bad = PromptCfg(100, 256, 4, 8, 9, 4)
+    assert lib.dv_prompt_plan_create(C.byref(bad), 1, 50, C.byref(p)) == -4
+    # conv feed-forward: reference expression vs tap-GEMM over the packed weights
+    g = torch.Generator().manual_seed(3)
+    T, B, Cc, Fh = 21, 2, 128, 512
+    x = torch.randn(T, B, Cc, generator=g)
+    ws = [torch.randn(Fh, Cc, generator=g) * 0.05 for _ in range(9)]
+    b0 = torch.randn(Fh, generator=g)
+    padded = F.pad(x, (0, 0, 0, 0, 4, 4))
+    ref = sum(F.linear(padded[i:T + i] if i else x, ws[i], b0 if i == 0 else None) for i in range(9)) * 9 ** -0.5
+    ref = F.relu(ref).transpose(0, 1)                                     # [B, T, F]
+    slot = next(s for s in man if s["name"] == "layers.0.op.ffn.ffn_1.W")
+    sd = {f"layers.0.op.ffn.ffn_1.{i}.weight": ws[i] for i in range(9)}
+    sd["layers.0.op.ffn.ffn_1.0.bias"] = b0
+    wp = pack_slot(slot, sd).float().reshape(slot["shape"])
+    bp = pack_slot(next(s for s in man if s["name"] == "layers.0.op.ffn.ffn_1.b"), sd)
+    xb = x.transpose(0, 1).contiguous()                                   # channel-last [B, T, C]
+    taps = [0, -3, -2, -1, 0, 1, 2, 3, 4]
+    got = F.relu(_tap_gemm_cpu([xb], [(0, ro, 0, Cc) for ro in taps], wp, T) + bp)
+    assert torch.allclose(got, ref, atol=2e-2, rtol=2e-2)                 # packed weights are bf16
+    # ConvTBC k = 1 with K padded from 100 to 128
+    w1 = torch.randn(1, 100, 128, generator=g)
+    wp1 = pack_slot(next(s for s in man if s["name"] == "pre.conv.W"), {"pre.conv.weight": w1}).float().reshape(128, 128)
+    assert torch.allclose(wp1[:, :100], w1[0].t().to(torch.bfloat16).float()) and bool((wp1[:, 100:] == 0).all())
