@@ -19,6 +19,8 @@ DEBUG = os.environ.get("DV_DEBUG", "0") == "1"
 BUILD = os.path.join(HERE, "build_dbg" if DEBUG else "build")
 LIB = os.path.join(HERE, "libdiffvits_b200_dbg.so" if DEBUG else "libdiffvits_b200.so")
 SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu", "elementwise.cu", "engine.cu", "prompt_encoder.cu", "api.cu"]
+KERNEL_SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu",
+                  "elementwise.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -34,7 +36,7 @@ def _nvcc() -> str:
 
 
 def _newest_header() -> float:
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
     hs.append(os.path.join(HERE, "..", "include", "diffvits_b200.h"))
     hs.append(os.path.join(HERE, "..", "include", "diffvits_b200_debug.h"))
     return max(os.path.getmtime(h) for h in hs)
@@ -45,15 +47,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     hdr_t = _newest_header()
     jobs = []
+    objs = []
+    # every kernel source twice: BF16 operands (namespace dv) and FP16 operands (-DDV_F16, namespace dv16, mode "fp16s")
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(BUILD, src.replace(".cu", ".o"))
-        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
-            jobs.append((s, o))
+        for suffix, extra in ((".o", []), ("_f16.o", ["-DDV_F16"])):
+            if extra and src not in KERNEL_SOURCES:
+                continue
+            o = os.path.join(BUILD, src.replace(".cu", suffix))
+            objs.append(o)
+            if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
+                jobs.append((s, o, extra))
 
     def compile_one(job):
-        s, o = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        s, o, extra = job
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -63,9 +71,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr, file=sys.stderr)
 
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(compile_one, jobs))
-    objs = [os.path.join(BUILD, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
                "-cudart", "static"]

@@ -15,7 +15,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 namespace {
 
 constexpr int BQ = 64;    // queries per CTA (4 warps x 16 rows)
@@ -32,7 +32,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." DV_MMA_T "." DV_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -307,7 +307,11 @@ __global__ void __launch_bounds__(32 * NW) attention2_kernel(const AttnParams p)
   const int kvlen = p.kv_len ? p.kv_len[b] : p.Lk;
   const float mask_raw = -10000.0f / p.scale;          // the reference's additive -10000 bias, in raw-score units
   const int kvalid = min(kvlen, p.Lk);                 // keys below this index need no masking
+#ifdef DV_F16
+  constexpr uint32_t ONES = 0x3C003C00u;               // f16x2 (1, 1)
+#else
   constexpr uint32_t ONES = 0x3F803F80u;               // bf16x2 (1, 1)
+#endif
 
   uint32_t qf[D / 16][4];
   float o[D / 8][4];
@@ -491,16 +495,16 @@ cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st) {
 // DV_ATTN=tc|legacy forces one kernel, DV_ATTN_TC_MIN_D moves the threshold.
 constexpr int kTcMinD = 32;        // measured choice, see profiles/r2e_attention_dispatch.txt
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
-  if (p.q_lo != nullptr) return launch_attention_split(p, st);     // FP32-class precision mode (hi + lo planes)
+  if (p.q_lo != nullptr) return DV_NS::launch_attention_split(p, st);     // FP32-class precision mode (hi + lo planes)
   // read per launch (launches are captured into a graph on the hot path): tests flip it between calls
   const char* e = getenv("DV_ATTN");
-  if (e && e[0] == 't') return launch_attention_tc(p, st);          // tcgen05 kernel
+  if (e && e[0] == 't') return DV_NS::launch_attention_tc(p, st);   // tcgen05 kernel
   {
     // head dims from which the tcgen05 kernel is the default (it wins stand-alone for d >= 32; DV_ATTN_TC_MIN_D overrides)
     static const int tc_min_d = [] { const char* m = getenv("DV_ATTN_TC_MIN_D"); return m ? atoi(m) : kTcMinD; }();
-    if (!(e && e[0] == 'l') && p.D >= tc_min_d) return launch_attention_tc(p, st);
+    if (!(e && e[0] == 'l') && p.D >= tc_min_d) return DV_NS::launch_attention_tc(p, st);
   }
-  if (e && e[0] == 'l') return launch_attention_legacy(p, st);      // first mma.sync kernel
+  if (e && e[0] == 'l') return DV_NS::launch_attention_legacy(p, st);      // first mma.sync kernel
   if (p.Lk < 1 || p.Lq < 1) return cudaErrorInvalidValue;
   const char* pj = getenv("DV_ATTN_POLY");                          // accumulator columns (of 8) on the FMA-pipe exp2
   const int polyj = pj ? atoi(pj) : kDefaultPolyJ;
@@ -514,4 +518,4 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t st) {
   }
 }
 
-}  // namespace dv
+}  // namespace DV_NS

@@ -11,7 +11,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 namespace {
 
 constexpr int SQ = 64;      // queries per CTA
@@ -19,7 +19,7 @@ constexpr int SK = 64;      // keys per shared-memory tile
 constexpr int SCH = 16;     // keys per online-softmax chunk
 
 __device__ __forceinline__ float ld_hilo(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t i) {
-  return __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+  return h16_to_f32(hi[i]) + h16_to_f32(lo[i]);
 }
 
 template <int D>
@@ -125,4 +125,4 @@ cudaError_t launch_attention_split(const AttnParams& p, cudaStream_t st) {
   }
 }
 
-}  // namespace dv
+}  // namespace DV_NS

@@ -27,7 +27,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 namespace {
 
 constexpr int TQ = 128;          // queries per CTA (= TMEM lanes)
@@ -449,4 +449,4 @@ cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st) {
   }
 }
 
-}  // namespace dv
+}  // namespace DV_NS

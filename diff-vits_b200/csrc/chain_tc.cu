@@ -27,7 +27,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 namespace {
 
 constexpr int BOX_BYTES = 16384;            // [128 rows x 64 bf16], 128-byte swizzle
@@ -618,4 +618,4 @@ cudaError_t launch_chain_tc(const ChainParams& p, cudaStream_t st) {
   }
 }
 
-}  // namespace dv
+}  // namespace DV_NS

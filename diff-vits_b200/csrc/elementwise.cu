@@ -9,7 +9,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 namespace {
 
 // ------------------------------------------------------------------ layout
@@ -31,9 +31,9 @@ __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict
     const int t = t0 + k, c = c0 + tx;
     if (t < T && c < Csrc) {
       const int col = col0 + c + (c >= split ? shift : 0);
-      const __nv_bfloat16 hi = __float2bfloat16_rn(tile[tx][k]);
+      const __nv_bfloat16 hi = h16_from_f32(tile[tx][k]);
       dst[(static_cast<size_t>(b) * T + t) * ld_dst + col] = hi;
-      if (dst_lo) dst_lo[(static_cast<size_t>(b) * T + t) * ld_dst + col] = __float2bfloat16_rn(tile[tx][k] - __bfloat162float(hi));
+      if (dst_lo) dst_lo[(static_cast<size_t>(b) * T + t) * ld_dst + col] = h16_from_f32(tile[tx][k] - h16_to_f32(hi));
     }
   }
 }
@@ -57,9 +57,9 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
     }
   } else {
     for (size_t i = i4; i < n; ++i) {
-      const __nv_bfloat16 hi = __float2bfloat16_rn(src[i]);
+      const __nv_bfloat16 hi = h16_from_f32(src[i]);
       dst[i] = hi;
-      if (dst_lo) dst_lo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(hi));
+      if (dst_lo) dst_lo[i] = h16_from_f32(src[i] - h16_to_f32(hi));
     }
   }
 }
@@ -285,4 +285,4 @@ cudaError_t launch_unipc_corr(float* x, const float* base, const float* mt, cons
   return launch_k(unipc_corr_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x, base, mt, m1, d, n);
 }
 
-}  // namespace dv
+}  // namespace DV_NS

@@ -10,6 +10,16 @@
 
 namespace dv {
 
+const KernelApi& kernel_api(bool f16) {
+  static const KernelApi bf{dv::gemm_tc_init,    dv::chain_tc_init,    dv::attention_tc_init, dv::attention_tc_prepare,
+                            dv::launch_gemm_tc,  dv::launch_chain_tc,  dv::launch_attention,  dv::launch_gn_apply,
+                            dv::launch_layernorm, dv::launch_nct_to_ntc, dv::launch_f32_to_bf16};
+  static const KernelApi hf{dv16::gemm_tc_init,    dv16::chain_tc_init,    dv16::attention_tc_init, dv16::attention_tc_prepare,
+                            dv16::launch_gemm_tc,  dv16::launch_chain_tc,  dv16::launch_attention,  dv16::launch_gn_apply,
+                            dv16::launch_layernorm, dv16::launch_nct_to_ntc, dv16::launch_f32_to_bf16};
+  return f16 ? hf : bf;
+}
+
 // --------------------------------------------------------------------------------------------- TMA descriptors
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn(std::string& err) {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -115,8 +125,9 @@ struct Builder {
     s.name = name; s.recipe = recipe; s.keys = std::move(keys); s.dtype = dtype; s.shape = std::move(shape);
     size_t n = 1;
     for (int d : s.shape) n *= static_cast<size_t>(d);
-    if (dtype == "bf16" && P.split) s.dtype = "bf16x2";     // hi matrix followed by the lo matrix
-    s.bytes = n * (s.dtype == "bf16" ? 2 : 4);
+    if (dtype == "bf16" && P.triple) s.dtype = "bf16x2";    // hi matrix followed by the lo matrix
+    if (dtype == "bf16" && P.f16) s.dtype = "f16";
+    s.bytes = n * ((s.dtype == "bf16" || s.dtype == "f16") ? 2 : 4);
     s.off = align_up(P.param_bytes, 256);
     P.param_bytes = s.off + s.bytes;
     P.slots.push_back(s);
@@ -253,7 +264,7 @@ struct Builder {
     g.n = N; g.n_pad = round_up(N, 128);
     long long wo = slot(tag + ".W", "conv3", wk, "bf16", {g.n_pad, g.k_tot});
     P.slots.back().shape.push_back(cin_real);  // [n_pad, k_tot, cin_real]: packer pads each tap from cin_real to cin
-    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.split ? 2 : 1);
+    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.triple ? 2 : 1);
     g.w_off = wo;
     g.bias_off = slot(tag + ".b", "vec_sum", bk, "f32", {g.n_pad});
     g.res = res; g.out = out; g.l_out = a0.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
@@ -521,7 +532,7 @@ struct Builder {
     g.n = C; g.n_pad = round_up(C, 128);
     g.w_off = slot(key + ".W", "conv3", {key + ".weight"}, "bf16", {g.n_pad, g.k_tot});
     P.slots.back().shape.push_back(C);
-    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.split ? 2 : 1);
+    P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.triple ? 2 : 1);
     g.bias_off = slot(key + ".b", "vec_sum", {key + ".bias"}, "f32", {g.n_pad});
     g.out = out; g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
     attach_stats(g, out);
@@ -624,8 +635,14 @@ int Plan::build(std::string& err) {
   if (c.cross_attention_dim % 64 != 0) { err = "cross_attention_dim must be a multiple of 64"; return DV_ERR_UNSUPPORTED; }
   if (c.x_channels < 1 || c.x_channels > c.in_channels) { err = "x_channels out of range"; return DV_ERR_INVALID; }
   if (c.out_channels > 128) { err = "out_channels > 128 not supported"; return DV_ERR_UNSUPPORTED; }
-  if (c.precision != DV_PRECISION_BF16 && c.precision != DV_PRECISION_FP32X3) { err = "unknown precision"; return DV_ERR_INVALID; }
-  split = c.precision == DV_PRECISION_FP32X3;
+  if (c.precision != DV_PRECISION_BF16 && c.precision != DV_PRECISION_FP32X3 && c.precision != DV_PRECISION_FP16S) {
+    err = "unknown precision";
+    return DV_ERR_INVALID;
+  }
+  triple = c.precision == DV_PRECISION_FP32X3;
+  f16 = c.precision == DV_PRECISION_FP16S;
+  split = triple || f16;
+  K = &kernel_api(f16);
   emb_dim = 4 * c.block_out_channels[0];
   if (emb_dim != 512) { err = "time_embed_dim must be 512 (block_out_channels[0] == 128)"; return DV_ERR_UNSUPPORTED; }
   cin_pad = round_up(c.in_channels, 64);
@@ -820,11 +837,11 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
   ws = static_cast<uint8_t*>(workspace);
   params = static_cast<const uint8_t*>(prm);
   {
-    cudaError_t ie = gemm_tc_init();
+    cudaError_t ie = K->gemm_tc_init();
     if (ie != cudaSuccess) { err = std::string("gemm_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
-    ie = chain_tc_init();
+    ie = K->chain_tc_init();
     if (ie != cudaSuccess) { err = std::string("chain_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
-    ie = attention_tc_init();
+    ie = K->attention_tc_init();
     if (ie != cudaSuccess) { err = std::string("attention_tc_init: ") + cudaGetErrorString(ie); return DV_ERR_CUDA; }
   }
   cudaError_t ce = cudaMemsetAsync(ws, 0, ws_bytes, st);
@@ -853,7 +870,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         }
         if (!make_tmap_2d(&p.mapW, params + g.w_off, g.k_tot, g.n_pad, 64, err)) return false;
         p.mapW2 = p.mapW;
-        if (split && !make_tmap_2d(&p.mapW2, params + g.w_off + static_cast<size_t>(g.n_pad) * g.k_tot * 2, g.k_tot, g.n_pad, 64, err))
+        if (triple && !make_tmap_2d(&p.mapW2, params + g.w_off + static_cast<size_t>(g.n_pad) * g.k_tot * 2, g.k_tot, g.n_pad, 64, err))
           return false;
         // logical segment -> kernel segments: a.w (BF16) or a_hi.w_hi + a_hi.w_lo + a_lo.w_hi (split: three K segments
         // over the same weight panels of the hi / lo matrix)
@@ -864,7 +881,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
           sg.wsel = 0;
           sg.src = static_cast<int16_t>(2 * lsrc);
           p.seg[p.nseg++] = sg;
-          if (split) {
+          if (triple) {
             sg.wsel = 1;
             p.seg[p.nseg++] = sg;                         // a_hi . w_lo
             sg.wsel = 0;
@@ -974,7 +991,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         o.ln.gamma = pf(o.lno.gamma); o.ln.beta = pf(o.lno.beta);
       } else if (o.kind == OP_ATTN) {
         o.at.q = ws + o.ato.q; o.at.k = ws + o.ato.k; o.at.v = ws + o.ato.v; o.at.o = ws + o.ato.o;
-        if (split) {   // lo plane of the tensor each operand lives in: + B * (batch stride) bf16 elements
+        if (triple) {  // lo plane of the tensor each operand lives in: + B * (batch stride) bf16 elements
           o.at.q_lo = ws + o.ato.q + static_cast<size_t>(B) * o.at.bs_q * 2;
           o.at.k_lo = ws + o.ato.k + static_cast<size_t>(B) * o.at.bs_k * 2;
           o.at.v_lo = ws + o.ato.v + static_cast<size_t>(B) * o.at.bs_v * 2;
@@ -982,7 +999,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         }
         o.at.kv_len = nullptr;  // set in prompt_prepare
         const char* ae = nullptr;
-        if (!attention_tc_prepare(o.at, &ae)) { err = std::string("attention_tc_prepare: ") + (ae ? ae : "?"); return false; }
+        if (!K->attention_tc_prepare(o.at, &ae)) { err = std::string("attention_tc_prepare: ") + (ae ? ae : "?"); return false; }
       }
     }
     return true;
@@ -1030,28 +1047,28 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
           GemmParams p = o.gp;
           if (o.g.out_dynamic) p.out = dyn_out;
           if (ss_slot && p.xf.scale_shift) p.xf.scale_shift += static_cast<size_t>(ss_slot) * B * n_all;
-          e = launch_gemm_tc(p, st);
+          e = K->launch_gemm_tc(p, st);
         } else {
-          e = launch_gemm_tc(o.gp, st);
+          e = K->launch_gemm_tc(o.gp, st);
         }
         break;
-      case OP_CHAIN: e = launch_chain_tc(o.cp, st); break;
+      case OP_CHAIN: e = K->launch_chain_tc(o.cp, st); break;
       case OP_GN_APPLY:
         if (ss_slot && o.gn.scale_shift) {
           GnParams g = o.gn;
           g.scale_shift += static_cast<size_t>(ss_slot) * B * n_all;
-          e = launch_gn_apply(g, st);
+          e = K->launch_gn_apply(g, st);
         } else {
-          e = launch_gn_apply(o.gn, st);
+          e = K->launch_gn_apply(o.gn, st);
         }
         break;
       case OP_LN:
-        e = launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st, o.ln.x_lo, o.ln.out_lo);
+        e = K->launch_layernorm(o.ln.x, o.ln.out, o.ln.gamma, o.ln.beta, o.ln.rows, o.ln.C, o.ln.eps, st, o.ln.x_lo, o.ln.out_lo);
         break;
       case OP_ATTN: {
         AttnParams a = o.at;
         if (o.ato.cross && has_kvlen) a.kv_len = reinterpret_cast<const int*>(ws + off_kvlen);
-        e = launch_attention(a, st);
+        e = K->launch_attention(a, st);
         break;
       }
     }
@@ -1068,7 +1085,7 @@ int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_l
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!ehs) { err = "ehs is null"; return DV_ERR_INVALID; }
   const size_t n = static_cast<size_t>(B) * Tp * cfg.cross_attention_dim;
-  DV_CK(launch_f32_to_bf16(ehs, ws + off_ehs, n, st, split ? ws + off_ehs + n * 2 : nullptr));
+  DV_CK(K->launch_f32_to_bf16(ehs, ws + off_ehs, n, st, split ? ws + off_ehs + n * 2 : nullptr));
   // The captured loop reads the prompt-side tensors at fixed workspace addresses, so a new batch of the same shape
   // keeps the graph; only a change of WHICH optional inputs exist (their pointers are baked into the launches) drops it.
   const bool topo_changed = prompt_ready && (has_aug != (aug != nullptr) || has_kvlen != (kv_len != nullptr));
@@ -1090,7 +1107,7 @@ int Plan::set_cond(const float* cond, cudaStream_t st, std::string& err) {
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   const int cc = cfg.in_channels - cfg.x_channels;
   if (cc <= 0) return DV_OK;
-  DV_CK(launch_nct_to_ntc(cond, ws + off_xin, B, cc, T, cin_pad, cfg.x_channels, 1 << 30, 0, st,
+  DV_CK(K->launch_nct_to_ntc(cond, ws + off_xin, B, cc, T, cin_pad, cfg.x_channels, 1 << 30, 0, st,
                           split ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
   return DV_OK;
 }
@@ -1151,7 +1168,7 @@ int Plan::forward(const float* sample, int x_only, const float* t, int t_stride,
                   std::string& err, int* launches, cudaEvent_t* events, int tables_slot) {
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
-  DV_CK(launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st,
+  DV_CK(K->launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st,
                           split ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
   if (tables_slot < 0) {
     int rc = enqueue_time_tables(t, t_stride, 0, st, err);

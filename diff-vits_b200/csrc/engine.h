@@ -10,6 +10,22 @@
 
 namespace dv {
 
+// The launch functions of one operand format (kernels_api.inc): BF16 (namespace dv) or FP16 (namespace dv16).
+struct KernelApi {
+  cudaError_t (*gemm_tc_init)();
+  cudaError_t (*chain_tc_init)();
+  cudaError_t (*attention_tc_init)();
+  bool (*attention_tc_prepare)(AttnParams&, const char**);
+  cudaError_t (*launch_gemm_tc)(const GemmParams&, cudaStream_t);
+  cudaError_t (*launch_chain_tc)(const ChainParams&, cudaStream_t);
+  cudaError_t (*launch_attention)(const AttnParams&, cudaStream_t);
+  cudaError_t (*launch_gn_apply)(const GnParams&, cudaStream_t);
+  cudaError_t (*launch_layernorm)(const void*, void*, const float*, const float*, int, int, float, cudaStream_t, const void*, void*);
+  cudaError_t (*launch_nct_to_ntc)(const float*, void*, int, int, int, int, int, int, int, cudaStream_t, void*);
+  cudaError_t (*launch_f32_to_bf16)(const float*, void*, size_t, cudaStream_t, void*);
+};
+const KernelApi& kernel_api(bool f16);
+
 struct TRef {  // bf16 channel-last tensor [B, L, C] at byte offset `off` of the workspace
   size_t off = 0;
   int L = 0, C = 0;
@@ -99,8 +115,12 @@ struct Plan {
   dv_unet_cfg cfg;
   int B, T, Tp;
   int n_levels, emb_dim, cin_pad;
-  bool split = false;        // cfg.precision == DV_PRECISION_FP32X3: every bf16 tensor [B, L, C] of the workspace is followed by
-                             // its lo plane (same shape, at + B*L*C*2 bytes), every bf16 weight matrix by its lo matrix
+  bool split = false;        // FP32X3 / FP16S: every 16-bit tensor [B, L, C] of the workspace is followed by its lo plane (same
+                             // shape, at + B*L*C*2 bytes): epilogues, norms and layout kernels read hi + lo and write both
+  bool triple = false;       // FP32X3 only: weights carry a lo matrix too and every product is three MMAs (hi.hi + hi.lo + lo.hi);
+                             // attention core in FP32. FP16S: one MMA on the hi planes (FP16 operands), tensor-core attention
+  bool f16 = false;          // FP16S: the dv16 kernel set (FP16 operand format)
+  const KernelApi* K = nullptr;
   size_t plane(const TRef& t) const { return static_cast<size_t>(B) * t.L * t.C * 2; }
   // Widest level whose transformer blocks run as chained kernels (DV_FUSE_MAXC). Measured on C2 (B200, 32 x 1000):
   // the chain wins or ties while a level has >= ~1.5 row tiles per SM (C = 128: 250 tiles); deeper levels have too few

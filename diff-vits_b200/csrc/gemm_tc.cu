@@ -22,7 +22,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 
 namespace {
 
@@ -508,8 +508,8 @@ __global__ void gemm_ref_kernel(GemmParams p, GemmRefSrc s0, GemmRefSrc s1, Gemm
         const int k = (sg.wk0 + t * sg.tap_stride) * BK + c;
         float a = 0.f;
         if (ls >= 0 && ls < src.L && cs < src.C)
-          a = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src.ptr)[(static_cast<size_t>(b) * src.L + ls) * src.ld + cs]);
-        acc += a * __bfloat162float(W[static_cast<size_t>(n) * k_tot + k]);
+          a = h16_to_f32(reinterpret_cast<const __nv_bfloat16*>(src.ptr)[(static_cast<size_t>(b) * src.L + ls) * src.ld + cs]);
+        acc += a * h16_to_f32(W[static_cast<size_t>(n) * k_tot + k]);
       }
     }
   }
@@ -600,7 +600,7 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   if (p.out_mode == GEMM_OUT_GEGLU && p.n_pad % 128 != 0) return cudaErrorInvalidValue;
   // shared conv taps / a GroupNorm fused into the operand path are features of the two-ring kernel (csrc/gemm_tc2.cu)
   for (int i = 0; i < p.nseg; ++i)
-    if (p.seg[i].ntap != 1 || p.seg[i].xf != 0) return launch_gemm_tc2(p_in, st);
+    if (p.seg[i].ntap != 1 || p.seg[i].xf != 0) return DV_NS::launch_gemm_tc2(p_in, st);
   for (int i = 0; i < GEMM_MAX_SRC; ++i)
     if (p.map_rows[i] != 128) return cudaErrorInvalidValue;
   const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
@@ -642,4 +642,4 @@ cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const v
   return cudaGetLastError();
 }
 
-}  // namespace dv
+}  // namespace DV_NS

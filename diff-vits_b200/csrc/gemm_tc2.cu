@@ -15,7 +15,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 
 namespace {
 
@@ -747,4 +747,4 @@ cudaError_t launch_gemm_tc2(const GemmParams& p_in, cudaStream_t st) {
   return ew == 8 ? launch_bn<128, 8>(p, st) : launch_bn<128, 16>(p, st);
 }
 
-}  // namespace dv
+}  // namespace DV_NS

@@ -119,15 +119,9 @@ struct alignas(64) GemmParams {
   unsigned long long* trace;  // debug: CTA 0 appends (role, tile, event, clock) records; [0] = record count
 };
 
-cudaError_t gemm_tc_init();                       // query the device, set kernel attributes (call outside graph capture)
-int gemm_pick_bn(int m_tiles, int n_pad);
-cudaError_t launch_gemm_tc(const GemmParams& p, cudaStream_t st);   // dispatches to launch_gemm_tc2 for shared taps / fused norms
-cudaError_t gemm_tc2_init();
-cudaError_t launch_gemm_tc2(const GemmParams& p, cudaStream_t st);  // two-ring kernel (csrc/gemm_tc2.cu)
 // Debug/reference implementation of exactly the same contract on CUDA cores (plain loads, fp32 FMA).
 // Used by tests to cross-check the tcgen05 kernel; never used by the engine.
 struct GemmRefSrc { const void* ptr; int L, C, ld; };
-cudaError_t launch_gemm_ref(const GemmParams& p, const GemmRefSrc* srcs, const void* W, int k_tot, cudaStream_t st);
 
 // ------------------------------------------------------------------ chained GEMMs (csrc/chain_tc.cu)
 // One persistent kernel runs a short program of row-local GEMMs of a transformer block over 128-row tiles, keeping
@@ -173,8 +167,6 @@ struct alignas(64) ChainParams {
   int tiles_per_batch;    // ceil(L / 128)
   int dbg_flags;          // timing experiments only (DV_CHAIN_DBG): 1 skip GELU math, 2 skip proxy fences, 4 skip bias loads
 };
-cudaError_t chain_tc_init();
-cudaError_t launch_chain_tc(const ChainParams& p, cudaStream_t st);
 
 // ------------------------------------------------------------------ attention (flash style, bf16 in, fp32 softmax)
 struct alignas(64) AttnParams {
@@ -189,14 +181,8 @@ struct alignas(64) AttnParams {
   // split precision: lo planes (same strides); q_lo != nullptr selects the FP32 CUDA-core kernel (csrc/attention_split.cu)
   const void* q_lo; const void* k_lo; const void* v_lo; void* o_lo;
 };
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t st);          // tcgen05 kernel (csrc/attention_tc.cu)
-cudaError_t attention_tc_init();                                            // kernel attributes (call outside graph capture)
 // Encodes mapQ/mapK/mapV from the pointers / strides / shape already stored in p (host only, no stream work). Must be
 // called whenever those change and before launch_attention_tc. Returns false with a message on failure.
-bool attention_tc_prepare(AttnParams& p, const char** err);
-cudaError_t launch_attention_tc(const AttnParams& p, cudaStream_t st);
-cudaError_t launch_attention_legacy(const AttnParams& p, cudaStream_t st);   // mma.sync kernel (csrc/attention.cu)
-cudaError_t launch_attention_split(const AttnParams& p, cudaStream_t st);    // hi + lo operands, fp32 math (csrc/attention_split.cu)
 
 // ------------------------------------------------------------------ norms
 // Partial statistics layout (written by the GEMM epilogue or by gn_stats): float [B][chunks][nblk][2] holding the
@@ -221,28 +207,18 @@ struct GnParams {
   void* out;                   // bf16 [B, L, c0 + c1]
   const void* x0_lo; const void* x1_lo; void* out_lo;   // split precision: lo planes (out_lo != nullptr selects it)
 };
-size_t gn_scratch_floats(int B, int L, int C);
 // standalone statistics pass over (x0 | x1) into `scratch` (same partial layout, one source covering all channels)
-cudaError_t launch_gn_stats(const GnParams& p, float* scratch, cudaStream_t st);
-cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st);
 // x_lo / out_lo: lo planes in split precision (both null otherwise)
-cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
-                             float eps, cudaStream_t st, const void* x_lo = nullptr, void* out_lo = nullptr);
 // LayerNorm variants of the prompt encoder (C = 128 columns stored, statistics over the first c_real of them; the rest
 // of the output row is zero): rows >= row_len[row / rows_per_batch] read as zeros when mask_in (masked_fill before the
 // norm, model.py:95-97) and are written as zeros when mask_out (x * (1 - mask) after it, model3.py:429-431);
 // out_f32 != nullptr: the result also goes there in fp32.
 struct LnMaskParams { const int* row_len; int rows_per_batch; int c_real; int mask_in; int mask_out; float* out_f32; };
-cudaError_t launch_layernorm_masked(const void* x, void* out, const float* gamma, const float* beta, int rows, float eps,
-                                    const LnMaskParams& m, cudaStream_t st);
 
 // ------------------------------------------------------------------ elementwise / small
 // [B, Csrc, T] fp32 -> channel-last bf16 [B, T, ld_dst]; channel c goes to column c + (c >= split ? shift : 0).
 // dst_lo != nullptr (split precision): the lo plane bf16(x - float(hi)) goes there.
-cudaError_t launch_nct_to_ntc(const float* src, void* dst, int B, int Csrc, int T, int ld_dst, int col0, int split,
-                              int shift, cudaStream_t st, void* dst_lo = nullptr);
 // [B, T, C] fp32 -> bf16 (same layout)
-cudaError_t launch_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t st, void* dst_lo = nullptr);
 
 struct TembParams {
   const float* t; int t_stride;          // model time per batch item (t_stride 0 = broadcast)
@@ -255,18 +231,22 @@ struct TembParams {
   float* ss_all;                         // out [B, n_all]
   int B, n_all, sin_dim, emb_dim;
 };
-cudaError_t launch_temb(const TembParams& p, cudaStream_t st);
 
 // sampler updates (fp32, [n] elements)
 // x_out = a*x + b*m1 + c*m0 ; if roundtrip: m1 is first replaced by the reference's x0->eps->x0 round trip
 // m1' = (x - sig*((x - alp*m1)/sig))/alp  and written back.
-cudaError_t launch_axpbypcz(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
-                            int roundtrip, float alp, float sig, size_t n, cudaStream_t st);
 // UniPC predictor: xpred = a*x + b*m1 + cp*(m0 - m1) ; base = a*x + b*m1 + cc*(m0 - m1)
-cudaError_t launch_unipc_pred(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a,
-                              float b, float cp, float cc, int has_m0, size_t n, cudaStream_t st);
 // UniPC corrector: x = base + d*(mt - m1)
-cudaError_t launch_unipc_corr(float* x, const float* base, const float* mt, const float* m1, float d, size_t n,
-                              cudaStream_t st);
 
 }  // namespace dv
+
+// Launch-level API of the kernel sources (csrc/kernels_api.inc). Every kernel source is compiled twice: BF16 operands
+// (namespace dv) and, with -DDV_F16, FP16 operands (namespace dv16, precision mode "fp16s"); the parameter structs above are
+// shared, the engine picks the set of functions by precision (engine.h: KernelApi).
+namespace dv {
+#include "kernels_api.inc"
+}
+namespace dv16 {
+using namespace dv;
+#include "kernels_api.inc"
+}

@@ -15,7 +15,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-namespace dv {
+namespace DV_NS {
 namespace {
 
 constexpr int NT = 256;
@@ -411,4 +411,4 @@ cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const
 #undef DV_LN_CASE
 }
 
-}  // namespace dv
+}  // namespace DV_NS

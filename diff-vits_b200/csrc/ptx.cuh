@@ -7,7 +7,18 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
-namespace dv {
+// Every kernel source is compiled twice: for BF16 operands (namespace dv) and, with -DDV_F16, for FP16 operands (namespace
+// dv16; precision mode "fp16s"). The 16-bit format shows up in exactly four places: pack_bf16 / bf16_lo / bf16_hi below,
+// the scalar conversions h16_from_f32 / h16_to_f32, the tcgen05 instruction descriptor and the mma.sync type suffix.
+#ifdef DV_F16
+#define DV_NS dv16
+#define DV_MMA_T "f16"
+#else
+#define DV_NS dv
+#define DV_MMA_T "bf16"
+#endif
+
+namespace DV_NS {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -105,8 +116,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32, both operands K-major, dense.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+#ifdef DV_F16
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |   // A / B format 0 = F16
          (static_cast<uint32_t>(m >> 4) << 24);
+#else
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |   // A / B format 1 = BF16
+         (static_cast<uint32_t>(m >> 4) << 24);
+#endif
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -217,12 +233,41 @@ __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
 }
 
 // ---------------------------------------------------------------- misc math / packing
+// Two fp32 -> one packed pair of 16-bit operands / back. (The names keep "bf16" for the default format; under DV_F16 they
+// are the FP16 forms, saturating so that an out-of-range activation becomes +-65504 instead of inf.)
+#ifdef DV_F16
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) {
+  float f;
+  asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l;}" : "=f"(f) : "r"(v));
+  return f;
+}
+__device__ __forceinline__ float bf16_hi(uint32_t v) {
+  float f;
+  asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, h;}" : "=f"(f) : "r"(v));
+  return f;
+}
+#else
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+#endif
+// scalar forms on the 16-bit storage type (pointers are typed __nv_bfloat16 in both builds: a 2-byte element)
+__device__ __forceinline__ __nv_bfloat16 h16_from_f32(float x) {
+  const uint32_t p = pack_bf16(x, 0.f);
+  const unsigned short u = static_cast<unsigned short>(p & 0xFFFFu);
+  return *reinterpret_cast<const __nv_bfloat16*>(&u);
+}
+__device__ __forceinline__ float h16_to_f32(__nv_bfloat16 h) {
+  return bf16_lo(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(&h)));
+}
 // SiLU with approximate MUFU ops (2 ulp class, output is stored as bf16): x * rcp(1 + 2^(-x log2 e)). A one-MUFU
 // form (h + h tanh(h), h = x/2) was measured 1 % faster per denoiser call but cancels in the negative tail
 // (|error| ~1e-3 at x = -4, 6x the bf16 step) and tripled the first-resnet parity error: not kept.
@@ -277,4 +322,4 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-}  // namespace dv
+}  // namespace DV_NS

@@ -132,6 +132,8 @@ def pack_slot(slot: dict, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
         hi = out.to(torch.bfloat16)
         lo = (out - hi.to(torch.float32)).to(torch.bfloat16)
         return torch.cat([hi.reshape(-1), lo.reshape(-1)])
+    if slot["dtype"] == "f16":
+        return out.clamp(-65504.0, 65504.0).to(torch.float16).reshape(-1)
     return out.to(torch.bfloat16 if slot["dtype"] == "bf16" else torch.float32).reshape(-1)
 
 
@@ -146,11 +148,12 @@ def pack_params(manifest: List[dict], sd: Dict[str, torch.Tensor], nbytes: int) 
     return blob
 
 
-PRECISIONS = {"bf16": 0, "fp32x3": 1}
+PRECISIONS = {"bf16": 0, "fp32x3": 1, "fp16s": 2}
 
 
 def default_precision() -> str:
-    """DV_PRECISION=bf16 (default, fast path) | fp32x3 (hi + lo BF16 operand split, FP32-class accuracy)."""
+    """DV_PRECISION=bf16 (default, fast path) | fp16s (FP16 operands + hi/lo residual stream, meets the 1e-3 gate) |
+    fp32x3 (hi + lo BF16 operand split, three MMAs per product, FP32-class accuracy)."""
     import os
     p = os.environ.get("DV_PRECISION", "bf16").lower()
     if p not in PRECISIONS:
@@ -315,9 +318,10 @@ class DenoiserEngine:
         for i in range(self.lib.dv_plan_tensor_count(self._plan)):
             check(self.lib.dv_plan_tensor_info(self._plan, i, buf, 160, C.byref(off), C.byref(L), C.byref(Cc)))
             n = self.B * L.value * Cc.value * 2
-            t = self.workspace[off.value: off.value + n].view(torch.bfloat16).view(self.B, L.value, Cc.value)
-            if self.precision == "fp32x3":      # hi + lo planes -> the fp32 value they carry
-                lo = self.workspace[off.value + n: off.value + 2 * n].view(torch.bfloat16).view(self.B, L.value, Cc.value)
+            dt = torch.float16 if self.precision == "fp16s" else torch.bfloat16
+            t = self.workspace[off.value: off.value + n].view(dt).view(self.B, L.value, Cc.value)
+            if self.precision in ("fp32x3", "fp16s"):      # hi + lo planes -> the fp32 value they carry
+                lo = self.workspace[off.value + n: off.value + 2 * n].view(dt).view(self.B, L.value, Cc.value)
                 t = t.float() + lo.float()
             out[buf.value.decode()] = t
         return out

@@ -42,6 +42,64 @@ def supported(module) -> Optional[PromptCfg]:
         return None
 
 
+class PromptEncoderParams(torch.nn.Module):
+    """Parameter container with the reference PromptEncoder's state_dict layout (model3.py:382-433; keys `pre.*`,
+    `layers.N.op.*`, `out_proj.*`, `layer_norm.*`) for callers that do not have the reference's `model3` module at hand
+    (bench.py, tests): `load_state_dict` of a reference checkpoint's `diff_model.prompt_encoder.*` entries works. No
+    `forward`: compute is `encode_prompt` / `NativePromptEncoder`. Random init: LayerNorm (1, 0), normal weights."""
+
+    class _Holder(torch.nn.Module):
+        pass
+
+    def __init__(self, in_channels: int = 100, hidden: int = 128, n_layers: int = 4, seed: int = 1234):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        P = torch.nn.Parameter
+
+        def ln(c):
+            h = self._Holder()
+            h.weight, h.bias = P(torch.ones(c)), P(torch.zeros(c))
+            return h
+
+        def randn(*shape, std):
+            return P(torch.randn(*shape, generator=g) * std)
+
+        self.hidden_size, self.num_layers, self.last_ln = hidden, n_layers, True
+        self.pre = self._Holder()
+        self.pre.layer_norm = ln(in_channels)
+        self.pre.conv = self._Holder()
+        self.pre.conv.weight, self.pre.conv.bias = randn(1, in_channels, hidden, std=(3.2 / in_channels) ** 0.5), P(torch.zeros(hidden))
+        self.layers = torch.nn.ModuleList()
+        for _ in range(n_layers):
+            lay, op = self._Holder(), self._Holder()
+            op.layer_norm1, op.layer_norm2 = ln(hidden), ln(hidden)
+            op.self_attn = self._Holder()
+            op.self_attn.num_heads = 8
+            op.self_attn.in_proj_weight = randn(3 * hidden, hidden, std=hidden ** -0.5)
+            op.self_attn.out_proj = self._Holder()
+            op.self_attn.out_proj.weight = randn(hidden, hidden, std=hidden ** -0.5)
+            op.ffn = self._Holder()
+            op.ffn.ffn_1 = torch.nn.ModuleList()
+            for i in range(9):
+                lin = self._Holder()
+                lin.weight = randn(4 * hidden, hidden, std=hidden ** -0.5)
+                if i == 0:
+                    lin.bias = P(torch.zeros(4 * hidden))
+                op.ffn.ffn_1.append(lin)
+            op.ffn.ffn_2 = self._Holder()
+            op.ffn.ffn_2.weight, op.ffn.ffn_2.bias = randn(hidden, 4 * hidden, std=(4 * hidden) ** -0.5), P(torch.zeros(hidden))
+            lay.op = op
+            self.layers.append(lay)
+        self.out_proj = self._Holder()
+        self.out_proj.layer_norm = ln(hidden)
+        self.out_proj.conv = self._Holder()
+        self.out_proj.conv.weight, self.out_proj.conv.bias = randn(1, hidden, hidden, std=(4.0 / hidden) ** 0.5), P(torch.zeros(hidden))
+        self.layer_norm = ln(hidden)
+
+    def forward(self, *_a, **_k):
+        raise RuntimeError("PromptEncoderParams holds parameters only; use diffvits_b200.prompt.encode_prompt (CUDA, no CPU fallback)")
+
+
 class NativePromptEncoder:
     """One plan of the native PromptEncoder at fixed (B, Tp) on the module's CUDA device."""
 

@@ -137,3 +137,77 @@ def test_batch_consistency_and_bf16_mode_coexist(env, seeded_unet):
     rel = U.rel_l2(o16, out)
     print(f"bf16 mode vs fp32x3 mode: rel {rel:.3e}")
     assert 1e-3 < rel < 1.5e-2
+
+
+# ------------------------------------------------------------------------------------------------ fp16s
+@pytest.fixture(scope="module")
+def env16(seeded_unet):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gpu_util
+    from oracle import inputs, unet_oracle
+    unet = copy.deepcopy(seeded_unet).to("cuda")
+    unet.native_precision = "fp16s"
+    sd_gpu = {k: v.detach().clone() for k, v in unet.state_dict().items()}
+    return dict(U=gpu_util, unet=unet, sd=sd_gpu, inputs=inputs, uo=unet_oracle)
+
+
+def test_fp16s_meets_the_16_bit_tier_gate(env16):
+    """"fp16s": FP16 operands (dv16 kernel set: same tcgen05 kind::f16 rate and bytes as BF16), residual stream and norm
+    inputs as hi + lo planes, ONE MMA per product. north_star's gate for the 16-bit tier: 2e-2 max-abs / 1e-3 rel-L2 per
+    denoiser call and on the final latent, against the FP32 reference goldens."""
+    import diffvits_b200
+    U, unet = env16["U"], env16["unet"]
+    g = np.load(os.path.join(GOLD, "unet_c1.npz"))
+    x_T, cond, ehs = env16["inputs"].make_inputs(1, 200, 282)
+    sample, ehs = torch.cat([x_T, cond], 1).cuda(), ehs.cuda()
+    for t, ref in zip(g["t"], g["out"]):
+        out = unet(sample, torch.tensor([float(t)], device="cuda"), ehs).sample
+        ref = torch.from_numpy(ref).cuda()
+        rel, mx = U.rel_l2(out, ref), U.max_abs(out, ref)
+        print(f"fp16s t={t}: vs fp32 reference golden rel {rel:.3e} max {mx:.3e}")
+        assert torch.isfinite(out).all() and rel < 1e-3 and mx < 2e-2
+    g2 = np.load(os.path.join(GOLD, "unet_oddlen.npz"))
+    for T, seed in ((203, 3), (198, 4)):
+        x, c, e = env16["inputs"].make_inputs(1, T, 40, seed=seed)
+        out = unet(torch.cat([x, c], 1).cuda(), torch.tensor([613.0], device="cuda"), e.cuda()).sample
+        rel = U.rel_l2(out, torch.from_numpy(g2[f"out{T}"]).cuda())
+        print(f"fp16s T={T}: rel {rel:.3e}")
+        assert rel < 1e-3
+    gs = np.load(os.path.join(GOLD, "sampler_c1.npz"))
+    gi = np.load(os.path.join(GOLD, "sampler_c1_inputs.npz"))
+    betas = env16["inputs"].betas_linear()
+    native = diffvits_b200.NativeDenoiser(unet, cond.cuda(), ehs)
+    assert native.engine.precision == "fp16s"
+    for x, t, ref in zip(gi["dpm_x"], gi["dpm_t"], gs["dpm_steps"]):
+        out = native(torch.from_numpy(x).cuda(), torch.tensor([float(t)], device="cuda"))
+        rel = U.rel_l2(out, torch.from_numpy(ref).cuda())
+        print(f"fp16s dpm t_in={float(t):8.3f}: teacher-forced denoiser output vs reference rel {rel:.3e}")
+        assert rel < 1e-3
+    for name, sampler, steps in (("dpm50", "dpmsolver++", 50), ("unipc10", "unipc", 10)):
+        lat = diffvits_b200.sample_native(unet, x_T.cuda(), cond.cuda(), ehs, sampler=sampler, steps=steps, betas=betas,
+                                          native=native)
+        ref = torch.from_numpy(gs[name]).cuda()
+        rel, mx = U.rel_l2(lat, ref), U.max_abs(lat, ref)
+        print(f"fp16s {name}: free-running final latent vs reference rel {rel:.3e} max {mx:.3e}")
+        assert torch.isfinite(lat).all() and mx < 2e-2 and rel < 4e-3      # per-call errors compound over the loop (x2.5, as in BF16)
+
+
+def test_fp16s_teacher_forced_per_block(env16):
+    U, unet, uo = env16["U"], env16["unet"], env16["uo"]
+    import diffvits_b200
+    x_T, cond, ehs = env16["inputs"].make_inputs(2, 200, 282, seed=21)
+    lens, mask = env16["inputs"].ragged_mask(2, 282)
+    ehs = ehs * mask[:, :, None]
+    native = diffvits_b200.NativeDenoiser(unet, cond.cuda(), ehs.cuda(), kv_len=lens.cuda())
+    t = torch.tensor([731.5], device="cuda")
+    out = native(x_T.cuda(), t).clone()
+    torch.cuda.synchronize()
+    got = {k: v.float().transpose(1, 2).contiguous() for k, v in native.engine.named_tensors().items()}
+    trace = {}
+    final = uo.unet_forward(env16["sd"], torch.cat([x_T, cond], 1).cuda(), t, ehs.cuda(), mask=mask.cuda(), trace=trace, teacher=got)
+    rels = {k: U.rel_l2(got[k], trace[k]) for k in trace}
+    rels["conv_out"] = U.rel_l2(out, final)
+    print(f"fp16s teacher-forced per-block vs fp32 oracle: {len(rels)} tensors, max {max(rels.values()):.2e}")
+    for k, v in rels.items():
+        assert v < 5e-4, (k, v)
