@@ -638,6 +638,30 @@ def run_native(args):
             "clocks": clocks,
             "roofline": roofline,
         }
+    # ---- the other precision modes on the same workload (device-resident loop; parity of each mode: tests/test_gpu_precision.py)
+    if rank == 0 and world == 1 and not args.no_modes and args.precision == "bf16":
+        import copy
+        modes = {"bf16": {"ms_per_step": round(ms_res, 2), "frames_per_s": round(value, 1),
+                          "parity_vs_fp32_reference": "per call 8.3e-3 rel-L2 / 1.4e-2 max-abs (the reference under autocast-bf16: 1.05e-2)"}}
+        notes = {"fp16s": "FP16 operands + hi/lo residual stream, one MMA per product: per call 8.1e-4 rel-L2 / 1.3e-3 max-abs, "
+                          "10-step UniPC latent 9.0e-4, 50-step DPM-Solver++ latent 1.9e-3",
+                 "fp32x3": "hi+lo BF16 split, three MMAs per product, FP32 attention core: per call 1.5e-5 rel-L2, 50-step latent 3.8e-5"}
+        for mode in ("fp16s", "fp32x3"):
+            u2 = copy.deepcopy(unet)
+            u2.native_precision = mode
+            n2 = diffvits_b200.NativeDenoiser(u2, cond_d, ehs_d)
+
+            def step2():
+                diffvits_b200.sample_native(u2, x_d, cond_d, ehs_d, sampler=sampler, steps=nfe, betas=betas, native=n2)
+
+            for _ in range(3):
+                step2()
+            ms2 = timed(step2, 2)
+            modes[mode] = {"ms_per_step": round(ms2, 2), "frames_per_s": round(frames / (ms2 * 1e-3), 1),
+                           "parity_vs_fp32_reference": notes[mode]}
+            n2.close()
+            del n2, u2
+        line["precision_modes"] = modes
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -679,6 +703,7 @@ def main():
     ap.add_argument("--cpu-target", type=float, default=10.0, help="reference arm: seconds of CPU work per timed step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-ref", action="store_true", help="skip the gpu_reference leg")
+    ap.add_argument("--no-modes", action="store_true", help="skip the fp16s / fp32x3 timing legs")
     ap.add_argument("--lanes", type=int, default=None,
                     help="concurrent batch slices inside the loop graph (default: engine heuristic / DV_LANES)")
     args = ap.parse_args()

@@ -99,20 +99,22 @@ struct Builder {
     return o;
   }
   // bf16 tensors are followed by their lo plane in split precision (Plan::plane)
-  size_t tensor_bytes(int L, int C) const { return static_cast<size_t>(P.B) * L * C * 2 * (P.split ? 2 : 1); }
+  size_t tensor_bytes(int L, int C, bool lo) const { return static_cast<size_t>(P.B) * L * C * 2 * (lo ? 2 : 1); }
+  // block outputs: the residual stream (lo plane in both split modes)
   TRef act(int L, int C) {
     TRef t;
-    t.L = L; t.C = C;
-    t.off = ws_alloc(tensor_bytes(L, C));
+    t.L = L; t.C = C; t.lo = P.split;
+    t.off = ws_alloc(tensor_bytes(L, C, t.lo));
     return t;
   }
   // scratch tensors: lifetime = one block; offsets are relative to the scratch arena until finalize()
   static constexpr size_t SCRATCH_TAG = size_t(1) << 62;
-  TRef tmp(int L, int C) {
+  // stream = part of the residual stream (the transformer's z); everything else is read by the tensor core / attention only
+  TRef tmp(int L, int C, bool stream = false) {
     TRef t;
-    t.L = L; t.C = C;
+    t.L = L; t.C = C; t.lo = P.triple || (P.split && stream);
     size_t o = align_up(scratch_cur, 1024);
-    scratch_cur = o + tensor_bytes(L, C);
+    scratch_cur = o + tensor_bytes(L, C, t.lo);
     if (scratch_cur > scratch_max) scratch_max = scratch_cur;
     t.off = SCRATCH_TAG | o;
     return t;
@@ -163,6 +165,7 @@ struct Builder {
       ap.gno.st[i] = xs[i]->st_off;
     }
     ap.gno.x0 = x0.off; ap.gno.x1 = x1.valid() ? x1.off : 0; ap.gno.out = out.off;
+    ap.gno.x_lo = x0.lo && (!x1.valid() || x1.lo); ap.gno.out_lo = out.lo;
     ap.gno.gamma = vec(norm_key + ".weight", C);
     ap.gno.beta = vec(norm_key + ".bias", C);
     ap.gno.ss = ss_off;
@@ -172,6 +175,7 @@ struct Builder {
     Op o;
     o.kind = OP_LN; o.tag = tag;
     o.lno.x = x.off; o.lno.out = out.off;
+    o.lno.x_lo = x.lo; o.lno.out_lo = out.lo;
     o.lno.gamma = vec(key + ".weight", x.C);
     o.lno.beta = vec(key + ".bias", x.C);
     o.ln.rows = P.B * x.L; o.ln.C = x.C; o.ln.eps = 1e-5f;
@@ -327,7 +331,7 @@ struct Builder {
       emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
       gn_key.clear();
     }
-    TRef z = tmp(L, C);
+    TRef z = tmp(L, C, true);
     TRef nrm = tmp(L, C);
     TRef qkv = tmp(L, 3 * C);
     TRef ao = tmp(L, C);
@@ -369,12 +373,13 @@ struct Builder {
     // --- cross attention to the prompt (K/V hoisted into prep_ops)
     TRef kv;
     kv.L = P.Tp; kv.C = 2 * C;
-    kv.off = ws_alloc(tensor_bytes(P.Tp, 2 * C));
+    kv.lo = P.triple;
+    kv.off = ws_alloc(tensor_bytes(P.Tp, 2 * C, kv.lo));
     linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
            2 * C, TRef(), kv, GEMM_OUT_BF16);
     TRef q = qkv;  // reuse the first C columns' storage as a dense [L, C] tensor
     q.C = C;
-    if (P.split) q = tmp(L, C);   // (an alias would put its lo plane inside qkv's hi plane: keep the two-plane rule simple)
+    if (P.triple) q = tmp(L, C);  // (an alias would put its lo plane inside qkv's hi plane: keep the two-plane rule simple)
     linear(P.ops, tb + ".attn2.to_q", nrm, "linear", {tb + ".attn2.to_q.weight"}, "", C, TRef(), q, GEMM_OUT_BF16);
     {
       Op o;
@@ -461,7 +466,8 @@ struct Builder {
     }
     TRef kv;
     kv.L = P.Tp; kv.C = 2 * C;
-    kv.off = ws_alloc(tensor_bytes(P.Tp, 2 * C));
+    kv.lo = P.triple;
+    kv.off = ws_alloc(tensor_bytes(P.Tp, 2 * C, kv.lo));
     linear(P.prep_ops, tb + ".attn2.kv", ehs_bf16, "linear", {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, "",
            2 * C, TRef(), kv, GEMM_OUT_BF16);
     TRef q = qkv;  // the first [L, C] worth of the qkv scratch, dense
@@ -662,9 +668,9 @@ int Plan::build(std::string& err) {
   const int C0 = c.block_out_channels[0];
 
   // ---- persistent regions
-  off_xin = b.ws_alloc(b.tensor_bytes(T, cin_pad));
-  b.ehs_bf16.L = Tp; b.ehs_bf16.C = c.cross_attention_dim;
-  b.ehs_bf16.off = b.ws_alloc(b.tensor_bytes(Tp, c.cross_attention_dim));
+  off_xin = b.ws_alloc(b.tensor_bytes(T, cin_pad, triple));
+  b.ehs_bf16.L = Tp; b.ehs_bf16.C = c.cross_attention_dim; b.ehs_bf16.lo = triple;
+  b.ehs_bf16.off = b.ws_alloc(b.tensor_bytes(Tp, c.cross_attention_dim, triple));
   off_ehs = b.ehs_bf16.off;
   off_aug = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4);
   off_embact = b.ws_alloc(static_cast<size_t>(B) * emb_dim * 4 * 2);          // two time-table slots
@@ -687,7 +693,7 @@ int Plan::build(std::string& err) {
 
   // ---- the network (unet_1d_condition.py:943-1032)
   TRef xin;
-  xin.off = off_xin; xin.L = T; xin.C = cin_pad;
+  xin.off = off_xin; xin.L = T; xin.C = cin_pad; xin.lo = triple;
   std::vector<TRef> skips;
   TRef h = b.act(T, C0);
   b.conv3(ops, "conv_in", xin, TRef(), c.in_channels, "conv_in.weight", "conv_in.bias", C0, nullptr, 0, "", TRef(), h,
@@ -860,7 +866,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         for (int i = 0; i < GEMM_MAX_SRC; ++i) {
           const int s = (i >> 1) < g.nsrc ? (i >> 1) : 0;  // unused maps alias source 0 so prefetch.tensormap stays valid
           const TRef& t = g.src[s];
-          const size_t lo = (split && (i & 1)) ? plane(t) : 0;
+          const size_t lo = (triple && (i & 1)) ? plane(t) : 0;
           int rows = 128;                                  // sources read with shared conv taps stage a 136-row box
           for (int k = 0; k < g.nseg; ++k) if (g.seg[k].src == s && g.seg[k].ntap == 3) rows = 136;
           p.map_rows[i] = static_cast<int16_t>(rows);
@@ -909,10 +915,10 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.out_mode = g.out_mode;
         p.bias = pf(g.bias_off);
         p.res = g.res.valid() ? ws + g.res.off : nullptr;
-        p.res_lo = (split && g.res.valid()) ? ws + g.res.off + plane(g.res) : nullptr;
+        p.res_lo = (g.res.valid() && g.res.lo) ? ws + g.res.off + plane(g.res) : nullptr;
         p.ld_res = g.res.valid() ? g.res.C : 0;
         p.out = g.out_dynamic ? nullptr : ws + g.out.off;
-        p.out_lo = (split && !g.out_dynamic && g.out_mode != GEMM_OUT_F32_NCL) ? ws + g.out.off + plane(g.out) : nullptr;
+        p.out_lo = (g.out.lo && !g.out_dynamic && g.out_mode != GEMM_OUT_F32_NCL) ? ws + g.out.off + plane(g.out) : nullptr;
         p.ld_out = g.ld_out;
         p.out_bs = g.out_bs;
         p.trim_col = g.trim_col;
@@ -971,11 +977,13 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         o.gn.x1 = o.gn.c1 ? ws + o.gno.x1 : nullptr;
         o.gn.out = ws + o.gno.out;
         o.gn.x0_lo = o.gn.x1_lo = nullptr; o.gn.out_lo = nullptr;
-        if (split) {
+        {
           const size_t rows = static_cast<size_t>(B) * o.gn.L * 2;
-          o.gn.x0_lo = ws + o.gno.x0 + rows * o.gn.c0;
-          if (o.gn.c1) o.gn.x1_lo = ws + o.gno.x1 + rows * o.gn.c1;
-          o.gn.out_lo = ws + o.gno.out + rows * (o.gn.c0 + o.gn.c1);
+          if (o.gno.x_lo) {
+            o.gn.x0_lo = ws + o.gno.x0 + rows * o.gn.c0;
+            if (o.gn.c1) o.gn.x1_lo = ws + o.gno.x1 + rows * o.gn.c1;
+          }
+          if (o.gno.out_lo) o.gn.out_lo = ws + o.gno.out + rows * (o.gn.c0 + o.gn.c1);
         }
         for (int i = 0; i < o.gn.nst; ++i) o.gn.st[i].ptr = reinterpret_cast<const float*>(ws + off_stats + o.gno.st[i]);
         o.gn.gamma = pf(o.gno.gamma);
@@ -984,9 +992,10 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
       } else if (o.kind == OP_LN) {
         o.ln.x = ws + o.lno.x; o.ln.out = ws + o.lno.out;
         o.ln.x_lo = nullptr; o.ln.out_lo = nullptr;
-        if (split) {
+        {
           const size_t pl = static_cast<size_t>(o.ln.rows) * o.ln.C * 2;
-          o.ln.x_lo = ws + o.lno.x + pl; o.ln.out_lo = ws + o.lno.out + pl;
+          if (o.lno.x_lo) o.ln.x_lo = ws + o.lno.x + pl;
+          if (o.lno.out_lo) o.ln.out_lo = ws + o.lno.out + pl;
         }
         o.ln.gamma = pf(o.lno.gamma); o.ln.beta = pf(o.lno.beta);
       } else if (o.kind == OP_ATTN) {
@@ -1085,7 +1094,7 @@ int Plan::prompt_prepare(const float* ehs, const float* aug, const int32_t* kv_l
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!ehs) { err = "ehs is null"; return DV_ERR_INVALID; }
   const size_t n = static_cast<size_t>(B) * Tp * cfg.cross_attention_dim;
-  DV_CK(K->launch_f32_to_bf16(ehs, ws + off_ehs, n, st, split ? ws + off_ehs + n * 2 : nullptr));
+  DV_CK(K->launch_f32_to_bf16(ehs, ws + off_ehs, n, st, triple ? ws + off_ehs + n * 2 : nullptr));
   // The captured loop reads the prompt-side tensors at fixed workspace addresses, so a new batch of the same shape
   // keeps the graph; only a change of WHICH optional inputs exist (their pointers are baked into the launches) drops it.
   const bool topo_changed = prompt_ready && (has_aug != (aug != nullptr) || has_kvlen != (kv_len != nullptr));
@@ -1108,7 +1117,7 @@ int Plan::set_cond(const float* cond, cudaStream_t st, std::string& err) {
   const int cc = cfg.in_channels - cfg.x_channels;
   if (cc <= 0) return DV_OK;
   DV_CK(K->launch_nct_to_ntc(cond, ws + off_xin, B, cc, T, cin_pad, cfg.x_channels, 1 << 30, 0, st,
-                          split ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
+                          triple ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
   return DV_OK;
 }
 
@@ -1169,7 +1178,7 @@ int Plan::forward(const float* sample, int x_only, const float* t, int t_stride,
   if (!bound) { err = "plan not bound"; return DV_ERR_STATE; }
   if (!prompt_ready) { err = "dv_prompt_prepare has not been called"; return DV_ERR_STATE; }
   DV_CK(K->launch_nct_to_ntc(sample, ws + off_xin, B, x_only ? cfg.x_channels : cfg.in_channels, T, cin_pad, 0, 1 << 30, 0, st,
-                          split ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
+                          triple ? ws + off_xin + static_cast<size_t>(B) * T * cin_pad * 2 : nullptr));
   if (tables_slot < 0) {
     int rc = enqueue_time_tables(t, t_stride, 0, st, err);
     if (rc != DV_OK) return rc;

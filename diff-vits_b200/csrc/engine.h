@@ -26,9 +26,10 @@ struct KernelApi {
 };
 const KernelApi& kernel_api(bool f16);
 
-struct TRef {  // bf16 channel-last tensor [B, L, C] at byte offset `off` of the workspace
+struct TRef {  // 16-bit channel-last tensor [B, L, C] at byte offset `off` of the workspace
   size_t off = 0;
   int L = 0, C = 0;
+  bool lo = false;   // followed by its lo plane (same shape, at + B*L*C*2 bytes): FP32X3 every tensor, FP16S the residual stream
   // GroupNorm partial statistics written by the producing GEMM's epilogue (offset inside the stats region)
   long long st_off = -1;
   int st_chunks = 0, st_nblk = 0, st_fold = 0;
@@ -106,8 +107,8 @@ struct Op {
   struct { const void* x; void* out; const float* gamma; const float* beta; int rows, C; float eps; const void* x_lo; void* out_lo; } ln;
   AttnParams at;
   // deferred (offset-based) descriptions resolved in bind()
-  struct { size_t x0, x1, out; long long st[2]; long long gamma, beta, ss; } gno;
-  struct { size_t x, out; long long gamma, beta; } lno;
+  struct { size_t x0, x1, out; long long st[2]; long long gamma, beta, ss; bool x_lo, out_lo; } gno;
+  struct { size_t x, out; long long gamma, beta; bool x_lo, out_lo; } lno;
   struct { size_t q, k, v, o; bool cross; } ato;
 };
 
@@ -115,8 +116,8 @@ struct Plan {
   dv_unet_cfg cfg;
   int B, T, Tp;
   int n_levels, emb_dim, cin_pad;
-  bool split = false;        // FP32X3 / FP16S: every 16-bit tensor [B, L, C] of the workspace is followed by its lo plane (same
-                             // shape, at + B*L*C*2 bytes): epilogues, norms and layout kernels read hi + lo and write both
+  bool split = false;        // FP32X3 / FP16S: tensors may carry a lo plane (TRef::lo): FP32X3 all of them, FP16S the residual stream
+                             // (block outputs, the transformer's z): epilogues and norms read hi + lo where it exists
   bool triple = false;       // FP32X3 only: weights carry a lo matrix too and every product is three MMAs (hi.hi + hi.lo + lo.hi);
                              // attention core in FP32. FP16S: one MMA on the hi planes (FP16 operands), tensor-core attention
   bool f16 = false;          // FP16S: the dv16 kernel set (FP16 operand format)

@@ -130,7 +130,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
   uint32_t packed[16];
   uint32_t packed_lo[SPLIT ? 16 : 1];
   // this thread's accumulator row is l = lq + lane of batch item rowbase / L: masked rows are stored as zeros
-  const bool row_keep = p.row_len == nullptr || (lq + e.lane) < __ldg(p.row_len + rowbase / p.L);
+  const bool row_keep = !TRIM || p.row_len == nullptr || (lq + e.lane) < __ldg(p.row_len + rowbase / p.L);
   float2 s0 = make_float2(0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {                      // 4 columns per iteration: one broadcast LDS.128 of bias
@@ -143,8 +143,10 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
       v = add_f32x2(v, h ? make_float2(bq.z, bq.w) : make_float2(bq.x, bq.y));
       if (HAS_RES) v = add_f32x2(v, make_float2(bf16_lo(rr[j >> 1]), bf16_hi(rr[j >> 1])));
       if (HAS_RES && SPLIT) v = add_f32x2(v, make_float2(bf16_lo(rrl[j >> 1]), bf16_hi(rrl[j >> 1])));
-      if (p.relu) v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
-      if (!row_keep) v = make_float2(0.f, 0.f);
+      if (TRIM) {                                         // rare-path instantiation: also ReLU / padding-row mask (prompt encoder)
+        if (p.relu) v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+        if (!row_keep) v = make_float2(0.f, 0.f);
+      }
       packed[j >> 1] = pack_bf16(v.x, v.y);
       if (SPLIT) packed_lo[j >> 1] = pack_bf16(v.x - bf16_lo(packed[j >> 1]), v.y - bf16_hi(packed[j >> 1]));
       if (HAS_STATS) {
@@ -613,6 +615,12 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
     return launch_bn<128, 16, false, true>(p, st);
   }
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
+  if (p.relu || p.row_len) {                             // prompt-encoder epilogue options live in the rare-path instantiation
+    if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
+    if (p.trim_col == 0) p.trim_col = 1 << 30;           // (no trimmed half row)
+    if (bn == 256 && p.n_pad % 256 == 0) return launch_bn<256, 16, true>(p, st);
+    return launch_bn<128, 16, true>(p, st);
+  }
   if (p.trim_col > 0 || !dense) {                        // odd-length folded upsample conv: its own instantiations
     if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
     if (bn == 256 && p.n_pad % 256 == 0) return launch_bn<256, 16, true>(p, st);

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const GnParams p, int rows
         if (SPLIT) yl[j] = pack_bf16(a - bf16_lo(y[j]), c - bf16_hi(y[j]));
       }
       *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * p.L + l) * C + cbase) = make_uint4(y[0], y[1], y[2], y[3]);
-      if (SPLIT)
+      if (SPLIT && p.out_lo != nullptr)
         *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + (static_cast<size_t>(b) * p.L + l) * C + cbase) =
             make_uint4(yl[0], yl[1], yl[2], yl[3]);
     }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
       o.x = pack_bf16(y0, y1);
       o.y = pack_bf16(y2, y3);
       orow[lane + 32 * i] = o;
-      if (SPLIT) {
+      if (SPLIT && out_lo != nullptr) {
         uint2 ol;
         ol.x = pack_bf16(y0 - bf16_lo(o.x), y1 - bf16_hi(o.x));
         ol.y = pack_bf16(y2 - bf16_lo(o.y), y3 - bf16_hi(o.y));
@@ -379,10 +379,13 @@ cudaError_t launch_gn_apply(const GnParams& p, cudaStream_t st) {
   int rows = 4 * (NT / (C >> 3));
   if (rows < 4) rows = 4;
   dim3 grid((p.L + rows - 1) / rows, p.B);
-  if (p.out_lo != nullptr) {
-    if (!p.x0_lo || (p.c1 && !p.x1_lo)) return cudaErrorInvalidValue;
+  // SPLIT kernel: the input is hi + lo (FP32X3: every tensor; FP16S: residual-stream tensors); the lo plane of the output is
+  // written only where the consumer is not the tensor core alone (out_lo != nullptr)
+  if (p.x0_lo != nullptr) {
+    if (p.c1 && !p.x1_lo) return cudaErrorInvalidValue;
     return launch_k(gn_apply_kernel<true>, grid, dim3(NT), 0, st, p, rows);
   }
+  if (p.out_lo != nullptr) return cudaErrorInvalidValue;
   return launch_k(gn_apply_kernel<false>, grid, dim3(NT), 0, st, p, rows);
 }
 cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const float* beta, int rows, int C,
@@ -393,10 +396,10 @@ cudaError_t launch_layernorm(const void* x, void* out, const float* gamma, const
   __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
   const int rpc = LN_WARPS * (C <= 256 ? 4 : 2);   // rows per CTA, matches LN_ROWS in the kernel
   dim3 grid((rows + rpc - 1) / rpc);
-  if ((x_lo == nullptr) != (out_lo == nullptr)) return cudaErrorInvalidValue;
+  if (x_lo == nullptr && out_lo != nullptr) return cudaErrorInvalidValue;
 #define DV_LN_CASE(CH)                                                                                                   \
   case CH * 128:                                                                                                         \
-    return out_lo ? launch_k(layernorm_kernel<CH, true>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps, xl, ol) \
+    return x_lo ? launch_k(layernorm_kernel<CH, true>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps, xl, ol) \
                   : launch_k(layernorm_kernel<CH, false>, grid, dim3(256), 0, st, xi, oo, gamma, beta, rows, eps, xl, ol);
   switch (C) {
     DV_LN_CASE(1)
