@@ -80,6 +80,12 @@ size_t dv_plan_param_bytes(const dv_plan* plan) { return plan ? plan->impl.param
 const char* dv_plan_manifest_json(const dv_plan* plan) { return plan ? plan->impl.manifest.c_str() : ""; }
 int dv_plan_launches_per_forward(const dv_plan* plan) { return plan ? static_cast<int>(plan->impl.ops.size()) + 3 : 0; }
 int dv_plan_last_sample_launches(const dv_plan* plan) { return plan ? plan->impl.last_sample_launches : 0; }
+int dv_plan_sample_diag(const dv_plan* plan, size_t* offset, int* rows) {
+  if (!plan || !offset || !rows) return fail(DV_ERR_INVALID, "null argument");
+  *offset = plan->impl.off_diag_rows;
+  *rows = plan->impl.last_diag_rows;
+  return DV_OK;
+}
 
 int dv_plan_bind(dv_plan* plan, void* workspace, const void* params, void* stream) {
   if (!plan) return fail(DV_ERR_INVALID, "null plan");

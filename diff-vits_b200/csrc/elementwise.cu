@@ -150,11 +150,69 @@ __device__ __forceinline__ float roundtrip(float x, float m, float alp, float si
   return __fdiv_rn(__fsub_rn(x, __fmul_rn(sig, eps)), alp);
 }
 
-__global__ void __launch_bounds__(256) axpbypcz_kernel(float* xo, const float* x, float* m1,
-                                                       const float* __restrict__ m0, float a, float b, float c,
-                                                       int rt, float alp, float sig, size_t n) {
+
+// ---- sampler diagnostics (replaces the reference's syncing `assert torch.isnan(x).any() == False`, model3.py:903):
+// every update kernel counts the non-finite values among the model output it consumes and the state it writes, and
+// takes their sums of squares: per-thread accumulators -> warp shuffle tree -> the 8 warps of the CTA through shared memory
+// (fixed order, no atomics) -> ONE 16-byte store per CTA into this launch's row of partials; diag_reduce_kernel folds the
+// rows once, after the loop. part == nullptr: diagnostics off (the stand-alone C-ABI entry points).
+struct DiagAcc { float bad = 0.f, sm = 0.f, sx = 0.f; };
+__device__ __forceinline__ float nonfinite(float v) { return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u ? 1.f : 0.f; }
+__device__ __forceinline__ void diag_add(DiagAcc& d, float m, float r) {
+  d.bad += nonfinite(m) + nonfinite(r);
+  d.sm = fmaf(m, m, d.sm);
+  d.sx = fmaf(r, r, d.sx);
+}
+__device__ __forceinline__ void diag_add4(DiagAcc& d, const float4& m, const float4& r) {
+  diag_add(d, m.x, r.x); diag_add(d, m.y, r.y); diag_add(d, m.z, r.z); diag_add(d, m.w, r.w);
+}
+__device__ __forceinline__ void diag_store(float4* part, DiagAcc d, float kind) {   // all 256 threads of the CTA
+  __shared__ float sh[8][3];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    d.bad += __shfl_xor_sync(0xffffffffu, d.bad, o);
+    d.sm += __shfl_xor_sync(0xffffffffu, d.sm, o);
+    d.sx += __shfl_xor_sync(0xffffffffu, d.sx, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = d.bad; sh[threadIdx.x >> 5][1] = d.sm; sh[threadIdx.x >> 5][2] = d.sx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f, m = 0.f, x = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { b += sh[w][0]; m += sh[w][1]; x += sh[w][2]; }
+    part[blockIdx.x] = make_float4(b, m, x, kind);
+  }
+}
+// rows[j] = fold of the `per_row` CTA partials of update launch j: {non-finite count, sum m^2, sum x^2, kernel kind}
+__global__ void __launch_bounds__(256) diag_reduce_kernel(const float4* __restrict__ part, float4* __restrict__ rows, int per_row) {
   pdl_launch_dependents();
   pdl_wait();
+  __shared__ float sh[8][3];
+  const float4* p = part + static_cast<size_t>(blockIdx.x) * per_row;
+  DiagAcc d;
+  for (int i = threadIdx.x; i < per_row; i += 256) { const float4 v = p[i]; d.bad += v.x; d.sm += v.y; d.sx += v.z; }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    d.bad += __shfl_xor_sync(0xffffffffu, d.bad, o);
+    d.sm += __shfl_xor_sync(0xffffffffu, d.sm, o);
+    d.sx += __shfl_xor_sync(0xffffffffu, d.sx, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = d.bad; sh[threadIdx.x >> 5][1] = d.sm; sh[threadIdx.x >> 5][2] = d.sx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f, m = 0.f, x = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { b += sh[w][0]; m += sh[w][1]; x += sh[w][2]; }
+    rows[blockIdx.x] = make_float4(b, m, x, p[0].w);
+  }
+}
+
+__global__ void __launch_bounds__(256) axpbypcz_kernel(float* xo, const float* x, float* m1,
+                                                       const float* __restrict__ m0, float a, float b, float c,
+                                                       int rt, float alp, float sig, size_t n, float4* diag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  DiagAcc dg;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -173,6 +231,7 @@ __global__ void __launch_bounds__(256) axpbypcz_kernel(float* xo, const float* x
         r.x += c * pv.x; r.y += c * pv.y; r.z += c * pv.z; r.w += c * pv.w;
       }
       st4(xo, i, r);
+      diag_add4(dg, mv, r);
     } else {
       for (size_t k = i; k < n; ++k) {
         float mv = m1[k];
@@ -180,17 +239,20 @@ __global__ void __launch_bounds__(256) axpbypcz_kernel(float* xo, const float* x
         float r = a * x[k] + b * mv;
         if (m0) r += c * m0[k];
         xo[k] = r;
+        diag_add(dg, mv, r);
       }
     }
   }
+  if (diag) diag_store(diag, dg, 0.f);
 }
 
 __global__ void __launch_bounds__(256) unipc_pred_kernel(float* xp, float* __restrict__ base,
                                                          const float* x, const float* __restrict__ m1,
                                                          const float* __restrict__ m0, float a, float b, float cp,
-                                                         float cc, int has_m0, size_t n) {
+                                                         float cc, int has_m0, size_t n, float4* diag) {
   pdl_launch_dependents();
   pdl_wait();
+  DiagAcc dg;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -206,22 +268,26 @@ __global__ void __launch_bounds__(256) unipc_pred_kernel(float* xp, float* __res
       }
       st4(xp, i, p);
       if (base) st4(base, i, q);
+      diag_add4(dg, mv, p);
     } else {
       for (size_t k = i; k < n; ++k) {
         const float xb = a * x[k] + b * m1[k];
         const float d = has_m0 ? (m0[k] - m1[k]) : 0.f;
         xp[k] = xb + cp * d;
         if (base) base[k] = xb + cc * d;
+        diag_add(dg, m1[k], xb + cp * d);
       }
     }
   }
+  if (diag) diag_store(diag, dg, 1.f);
 }
 
 __global__ void __launch_bounds__(256) unipc_corr_kernel(float* __restrict__ x, const float* __restrict__ base,
                                                          const float* __restrict__ mt, const float* __restrict__ m1,
-                                                         float d, size_t n) {
+                                                         float d, size_t n, float4* diag) {
   pdl_launch_dependents();
   pdl_wait();
+  DiagAcc dg;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -230,10 +296,16 @@ __global__ void __launch_bounds__(256) unipc_corr_kernel(float* __restrict__ x, 
       r.x = bv.x + d * (tv.x - mv.x); r.y = bv.y + d * (tv.y - mv.y);
       r.z = bv.z + d * (tv.z - mv.z); r.w = bv.w + d * (tv.w - mv.w);
       st4(x, i, r);
+      diag_add4(dg, tv, r);
     } else {
-      for (size_t k = i; k < n; ++k) x[k] = base[k] + d * (mt[k] - m1[k]);
+      for (size_t k = i; k < n; ++k) {
+        const float r = base[k] + d * (mt[k] - m1[k]);
+        x[k] = r;
+        diag_add(dg, mt[k], r);
+      }
     }
   }
+  if (diag) diag_store(diag, dg, 2.f);
 }
 
 inline int ew_grid(size_t n) {
@@ -273,16 +345,22 @@ cudaError_t launch_temb(const TembParams& p, cudaStream_t st) {
 }
 
 cudaError_t launch_axpbypcz(float* x_out, const float* x, float* m1, const float* m0, float a, float b, float c,
-                            int roundtrip_flag, float alp, float sig, size_t n, cudaStream_t st) {
-  return launch_k(axpbypcz_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x_out, x, m1, m0, a, b, c, roundtrip_flag, alp, sig, n);
+                            int roundtrip_flag, float alp, float sig, size_t n, cudaStream_t st, float* diag) {
+  return launch_k(axpbypcz_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x_out, x, m1, m0, a, b, c, roundtrip_flag, alp, sig, n,
+                  reinterpret_cast<float4*>(diag));
 }
 cudaError_t launch_unipc_pred(float* xpred, float* base, const float* x, const float* m1, const float* m0, float a,
-                              float b, float cp, float cc, int has_m0, size_t n, cudaStream_t st) {
-  return launch_k(unipc_pred_kernel, dim3(ew_grid(n)), dim3(256), 0, st, xpred, base, x, m1, m0, a, b, cp, cc, has_m0, n);
+                              float b, float cp, float cc, int has_m0, size_t n, cudaStream_t st, float* diag) {
+  return launch_k(unipc_pred_kernel, dim3(ew_grid(n)), dim3(256), 0, st, xpred, base, x, m1, m0, a, b, cp, cc, has_m0, n,
+                  reinterpret_cast<float4*>(diag));
 }
 cudaError_t launch_unipc_corr(float* x, const float* base, const float* mt, const float* m1, float d, size_t n,
-                              cudaStream_t st) {
-  return launch_k(unipc_corr_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x, base, mt, m1, d, n);
+                              cudaStream_t st, float* diag) {
+  return launch_k(unipc_corr_kernel, dim3(ew_grid(n)), dim3(256), 0, st, x, base, mt, m1, d, n, reinterpret_cast<float4*>(diag));
+}
+int sampler_diag_ctas(size_t n) { return ew_grid(n); }
+cudaError_t launch_diag_reduce(const float* part, float* rows, int nrows, int per_row, cudaStream_t st) {
+  return launch_k(diag_reduce_kernel, dim3(nrows), dim3(256), 0, st, reinterpret_cast<const float4*>(part), reinterpret_cast<float4*>(rows), per_row);
 }
 
 }  // namespace DV_NS

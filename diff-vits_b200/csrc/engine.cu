@@ -683,6 +683,9 @@ int Plan::build(std::string& err) {
   off_h0 = b.ws_alloc(obytes);
   off_h1 = b.ws_alloc(obytes);
   off_ttab = b.ws_alloc(4096 * 4);
+  diag_ctas = sampler_diag_ctas(static_cast<size_t>(B) * c.x_channels * T);
+  off_diag_part = b.ws_alloc(static_cast<size_t>(DIAG_MAX_ROWS) * diag_ctas * 16);
+  off_diag_rows = b.ws_alloc(static_cast<size_t>(DIAG_MAX_ROWS) * 16);
 
   // ---- time embedding parameters (fp32; tiny GEMVs on CUDA cores)
   p_freqs = b.slot("time.freqs", "time_freqs", {}, "f32", {C0 / 2});
@@ -1196,7 +1199,7 @@ static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
 
 // One model evaluation per step (NFE == nsteps); history slots rotate by pointer at enqueue time.
 int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cudaStream_t s, int* launches,
-                       std::string& err) {
+                       std::string& err, int* diag_rows) {
   const size_t n = static_cast<size_t>(B) * cfg.x_channels * T;
   float* X = reinterpret_cast<float*>(ws + off_x);
   float* XP = reinterpret_cast<float*>(ws + off_xp);
@@ -1204,6 +1207,12 @@ int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cuda
   float* H[2] = {reinterpret_cast<float*>(ws + off_h0), reinterpret_cast<float*>(ws + off_h1)};
   const float* ttab = reinterpret_cast<const float*>(ws + off_ttab);
   int cur = 0;  // H[cur] = newest model output m_{-1}, H[cur^1] = m_{-2}
+  // sampler diagnostics: update launch j writes its per-CTA partials into row j (rows past DIAG_MAX_ROWS are not recorded)
+  int drow = 0;
+  auto diag = [&]() -> float* {
+    if (!diag_rows || drow >= DIAG_MAX_ROWS) return nullptr;
+    return reinterpret_cast<float*>(ws + off_diag_part) + static_cast<size_t>(drow++) * diag_ctas * 4;
+  };
   // Denoiser calls of the loop in order: call 0 at ttab[0], then one at ttab[i+1] for every step that evaluates the
   // model. The time tables of call k+1 depend on t only: they are computed on a side stream while call k runs.
   std::vector<int> tcall(1, 0);
@@ -1247,7 +1256,7 @@ int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cuda
     const bool last = (i == nsteps - 1);
     if (sampler == DV_SAMPLER_DPMPP_2M) {
       const bool has_prev = c[3] != 0.f;
-      DV_CK(launch_axpbypcz(X, X, H[cur], has_prev ? H[cur ^ 1] : nullptr, c[0], c[1], c[2], rt ? 1 : 0, c[4], c[5], n, s));
+      DV_CK(launch_axpbypcz(X, X, H[cur], has_prev ? H[cur ^ 1] : nullptr, c[0], c[1], c[2], rt ? 1 : 0, c[4], c[5], n, s, diag()));
       ++*launches;
       if (!last) {
         cur ^= 1;
@@ -1258,18 +1267,26 @@ int Plan::enqueue_loop(int sampler, int nsteps, const float* coef, bool rt, cuda
       const bool has_prev = c[5] != 0.f, use_corr = c[6] != 0.f;
       if (use_corr) {
         if (last) { err = "UniPC table: corrector on the last step"; return DV_ERR_INVALID; }
-        DV_CK(launch_unipc_pred(XP, BASE, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
+        DV_CK(launch_unipc_pred(XP, BASE, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s, diag()));
         ++*launches;
         rc = model(XP, H[cur ^ 1]);  // m_t overwrites the consumed m_{-2}
         if (rc != DV_OK) return rc;
-        DV_CK(launch_unipc_corr(X, BASE, H[cur ^ 1], H[cur], c[4], n, s));
+        DV_CK(launch_unipc_corr(X, BASE, H[cur ^ 1], H[cur], c[4], n, s, diag()));
         ++*launches;
         cur ^= 1;
       } else {
-        DV_CK(launch_unipc_pred(X, nullptr, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s));
+        DV_CK(launch_unipc_pred(X, nullptr, X, H[cur], H[cur ^ 1], c[0], c[1], c[2], c[3], has_prev ? 1 : 0, n, s, diag()));
         ++*launches;
       }
     }
+  }
+  if (diag_rows) {
+    if (drow) {
+      DV_CK(launch_diag_reduce(reinterpret_cast<const float*>(ws + off_diag_part), reinterpret_cast<float*>(ws + off_diag_rows), drow,
+                               diag_ctas, s));
+      ++*launches;
+    }
+    *diag_rows = drow;
   }
   return DV_OK;
 }
@@ -1298,6 +1315,7 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
     if (p->cfg.x_channels != p->cfg.out_channels) { err = "sampler needs x_channels == out_channels"; return DV_ERR_INVALID; }
   }
   const bool rt = (flags & DV_SAMPLE_ROUNDTRIP) != 0;
+  const bool dg = (flags & DV_SAMPLE_NO_DIAG) == 0;
   Plan* lead = plans[0];
   for (int i = 0; i < n; ++i) {
     Plan* p = plans[i];
@@ -1315,6 +1333,7 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
     key = fnv1a(key, &sampler, sizeof sampler);
     key = fnv1a(key, &nsteps, sizeof nsteps);
     key = fnv1a(key, &rt, sizeof rt);
+    key = fnv1a(key, &dg, sizeof dg);
     { const int sk = skip_kinds_mask(); key = fnv1a(key, &sk, sizeof sk); }
     key = fnv1a(key, coef, static_cast<size_t>(nsteps) * 8 * 4);
     key = fnv1a(key, plans, static_cast<size_t>(n) * sizeof(Plan*));
@@ -1329,8 +1348,10 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
   if (eager) {
     int launches = 0;
     for (int i = 0; i < n; ++i) {
-      int rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, st, &launches, err);
+      int rows = 0;
+      int rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, st, &launches, err, dg ? &rows : nullptr);
       if (rc != DV_OK) return rc;
+      plans[i]->last_diag_rows = rows;
     }
     lead->last_sample_launches = launches;
   } else {
@@ -1350,7 +1371,7 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
       if (n > 1) ce = cudaEventRecord(lead->ev_fork, s0);
       for (int i = 1; i < n && ce == cudaSuccess; ++i) ce = cudaStreamWaitEvent(plans[i]->cap_stream, lead->ev_fork, 0);
       for (int i = 0; i < n && rc == DV_OK && ce == cudaSuccess; ++i)
-        rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, plans[i]->cap_stream, &launches, err);
+        rc = plans[i]->enqueue_loop(sampler, nsteps, coef, rt, plans[i]->cap_stream, &launches, err, dg ? &plans[i]->graph_diag_rows : nullptr);
       for (int i = 1; i < n && ce == cudaSuccess; ++i) {   // always join, also on failure, so the capture can end
         ce = cudaEventRecord(plans[i]->ev_join, plans[i]->cap_stream);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s0, plans[i]->ev_join, 0);
@@ -1371,6 +1392,7 @@ int sample_group(Plan* const* plans, int n, int sampler, int nsteps, const float
     }
     DV_CK(cudaGraphLaunch(lead->graph_exec, st));
     lead->last_sample_launches = lead->graph_launches;
+    for (int i = 0; i < n; ++i) plans[i]->last_diag_rows = dg ? plans[i]->graph_diag_rows : 0;
   }
   for (int i = 0; i < n; ++i) {
     Plan* p = plans[i];

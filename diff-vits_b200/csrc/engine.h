@@ -145,6 +145,8 @@ struct Plan {
   // workspace regions (byte offsets)
   size_t off_xin = 0, off_ehs = 0, off_aug = 0, off_embact = 0, off_ss = 0, off_stats = 0, off_kvlen = 0;
   size_t off_x = 0, off_xp = 0, off_base = 0, off_h0 = 0, off_h1 = 0, off_ttab = 0;
+  size_t off_diag_part = 0, off_diag_rows = 0;   // sampler diagnostics: per-CTA partials [DIAG_MAX_ROWS][diag_ctas][4], folded rows [DIAG_MAX_ROWS][4]
+  int diag_ctas = 0;
   size_t stats_bytes = 0;
   int n_all = 0;  // total time_emb_proj outputs
   long long p_freqs = -1, p_w1 = -1, p_b1 = -1, p_w2 = -1, p_b2 = -1, p_wall = -1, p_ball = -1;
@@ -155,6 +157,7 @@ struct Plan {
   const uint8_t* params = nullptr;
   bool bound = false, prompt_ready = false, has_aug = false, has_kvlen = false;
   int last_sample_launches = 0;
+  int last_diag_rows = 0;    // rows of sampler diagnostics the most recent dv_sample wrote (0: switched off)
 
   // graph cache for dv_sample
   cudaGraphExec_t graph_exec = nullptr;
@@ -168,6 +171,7 @@ struct Plan {
   uint64_t pending_key = 0;   // loop seen once (run eagerly): it is captured when it comes back
   uint64_t graph_epoch = 0;   // bumped whenever launches baked into a captured graph become stale
   int graph_launches = 0;
+  int graph_diag_rows = 0;
 
   int build(std::string& err);
   int bind(void* workspace, const void* params, cudaStream_t st, std::string& err);
@@ -186,8 +190,9 @@ struct Plan {
   int sample(int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags, cudaStream_t st,
              std::string& err);
   // the N-step loop (denoiser calls + sampler updates) of this plan, enqueued on `s` (no copies, no graph handling)
+  // diag_rows != nullptr: sampler diagnostics on, *diag_rows = rows written (one per update launch, <= DIAG_MAX_ROWS)
   int enqueue_loop(int sampler, int nsteps, const float* coef, bool roundtrip, cudaStream_t s, int* launches,
-                   std::string& err);
+                   std::string& err, int* diag_rows = nullptr);
   ~Plan();
 };
 
@@ -198,6 +203,8 @@ std::string manifest_json(const std::vector<ParamSlot>& slots);
 
 // PromptEncoder (model3.py:382-433): the speech-prompt encoder that produces encoder_hidden_states, as a plan of the same
 // kernels (csrc/prompt_encoder.cu). Channel-last [B, Tp, 128] throughout = the layout the UNet's cross-attention reads.
+constexpr int DIAG_MAX_ROWS = 512;   // update launches of one loop that get a diagnostics row (50-step DPM++: 50, 25-step UniPC: 49)
+
 struct PromptPlan {
   dv_prompt_cfg cfg;
   int B = 0, Tp = 0, device = -1;

@@ -309,6 +309,20 @@ class DenoiserEngine:
                                  C.cast(c_host.data_ptr(), fp), _ptr(x), flags, _stream(self.device)))
         return x
 
+    def sample_diag(self) -> torch.Tensor:
+        """Sampler diagnostics of the most recent `sample`: fp32 [rows, 4] view into the workspace (device), row j = j-th
+        sampler-update launch: {non-finite count, sum of squares of the denoiser output it consumed, sum of squares of
+        the state it wrote, kernel 0 DPM++ / 1 UniPC predictor / 2 UniPC corrector}. Reduced on the device inside the
+        update kernels (dv_plan_sample_diag); reading it is the only synchronising step."""
+        off, rows = C.c_size_t(), C.c_int()
+        check(self.lib.dv_plan_sample_diag(self._plan, C.byref(off), C.byref(rows)))
+        return self.workspace[off.value: off.value + rows.value * 16].view(torch.float32).view(rows.value, 4)
+
+    def check_finite(self) -> None:
+        """The reference asserts `torch.isnan(x).any() == False` on every denoiser call (model3.py:903, one device sync per
+        step); here the update kernels count non-finite values and one read after the loop raises the same AssertionError."""
+        _raise_nonfinite([self.sample_diag()])
+
     # ---- debug: block outputs left in the workspace by the last denoiser call
     def named_tensors(self) -> Dict[str, torch.Tensor]:
         """{reference module path: bf16 [B, L, C] view into the workspace}."""
@@ -355,6 +369,17 @@ class DenoiserEngine:
     @property
     def last_sample_launches(self) -> int:
         return self.lib.dv_plan_last_sample_launches(self._plan)
+
+
+def _raise_nonfinite(diags) -> None:
+    if not diags or diags[0].numel() == 0:
+        return
+    bad = torch.stack([d[:, 0] for d in diags]).sum(0).cpu()      # one small D2H (<= 2 KB) after the loop
+    if bool((bad != 0).any()) or bool(torch.isnan(bad).any()):
+        j = int(torch.nonzero((bad != 0) | torch.isnan(bad))[0])
+        raise AssertionError(f"non-finite values in the denoising loop, first seen by sampler update {j} "
+                             f"({int(bad[j]) if bad[j] == bad[j] else 'nan'} values); the reference asserts "
+                             "torch.isnan(x).any() == False per call (model3.py:903)")
 
 
 # ------------------------------------------------------------------------------------------------ lanes
@@ -444,6 +469,17 @@ class DenoiserGroup:
         check(self.lib.dv_sample_group(plans, n, sampler, nsteps, C.cast(t_host.data_ptr(), fp),
                                        C.cast(c_host.data_ptr(), fp), xs, flags, _stream(self.device)))
         return x
+
+    def sample_diag(self) -> torch.Tensor:
+        """Diagnostics rows of lane 0 with the counts / sums of all lanes added (see DenoiserEngine.sample_diag)."""
+        d = [e.sample_diag() for e in self.engines]
+        out = d[0].clone()
+        for o in d[1:]:
+            out[:, :3] += o[:, :3]
+        return out
+
+    def check_finite(self) -> None:
+        _raise_nonfinite([e.sample_diag() for e in self.engines])
 
     def named_tensors(self) -> Dict[str, torch.Tensor]:
         outs = [e.named_tensors() for e in self.engines]

@@ -7,6 +7,7 @@ libdiffvits_b200; called directly it runs one native denoiser call.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -32,6 +33,9 @@ class NativeDenoiser:
         self.engine: DenoiserGroup = unet.native_engine(B, T, Tp, x_channels=self.x_channels, private=True,
                                                         lanes=lanes)
         self.calls = 0
+        # the reference asserts "no NaN" on every denoiser call (model3.py:903); the native loop reduces that on the device
+        # and the drop-in solvers read it once with the result (DV_CHECK_FINITE=0 skips the read)
+        self.check_finite = os.environ.get("DV_CHECK_FINITE", "1") != "0"
         self.rebind(cond, ehs, kv_len, aug)
 
     def rebind(self, cond: torch.Tensor, ehs: torch.Tensor, kv_len: Optional[torch.Tensor] = None,
@@ -110,9 +114,12 @@ NATIVE_LOOPS = 0
 
 
 def tick_progress(native: NativeDenoiser, n: int) -> None:
-    """Advance the reference's tqdm bar (model3.py:1133, 1167) by the number of model evaluations done natively."""
+    """Advance the reference's tqdm bar (model3.py:1133, 1167) by the number of model evaluations done natively, and
+    raise the reference's per-call NaN assertion (model3.py:903) from the loop's device-side diagnostics."""
     global NATIVE_LOOPS
     NATIVE_LOOPS += 1
+    if getattr(native, "check_finite", False):
+        native.engine.check_finite()
     owner = getattr(native, "progress_owner", None)
     bar = getattr(owner, "bar", None) if owner is not None else None
     if bar is not None and hasattr(bar, "update"):
@@ -140,7 +147,8 @@ def sample_native(unet, x_T: torch.Tensor, cond: torch.Tensor, ehs: torch.Tensor
                   order: int = 2, skip_type: str = "time_uniform", betas: Optional[torch.Tensor] = None,
                   noise_schedule: Optional[NoiseScheduleVP] = None, lower_order_final: bool = True,
                   solver_type: str = "dpmsolver", variant: str = "bh2", graph: bool = True,
-                  roundtrip: bool = False, native: Optional[NativeDenoiser] = None) -> torch.Tensor:
+                  roundtrip: bool = False, native: Optional[NativeDenoiser] = None,
+                  check_finite: bool = False) -> torch.Tensor:
     """Explicit entry to the native loop: the reference's `NaturalSpeech2.sample` body (model3.py:1121-1193) from the
     drawn noise `x_T` [B, 100, T] to the final latent, for sampler in {"dpmsolver++", "unipc"}."""
     if noise_schedule is None:
@@ -160,4 +168,7 @@ def sample_native(unet, x_T: torch.Tensor, cond: torch.Tensor, ehs: torch.Tensor
     else:
         raise ValueError(f"unknown sampler {sampler!r}")
     x = x_T.to(native.engine.device, torch.float32).contiguous().clone()
-    return native.engine.sample(kind, t_in, coef, x, graph=graph, roundtrip=roundtrip)
+    out = native.engine.sample(kind, t_in, coef, x, graph=graph, roundtrip=roundtrip)
+    if check_finite:                  # synchronises; `native.engine.sample_diag()` has the per-update norms as well
+        native.engine.check_finite()
+    return out

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DV_VERSION 101
+#define DV_VERSION 102
 
 #if defined(__GNUC__)
 #define DV_API __attribute__((visibility("default")))
@@ -121,6 +121,7 @@ DV_API int dv_unet_forward(dv_plan* plan, const float* sample, int x_only, const
 #define DV_SAMPLER_UNIPC_BH2 1
 #define DV_SAMPLE_NO_GRAPH 1     /* enqueue directly instead of capturing/replaying a graph */
 #define DV_SAMPLE_ROUNDTRIP 2    /* DPM++ only: reproduce the reference's x0->eps->x0 round trip bit for bit */
+#define DV_SAMPLE_NO_DIAG 4      /* do not record the sampler diagnostics (dv_plan_sample_diag) */
 DV_API int dv_sample(dv_plan* plan, int sampler, int nsteps, const float* t_in, const float* coef, float* x, int flags,
               void* stream);
 /* The same loop for `nplans` plans at once ("lanes": disjoint slices of one batch of independent utterances - the path
@@ -131,6 +132,14 @@ DV_API int dv_sample_group(dv_plan* const* plans, int nplans, int sampler, int n
                            const float* coef, float* const* x, int flags, void* stream);
 /* Kernel launches enqueued by the most recent dv_sample / dv_sample_group (reported on plans[0]). */
 DV_API int dv_plan_last_sample_launches(const dv_plan* plan);
+/* Sampler diagnostics of the most recent dv_sample on this plan. Replaces the reference's per-call, device-synchronising
+ * `assert torch.isnan(x).any() == False` (model3.py:903): every sampler-update kernel also reduces (warp shuffles -> CTA ->
+ * one fixed-order fold after the loop; no atomics, no synchronisation) the denoiser output it consumes and the state it
+ * writes. Row j (fp32 x 4, at byte `offset + 16 j` of the workspace, j < rows <= 512) belongs to the j-th update launch of the
+ * loop: {count of non-finite values, sum of squares of the denoiser output, sum of squares of the new state, kernel
+ * (0 DPM-Solver++ update, 1 UniPC predictor, 2 UniPC corrector)}. Valid once the stream has passed the loop; the caller reads
+ * them with the latent (the drop-in raises the reference's AssertionError from them). */
+DV_API int dv_plan_sample_diag(const dv_plan* plan, size_t* offset, int* rows);
 
 /* ---- PromptEncoder (model3.py:382-433; model.py:72-97, 137-171; operations.py:644-714, 784-821) ---------------------------
  * The speech-prompt encoder whose output is the UNet's encoder_hidden_states: ConvLayer pre (LayerNorm + 1x1), n_layers x

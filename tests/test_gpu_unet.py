@@ -342,6 +342,62 @@ def test_dropin_sampler_api_runs_native(env, dropin):
     assert torch.equal(d, e)
 
 
+def test_sampler_diagnostics_and_nan_assertion(env, dropin):
+    """Device-side sampler diagnostics (north_star item 3: reductions inside the update kernels) that stand in for the
+    reference's per-call `assert torch.isnan(x).any() == False` (model3.py:903): one row per sampler-update launch with
+    the non-finite count and the sums of squares of the denoiser output consumed / the state written. Checked against
+    torch on a host-driven replay of the same loop, identical between graph replay and direct enqueue, and a NaN put
+    into the conditioning raises the reference's AssertionError from the drop-in solver."""
+    import diffvits_b200
+    from diffvits_b200.engine import SAMPLER_DPMPP_2M, SAMPLER_UNIPC_BH2
+    from diffvits_b200.schedule import (NoiseScheduleVP, dpmpp_multistep_table, get_time_steps, unipc_multistep_table)
+    unet = env["unet"]
+    x_T, cond, ehs = env["inputs"].make_inputs(2, 72, 40, seed=8)
+    betas = env["inputs"].betas_linear()
+    native = diffvits_b200.NativeDenoiser(unet, cond.cuda(), ehs.cuda())
+    eng = native.engine
+    ns = NoiseScheduleVP("discrete", betas=betas)
+    for sampler, steps, want_rows in (("dpmsolver++", 12, 12), ("unipc", 6, 11)):
+        ts = get_time_steps(ns, "time_uniform", ns.T, 1.0 / ns.total_N, steps, "cpu")
+        if sampler == "dpmsolver++":
+            t_in, coef = dpmpp_multistep_table(ns, ts, 2, True, "dpmsolver")
+            kind = SAMPLER_DPMPP_2M
+        else:
+            t_in, coef = unipc_multistep_table(ns, ts, 2, True, "bh2")
+            kind = SAMPLER_UNIPC_BH2
+        diags = []
+        for graph in (False, True, True):          # first sight: direct enqueue; third call: graph replay
+            out = eng.sample(kind, t_in, coef, x_T.cuda().clone(), graph=graph)
+            diags.append(eng.sample_diag().cpu().clone())
+        d = diags[0]
+        assert d.shape == (want_rows, 4), d.shape
+        assert torch.equal(diags[0], diags[1]) and torch.equal(diags[0], diags[2])     # fixed-order reductions
+        assert float(d[:, 0].abs().sum()) == 0.0
+        # last row: the state it wrote is the returned latent
+        assert abs(float(d[-1, 2]) / float((out.double() ** 2).sum()) - 1.0) < 1e-5
+        if sampler == "dpmsolver++":
+            assert set(d[:, 3].tolist()) == {0.0}
+            # row 0 consumed the first denoiser output m0 = model(x_T, t_0)
+            m0 = native(x_T.cuda(), t_in[:1].cuda())
+            assert abs(float(d[0, 1]) / float((m0.double() ** 2).sum()) - 1.0) < 1e-5
+        else:
+            assert d[:, 3].tolist() == [1.0, 2.0] * 5 + [1.0]      # predictor + corrector per step, last step predictor only
+        eng.check_finite()
+    # a NaN in the conditioning: the loop runs to the end (no per-step sync), the solver raises like the reference would
+    bad = cond.clone()
+    bad[1, 3, 5] = float("nan")
+    native.rebind(bad.cuda(), ehs.cuda())
+    dpm = dropin["dpm"]
+    ns2 = dpm.NoiseScheduleVP("discrete", betas=betas)
+    solver = dpm.DPM_Solver(dpm.model_wrapper(native, ns2, model_type="x_start", model_kwargs={}), ns2,
+                            algorithm_type="dpmsolver++")
+    with pytest.raises(AssertionError, match="non-finite"):
+        solver.sample(x_T.cuda(), steps=6, order=2, skip_type="time_uniform", method="multistep")
+    assert float(eng.sample_diag()[0, 0]) > 0
+    native.check_finite = False
+    solver.sample(x_T.cuda(), steps=6, order=2, skip_type="time_uniform", method="multistep")     # opt-out: no read
+
+
 def test_batch_consistency_at_bench_size(env):
     """Size-independent property at the benchmark shape (B=32, T=1000): every utterance of the batch equals the same
     utterance run alone (no cross-sample reduction exists on the path), which also covers multi-GPU sharding."""
