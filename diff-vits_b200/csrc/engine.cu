@@ -120,6 +120,38 @@ struct Builder {
     return t;
   }
   void scratch_reset() { scratch_cur = 0; }
+  // Normalised tensors written by the LAST GEMM of one block and read by the FIRST GEMM of the next (fused output GroupNorm
+  // across a block boundary) cannot live in the per-block scratch arena (the producer's block still uses it): they
+  // alternate between two buffers sized for the largest of them. Buffer k is read at the start of block k and next written
+  // at the end of block k + 1.
+  static constexpr size_t BOUND_TAG = size_t(1) << 61, BOUND_PAR = size_t(1) << 60;
+  size_t bound_max = 0;
+  int bound_n = 0;
+  TRef boundary(int L, int C) {
+    TRef t;
+    t.L = L; t.C = C; t.lo = false;
+    const size_t bytes = tensor_bytes(L, C, false);
+    if (bytes > bound_max) bound_max = bytes;
+    t.off = BOUND_TAG | ((bound_n++ & 1) ? BOUND_PAR : 0);
+    return t;
+  }
+  // Can GroupNorm(x0) be applied by the kernel that produces x0? (single source written by a plain bf16 tap-GEMM with
+  // statistics; every tile of a batch item inside one round of that kernel's persistent tile loop)
+  bool gn_fusable(const TRef& x0, const TRef& x1) const {
+    if (!P.gn_out || x1.valid() || x0.prod < 0 || x0.prod >= static_cast<int>(P.ops.size())) return false;
+    const Op& pr = P.ops[x0.prod];
+    if (pr.kind != OP_GEMM) return false;
+    const GemmDesc& g = pr.g;
+    if (g.out_mode != GEMM_OUT_BF16 || g.gnout.on || g.out_bs != 0 || g.trim_col != 0 || g.out_dynamic || g.stats_off < 0 ||
+        g.out.off != x0.off || g.out.lo || g.n != x0.C)
+      return false;
+    return ((g.l_out + 127) / 128) * (g.n_pad / 64) <= 128;
+  }
+  // the tensor a GroupNorm writes: scratch of the current block, or a boundary buffer when the producer of x0 (in the previous
+  // block) is going to write it
+  TRef gn_target(const TRef& x0, const TRef& x1, int L, int C, bool same_block = false) {
+    return (!same_block && gn_fusable(x0, x1)) ? boundary(L, C) : tmp(L, C);
+  }
 
   long long slot(const std::string& name, const std::string& recipe, std::vector<std::string> keys,
                  const std::string& dtype, std::vector<int> shape) {
@@ -151,6 +183,14 @@ struct Builder {
                bool silu, long long ss_off, TRef out) {
     const int C = x0.C + (x1.valid() ? x1.C : 0);
     if (x0.st_off < 0 || (x1.valid() && x1.st_off < 0)) { err = "internal: GroupNorm input without statistics: " + tag; return; }
+    if (&list == &P.ops && gn_fusable(x0, x1)) {          // applied by the producer's epilogue: no launch of its own
+      GnOutDesc& d = P.ops[x0.prod].g.gnout;
+      d.on = true; d.out = out; d.eps = eps; d.silu = silu; d.ss = ss_off; d.tag = tag;
+      P.ops[x0.prod].tag += " +gn:" + tag;          // shows up in the op table (dv_plan_op_info)
+      d.gamma = vec(norm_key + ".weight", C);
+      d.beta = vec(norm_key + ".bias", C);
+      return;
+    }
     Op ap;
     ap.kind = OP_GN_APPLY; ap.tag = tag;
     memset(&ap.gn, 0, sizeof ap.gn);
@@ -230,8 +270,10 @@ struct Builder {
     g.w_off = slot(tag + ".W", recipe, std::move(wkeys), "bf16", {g.n_pad, g.k_tot});
     if (!bias_key.empty())
       g.bias_off = slot(tag + ".b", recipe == "geglu" ? "geglu_vec" : "vec", {bias_key}, "f32", {g.n_pad});
-    g.res = res; g.out = out; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C;
+    g.res = res; g.l_out = a.L; g.out_mode = out_mode; g.ld_out = out.C;
     if (stats) attach_stats(g, out);
+    if (&list == &P.ops) out.prod = static_cast<int>(list.size()) - 1;
+    g.out = out;
   }
 
   // conv k3 s1 p1 over (a0 | a1) (+ optional 1x1 shortcut over xs fused as extra K panels) (+ optional identity residual).
@@ -271,8 +313,10 @@ struct Builder {
     P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.triple ? 2 : 1);
     g.w_off = wo;
     g.bias_off = slot(tag + ".b", "vec_sum", bk, "f32", {g.n_pad});
-    g.res = res; g.out = out; g.l_out = a0.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
+    g.res = res; g.l_out = a0.L; g.out_mode = out_mode; g.ld_out = out.C; g.out_dynamic = dynamic_out;
     if (out_mode == GEMM_OUT_BF16) attach_stats(g, out);
+    if (&list == &P.ops) out.prod = static_cast<int>(list.size()) - 1;
+    g.out = out;
   }
 
   TRef resnet(const std::string& pfx, TRef x0, TRef x1, int cout) {
@@ -285,7 +329,7 @@ struct Builder {
       conv3(P.ops, pfx + ".conv1", x0, x1, cin, pfx + ".conv1.weight", pfx + ".conv1.bias", cout, nullptr, 0, "", TRef(), u,
             GEMM_OUT_BF16, false, pfx + ".norm1", -1);
     } else {
-      TRef a = tmp(L, cin);
+      TRef a = gn_target(x0, x1, L, cin);
       emit_gn(P.ops, pfx + ".norm1", x0, x1, pfx + ".norm1", eps, true, -1, a);
       conv3(P.ops, pfx + ".conv1", a, TRef(), cin, pfx + ".conv1.weight", pfx + ".conv1.bias", cout, nullptr, 0, "", TRef(), u,
             GEMM_OUT_BF16, false);
@@ -327,7 +371,7 @@ struct Builder {
     TRef g = y;                                  // fused: proj_in reads the raw block input and normalises it in flight
     std::string gn_key = pfx + ".norm";
     if (!gn_in_gemm) {
-      g = tmp(L, C);
+      g = gn_target(y, TRef(), L, C);
       emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
       gn_key.clear();
     }
@@ -436,7 +480,7 @@ struct Builder {
     scratch_reset();
     const int L = y.L, C = y.C, H = P.cfg.num_heads, D = C / H;
     const std::string tb = pfx + ".transformer_blocks.0";
-    TRef g = tmp(L, C);
+    TRef g = gn_target(y, TRef(), L, C);
     emit_gn(P.ops, pfx + ".norm", y, TRef(), pfx + ".norm", 1e-6f, false, -1, g);
     TRef z = tmp(L, C);
     TRef qkv = tmp(L, 3 * C);
@@ -540,8 +584,10 @@ struct Builder {
     P.slots.back().shape.push_back(C);
     P.slots.back().bytes = static_cast<size_t>(g.n_pad) * g.k_tot * 2 * (P.triple ? 2 : 1);
     g.bias_off = slot(key + ".b", "vec_sum", {key + ".bias"}, "f32", {g.n_pad});
-    g.out = out; g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
+    g.l_out = Lo; g.out_mode = GEMM_OUT_BF16; g.ld_out = C;
     attach_stats(g, out);
+    out.prod = static_cast<int>(P.ops.size()) - 1;
+    g.out = out;
     P.named.emplace_back(key, out);
     return out;
   }
@@ -663,6 +709,8 @@ int Plan::build(std::string& err) {
     fuse_gn = !split && fg && fg[0] == '1';
     const char* g2 = getenv("DV_GEMM2");
     gemm2 = fuse_gn || (g2 && g2[0] == '1');
+    const char* go = getenv("DV_GN_OUT");
+    gn_out = !split && !gemm2 && !(go && go[0] == '0');
   }
   Builder b(*this);
   const int C0 = c.block_out_channels[0];
@@ -683,6 +731,7 @@ int Plan::build(std::string& err) {
   off_h0 = b.ws_alloc(obytes);
   off_h1 = b.ws_alloc(obytes);
   off_ttab = b.ws_alloc(4096 * 4);
+  off_gncnt = b.ws_alloc(static_cast<size_t>(B) * 4);
   diag_ctas = sampler_diag_ctas(static_cast<size_t>(B) * c.x_channels * T);
   off_diag_part = b.ws_alloc(static_cast<size_t>(DIAG_MAX_ROWS) * diag_ctas * 16);
   off_diag_rows = b.ws_alloc(static_cast<size_t>(DIAG_MAX_ROWS) * 16);
@@ -744,7 +793,7 @@ int Plan::build(std::string& err) {
       b.conv3(ops, "conv_out", h, TRef(), C0, "conv_out.weight", "conv_out.bias", c.out_channels, nullptr, 0, "", TRef(), dummy,
               GEMM_OUT_F32_NCL, true, "conv_norm_out", -1);
     } else {
-      TRef a = b.tmp(T, C0);
+      TRef a = b.gn_target(h, TRef(), T, C0);
       b.emit_gn(ops, "conv_norm_out", h, TRef(), "conv_norm_out", c.norm_eps, true, -1, a);
       b.conv3(ops, "conv_out", a, TRef(), C0, "conv_out.weight", "conv_out.bias", c.out_channels, nullptr, 0, "", TRef(), dummy,
               GEMM_OUT_F32_NCL, true);
@@ -758,10 +807,15 @@ int Plan::build(std::string& err) {
   off_ss = b.ws_alloc(static_cast<size_t>(B) * n_all * 4 * 2);                // two time-table slots
   off_stats = b.ws_alloc(stats_bytes);
   const size_t scratch_base = b.ws_alloc(b.scratch_max);
+  const size_t bound_stride = align_up(b.bound_max, 1024);
+  const size_t bound_base = b.ws_alloc(2 * bound_stride);
   ws_bytes = align_up(b.ws_cur, 1024);
 
   // ---- resolve scratch-relative offsets and n_all
-  auto fix = [&](size_t& o) { if (o & Builder::SCRATCH_TAG) o = (o & ~Builder::SCRATCH_TAG) + scratch_base; };
+  auto fix = [&](size_t& o) {
+    if (o & Builder::SCRATCH_TAG) o = (o & ~Builder::SCRATCH_TAG) + scratch_base;
+    else if (o & Builder::BOUND_TAG) o = (o & ~(Builder::BOUND_TAG | Builder::BOUND_PAR)) + bound_base + ((o & Builder::BOUND_PAR) ? bound_stride : 0);
+  };
   auto fix_list = [&](std::vector<Op>& list) {
     for (Op& o : list) {
       switch (o.kind) {
@@ -770,6 +824,7 @@ int Plan::build(std::string& err) {
           if (o.g.res.valid()) fix(o.g.res.off);
           fix(o.g.out.off);
           if (o.g.xf.on) { fix(o.g.xf.x0.off); if (o.g.xf.x1.valid()) fix(o.g.xf.x1.off); }
+          if (o.g.gnout.on) fix(o.g.gnout.out.off);
           break;
         case OP_GN_APPLY:
           fix(o.gno.x0); fix(o.gno.x1); fix(o.gno.out);
@@ -806,7 +861,8 @@ int Plan::build(std::string& err) {
         o.flops = 2.0 * Bd * o.g.l_out * o.g.n * (o.g.alg_k ? o.g.alg_k : o.g.k_tot);
         const double outw = o.g.out_mode == GEMM_OUT_F32_NCL ? 4.0 * o.g.n : (o.g.out_mode == GEMM_OUT_GEGLU ? o.g.n : 2.0 * o.g.n);
         o.bytes = abytes + 2.0 * o.g.n_pad * o.g.k_tot + Bd * o.g.l_out * outw +
-                  (o.g.res.valid() ? Bd * o.g.l_out * o.g.n * 2.0 : 0.0);
+                  (o.g.res.valid() ? Bd * o.g.l_out * o.g.n * 2.0 : 0.0) +
+                  (o.g.gnout.on ? Bd * o.g.l_out * o.g.n * 2.0 : 0.0);   // fused output GroupNorm: the normalised copy
         break;
       }
       case OP_ATTN:
@@ -928,6 +984,15 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         p.stats = g.stats_off >= 0 ? reinterpret_cast<float*>(ws + off_stats + g.stats_off) : nullptr;
         p.stats_nblk = g.stats_nblk;
         p.bn = 0;
+        if (g.gnout.on) {
+          GemmGnOut& n = p.gn;
+          n.out = ws + g.gnout.out.off;
+          n.counter = reinterpret_cast<unsigned*>(ws + off_gncnt);
+          n.G = cfg.norm_num_groups; n.eps = g.gnout.eps; n.silu = g.gnout.silu ? 1 : 0;
+          n.gamma = pf(g.gnout.gamma); n.beta = pf(g.gnout.beta);
+          n.scale_shift = g.gnout.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + g.gnout.ss;
+          n.ss_ld = n_all;
+        }
 #ifdef DV_DEBUG_HOOKS
         { const char* de = getenv("DV_GEMM_DBG"); p.dbg_flags = de ? atoi(de) : 0; }   // timing experiments only
 #endif
@@ -1055,10 +1120,11 @@ int Plan::enqueue_ops(std::vector<Op>& list, float* dyn_out, cudaStream_t st, st
     if (skip_kinds & (1 << o.kind)) { if (launches) ++*launches; continue; }
     switch (o.kind) {
       case OP_GEMM:
-        if (o.g.out_dynamic || (ss_slot && o.gp.xf.scale_shift)) {
+        if (o.g.out_dynamic || (ss_slot && (o.gp.xf.scale_shift || o.gp.gn.scale_shift))) {
           GemmParams p = o.gp;
           if (o.g.out_dynamic) p.out = dyn_out;
           if (ss_slot && p.xf.scale_shift) p.xf.scale_shift += static_cast<size_t>(ss_slot) * B * n_all;
+          if (ss_slot && p.gn.scale_shift) p.gn.scale_shift += static_cast<size_t>(ss_slot) * B * n_all;
           e = K->launch_gemm_tc(p, st);
         } else {
           e = K->launch_gemm_tc(o.gp, st);

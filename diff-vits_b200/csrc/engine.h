@@ -33,6 +33,7 @@ struct TRef {  // 16-bit channel-last tensor [B, L, C] at byte offset `off` of t
   // GroupNorm partial statistics written by the producing GEMM's epilogue (offset inside the stats region)
   long long st_off = -1;
   int st_chunks = 0, st_nblk = 0, st_fold = 0;
+  int prod = -1;     // index in Plan::ops of the tap-GEMM that writes this tensor (-1: another kind of producer)
   bool valid() const { return C > 0; }
 };
 
@@ -57,6 +58,16 @@ struct XfDesc {
   bool silu = false;
 };
 
+// GroupNorm of a GEMM's output applied by the producing kernel (kernels.h: GemmGnOut) instead of a stand-alone gn_apply launch
+struct GnOutDesc {
+  bool on = false;
+  TRef out;                                   // the normalised tensor (what the consumer GEMM reads)
+  long long gamma = -1, beta = -1, ss = -1;   // parameter slots / column offset into the time scale-shift table
+  float eps = 1e-5f;
+  bool silu = false;
+  std::string tag;                            // reference module path of the norm
+};
+
 struct GemmDesc {   // logical description: bind() expands it to the kernel's maps / segments (x3 in split precision)
   int nsrc = 0;
   TRef src[GEMM_MAX_LSRC];
@@ -74,6 +85,7 @@ struct GemmDesc {   // logical description: bind() expands it to the kernel's ma
   long long stats_off = -1;  // >= 0: emit GroupNorm partials of the output
   int stats_nblk = 0;
   XfDesc xf;
+  GnOutDesc gnout;
 };
 
 // One stage of a chained-GEMM launch (kernels.h: ChainStage), offsets instead of pointers until bind()
@@ -133,6 +145,8 @@ struct Plan {
   bool fuse = true;          // transformer sections as chained-GEMM kernels (DV_FUSE=0 selects the one-kernel-per-op program)
   bool gemm2 = false;        // DV_GEMM2=1: k=3 convs as ONE shared-tap segment on the two-ring kernel (csrc/gemm_tc2.cu) instead of
                              // three single-tap segments on the one-ring kernel (measured 4 % slower per C2 step: off)
+  bool gn_out = true;        // single-source GroupNorms applied by the PRODUCING GEMM's epilogue (per-batch-item arrival counter, GemmGnOut):
+                             // 47 of the 61 gn_apply launches of a call disappear; DV_GN_OUT=0 keeps them stand-alone. BF16 mode only.
   bool fuse_gn = false;      // DV_FUSE_GN=1 (implies gemm2): GroupNorm (+SiLU, +scale/shift) applied inside the consuming conv / 1x1 GEMM (operand transform in
                              // shared memory) instead of a stand-alone gn_apply pass. Parity-tested; measured 13 % slower per C2 step (gemm_tc2.cu header): off
   std::vector<ParamSlot> slots;
@@ -145,6 +159,7 @@ struct Plan {
   // workspace regions (byte offsets)
   size_t off_xin = 0, off_ehs = 0, off_aug = 0, off_embact = 0, off_ss = 0, off_stats = 0, off_kvlen = 0;
   size_t off_x = 0, off_xp = 0, off_base = 0, off_h0 = 0, off_h1 = 0, off_ttab = 0;
+  size_t off_gncnt = 0;      // [B] arrival counters of the fused output GroupNorm (zero between launches)
   size_t off_diag_part = 0, off_diag_rows = 0;   // sampler diagnostics: per-CTA partials [DIAG_MAX_ROWS][diag_ctas][4], folded rows [DIAG_MAX_ROWS][4]
   int diag_ctas = 0;
   size_t stats_bytes = 0;

@@ -43,7 +43,8 @@ struct SmemLayout {
   static constexpr int STAGES = EW == 8 ? 2 : (BN == 64 ? 6 : (BN == 128 ? 5 : (BN == 192 ? 4 : 3)));
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EW * EPI_SLAB;
-  static constexpr int BIAS_OFF = BAR_OFF + 256;       // barriers + tmem slot, then the bias vector (n_pad floats)
+  static constexpr int GNS_OFF = BAR_OFF + 256;        // barriers + tmem slot, then mean / rstd of up to 32 groups (fused output GroupNorm)
+  static constexpr int BIAS_OFF = GNS_OFF + 256;       // then the bias vector (n_pad floats)
   static constexpr int dyn_bytes(int n_pad) { return BIAS_OFF + n_pad * 4 + 1024; }   // + slack for 1024-byte alignment
   static_assert(dyn_bytes(MAX_NPAD) <= (EW == 8 ? 116224 : 232448), "exceeds the shared memory budget");
 };
@@ -182,6 +183,117 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
             lds128(e.coal + i * 8 * EPI_PITCH);
     }
     __syncwarp();
+  }
+}
+
+
+// ---- GroupNorm of the output applied by the producing CTAs (GemmGnOut)
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {   // named barrier 1: the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+// One thread per CTA: arrive on the batch item's counter, wait for all `S` tiles of the item, depart; the last departure
+// resets the counter for the next launch. The wait is bounded (a few ms) so that a scheduling assumption that does not hold
+// produces wrong numbers (caught by the parity tests) instead of a hung GPU.
+__device__ __forceinline__ void gn_item_arrive_wait(unsigned* c, unsigned S) {
+  __threadfence();                    // (after the CTA barrier) the tile's stores and partials are visible before the arrival
+  atomicAdd(c, 1u);
+  for (int spins = 0; spins < (1 << 20); ++spins) {
+    if (ld_acquire_u32(c) >= S) break;
+    if (spins > 4) __nanosleep(40);
+  }
+}
+__device__ __forceinline__ void gn_item_depart(unsigned* c, unsigned S) {   // off the critical path: after the CTA barrier
+  if (atomicAdd(c, 1u) == 2u * S - 1u) atomicExch(c, 0u);
+}
+// Sum / sum of squares of one group of one batch item from the producers' partials [chunks][nblk][2]: the same flattened
+// lane assignment, fp64 accumulation order and shuffle tree as gn_apply_kernel (csrc/norm.cu), so both give the same bits.
+__device__ __forceinline__ void gn_group_fold(const float* base, int chunks, int nblk, int kb0, int nkb, int lane, double& sum,
+                                              double& sumsq) {
+  sum = 0.0; sumsq = 0.0;
+  const int items = nkb * chunks;
+  for (int i0 = 0; i0 < items; i0 += 128) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 32 + lane;
+      v[u] = make_float2(0.f, 0.f);
+      if (i < items) {
+        const int kl = i / chunks, ch = i % chunks;
+        v[u] = __ldcg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(ch) * nblk + kb0 + kl) * 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sum += static_cast<double>(v[u].x); sumsq += static_cast<double>(v[u].y); }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    sumsq += __shfl_xor_sync(0xffffffffu, sumsq, m);
+  }
+}
+// Normalise one 32-row x 32-column chunk of the tile this warp has just stored: read back in the row-contiguous layout
+// (each lane: 8 columns of 4 rows), y = SiLU?(x * ca + cb) with the coefficients built exactly like gn_apply_kernel's.
+__device__ __forceinline__ void gn_apply_chunk(const GemmParams& p, const EpiCtx& e, int gcol, int lq, int b, size_t obase,
+                                               const float* s_mean, const float* s_rstd, int gfirst, int cpg) {
+  const int c8 = gcol + e.spiece * 8;
+  if (c8 >= p.N) return;
+  const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(p.out);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.gn.out);
+  uint4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = lq + i * 8 + e.srow;
+    v[i] = l < p.L ? __ldcg(reinterpret_cast<const uint4*>(raw + obase + static_cast<size_t>(l) * p.ld_out + c8)) : make_uint4(0, 0, 0, 0);
+  }
+  const int grp = c8 / cpg - gfirst;
+  const float mean = s_mean[grp], rstd = s_rstd[grp];
+  float ca[8], cb[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 4) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gn.gamma + c8 + j));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.gn.beta + c8 + j));
+    const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = rstd * ga[k];
+      ca[j + k] = a;
+      cb[j + k] = be[k] - mean * a;
+    }
+  }
+  if (p.gn.scale_shift) {
+    const float* ssp = p.gn.scale_shift + static_cast<size_t>(b) * p.gn.ss_ld + c8;
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(ssp + j));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(ssp + p.N + j));
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float s1 = 1.0f + scv[k];
+        ca[j + k] *= s1;
+        cb[j + k] = cb[j + k] * s1 + shv[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = lq + i * 8 + e.srow;
+    if (l >= p.L) continue;
+    const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    uint32_t y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = fmaf(bf16_lo(w[j]), ca[2 * j], cb[2 * j]);
+      float c = fmaf(bf16_hi(w[j]), ca[2 * j + 1], cb[2 * j + 1]);
+      if (p.gn.silu) { a = silu_f(a); c = silu_f(c); }
+      y[j] = pack_bf16(a, c);
+    }
+    *reinterpret_cast<uint4*>(dst + obase + static_cast<size_t>(l) * p.ld_out + c8) = make_uint4(y[0], y[1], y[2], y[3]);
   }
 }
 
@@ -478,6 +590,41 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (!TRIM && !SPLIT && p.gn.out != nullptr) {
+          // ---- GroupNorm of the output, applied here: wait for the other tiles of this batch item, then normalise this tile
+          float* s_mean = reinterpret_cast<float*>(smem + SL::GNS_OFF);
+          float* s_rstd = s_mean + 32;
+          epi_bar_sync(EW * 32);                          // every warp's raw store and partials are issued
+          if (warp == 2 && lane == 0)
+            gn_item_arrive_wait(p.gn.counter + b, static_cast<unsigned>(p.tiles_per_batch * n_tiles_n));
+          epi_bar_sync(EW * 32);
+          if (warp == 2 + EW - 1 && lane == 0)              // (a warp that folds no group unless the tile spans EW groups)
+            gn_item_depart(p.gn.counter + b, static_cast<unsigned>(p.tiles_per_batch * n_tiles_n));
+          const int cpg = p.N / p.gn.G;
+          const int gfirst = n0 / cpg;
+          const int glast = (min(n0 + BN, p.N) - 1) / cpg;
+          const int chunks = p.tiles_per_batch * 4;
+          const float* sbase = p.stats + static_cast<size_t>(b) * chunks * p.stats_nblk * 2;
+          for (int g = gfirst + (warp - 2); g <= glast; g += EW) {
+            double sum, sumsq;
+            gn_group_fold(sbase, chunks, p.stats_nblk, (g * cpg) >> 4, cpg >> 4, lane, sum, sumsq);
+            if (lane == 0) {
+              const double n = static_cast<double>(p.L) * cpg;
+              const double mean = sum / n;
+              double var = sumsq / n - mean * mean;
+              if (var < 0.0) var = 0.0;
+              s_mean[g - gfirst] = static_cast<float>(mean);
+              s_rstd[g - gfirst] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.gn.eps)));
+            }
+          }
+          epi_bar_sync(EW * 32);
+#pragma unroll 1
+          for (int ch = part; ch < NCH; ch += PARTS) {
+            const int gcol = n0 + ch * 32;
+            if (gcol >= p.N) continue;
+            gn_apply_chunk(p, e, gcol, lq, b, obase, s_mean, s_rstd, gfirst, cpg);
+          }
+        }
       }
       if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -520,6 +667,7 @@ __global__ void gemm_ref_kernel(GemmParams p, GemmRefSrc s0, GemmRefSrc s1, Gemm
   reinterpret_cast<float*>(p.out)[(static_cast<size_t>(b) * p.L + l) * p.n_pad + n] = acc;
 }
 
+inline int min_i(int a, int b) { return a < b ? a : b; }
 int g_num_sms = 0;
 int g_force_ew = 0;   // DV_GEMM_EW: 8 / 16 force the CTA shape of the 128-wide tile kernel (0 = heuristic)
 
@@ -602,7 +750,7 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   if (p.out_mode == GEMM_OUT_GEGLU && p.n_pad % 128 != 0) return cudaErrorInvalidValue;
   // shared conv taps / a GroupNorm fused into the operand path are features of the two-ring kernel (csrc/gemm_tc2.cu)
   for (int i = 0; i < p.nseg; ++i)
-    if (p.seg[i].ntap != 1 || p.seg[i].xf != 0) return DV_NS::launch_gemm_tc2(p_in, st);
+    if (p.seg[i].ntap != 1 || p.seg[i].xf != 0) return p.gn.out ? cudaErrorInvalidValue : DV_NS::launch_gemm_tc2(p_in, st);
   for (int i = 0; i < GEMM_MAX_SRC; ++i)
     if (p.map_rows[i] != 128) return cudaErrorInvalidValue;
   const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
@@ -615,6 +763,15 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
     return launch_bn<128, 16, false, true>(p, st);
   }
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
+  if (p.gn.out != nullptr) {
+    // fused output GroupNorm: plain bf16 epilogue with statistics, and every tile of a batch item must be co-scheduled in one
+    // round of the persistent tile loop (the item barrier waits on them)
+    if (p.out_mode != GEMM_OUT_BF16 || !p.stats || !p.gn.counter || p.relu || p.row_len || p.trim_col > 0 || !dense ||
+        p.gn.G < 1 || p.N % (16 * p.gn.G) != 0)
+      return cudaErrorInvalidValue;
+    if (p.tiles_per_batch * (p.n_pad / bn) > g_num_sms) return cudaErrorInvalidValue;
+    if ((min_i(bn, p.N) + p.N / p.gn.G - 1) / (p.N / p.gn.G) + 1 > 32) return cudaErrorInvalidValue;
+  }
   if (p.relu || p.row_len) {                             // prompt-encoder epilogue options live in the rare-path instantiation
     if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
     if (p.trim_col == 0) p.trim_col = 1 << 30;           // (no trimmed half row)

@@ -87,6 +87,19 @@ struct GemmXf {
   const float* scale_shift; int ss_ld;        // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + C + c]
 };
 
+// GroupNorm of this GEMM's OUTPUT applied by the producing CTAs themselves (out != nullptr), instead of a stand-alone
+// gn_apply launch: after a tile's raw store + partial statistics, the CTA arrives on its batch item's counter, waits until
+// every tile of that item (tiles_per_batch x N tiles, a contiguous range of the static tile schedule) has arrived, folds the
+// item's partials into mean / rstd (same order as gn_apply: bit-identical) and writes the normalised (+scale/shift, +SiLU)
+// copy of its own tile. Only the epilogue warps wait; the producer / MMA warps go on with the CTA's next tile.
+struct GemmGnOut {
+  void* out;                                  // normalised 16-bit [B, L, ld_out] (same geometry as the raw output)
+  unsigned* counter;                          // [B], zero between launches (arrivals then departures; the last departure resets it)
+  int G; float eps; int silu;
+  const float* gamma; const float* beta;      // [N]
+  const float* scale_shift; int ss_ld;        // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + N + c]
+};
+
 struct alignas(64) GemmParams {
   CUtensorMap mapA[GEMM_MAX_SRC];
   CUtensorMap mapW;
@@ -95,6 +108,7 @@ struct alignas(64) GemmParams {
   int nseg;
   int16_t map_rows[GEMM_MAX_SRC];   // rows of the TMA box of each A map (128, or 136 for sources read with shared taps)
   GemmXf xf;                        // used when any segment has xf != 0
+  GemmGnOut gn;                     // gn.out != nullptr: GroupNorm of the output applied in the epilogue (GEMM_OUT_BF16, dense, with stats)
   int B, L, N;          // L = output rows per batch item, N = real output columns
   int n_pad;            // N rounded up to the N tile
   int tiles_per_batch;  // ceil(L / 128)

@@ -96,3 +96,35 @@ def test_fused_deterministic(unet):
     a = eng.forward(x, t, x_only=True).clone()
     b = eng.forward(x, t, x_only=True).clone()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,T,Tp,fuse", [(2, 256, 40, True), (3, 203, 282, True), (5, 1000, 64, False), (2, 40, 16, True),
+                                         (40, 136, 33, True)])
+def test_groupnorm_in_producer_epilogue_matches_standalone_pass(unet, monkeypatch, B, T, Tp, fuse):
+    """GroupNorm applied by the PRODUCING GEMM's CTAs (per-batch-item arrival counter, kernels.h GemmGnOut; default) against
+    the stand-alone gn_apply launches (DV_GN_OUT=0): same stored bf16 input, same partial statistics folded in the same
+    order, same coefficient arithmetic, so every block output must be bit-identical. Shapes: one and several row tiles
+    per item, ragged last tiles, odd lengths, more tiles than SMs (B = 40 x 2 tiles at level 0 with two CTAs per SM), and
+    the one-kernel-per-op transformer program (GroupNorm fused into proj_out / conv2 at every level)."""
+    from oracle import inputs
+    x, cond, ehs = (t.cuda() for t in inputs.make_inputs(B, T, Tp, seed=21))
+    t = torch.tensor([611.0], device="cuda")
+    outs, named, n_gn = [], [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DV_GN_OUT", flag)
+        eng = _engine(unet, B, T, Tp, fuse)
+        ops = eng.op_table()
+        n_gn.append(sum(1 for o in ops if o["kind"] == 2))
+        assert any("+gn:" in o["tag"] for o in ops) == (flag == "1")
+        eng.prepare_prompt(ehs)
+        eng.set_cond(cond)
+        for _ in range(3):                       # the item counters must return to zero after every launch
+            out = eng.forward(x, t, x_only=True).clone()
+        outs.append(out)
+        torch.cuda.synchronize()
+        named.append({k: v.float().clone() for k, v in eng.named_tensors().items()})
+    print(f"gn_apply launches per call: fused {n_gn[0]}, stand-alone {n_gn[1]}")
+    assert n_gn[0] <= 16 < n_gn[1]
+    for k in named[0]:
+        assert torch.equal(named[0][k], named[1][k]), k
+    assert torch.equal(outs[0], outs[1])
