@@ -1,13 +1,16 @@
 // Attention core of the FP32-class precision mode ("fp32x3"): F.scaled_dot_product_attention
 // (unet1d/attention_processor.py:1032, additive -10000 key-padding bias :1003-1007) on operands stored as hi + lo bf16
-// planes, evaluated entirely in fp32 on the CUDA cores. Q.K^T, the softmax and P.V never round to bf16: the only
+// planes. Two kernels with the same contract: attention_split_mma_kernel (default, further down: tensor cores, three MMAs per
+// product) and attention_split_kernel (DV_ATTN_SPLIT=cuda: everything in fp32 on the CUDA cores, the cross-check). The only
 // rounding points are the hi + lo operands (16 mantissa bits) and the hi + lo output. This mode exists to prove the
 // engine against the fp32 reference at the 1e-4 gate; the BF16 mode's tensor-core kernels (attention.cu /
 // attention_tc.cu) are the fast path.
 //
-// CTA = 64 queries of one (batch, head) x 4 threads per query: thread `part` owns D/4 of the head dimension (its slice
+// CUDA-core kernel: CTA = 64 queries of one (batch, head) x 4 threads per query: thread `part` owns D/4 of the head dimension (its slice
 // of q and of the output accumulator); a score is the sum of the four partial dot products (two shuffles). K/V tiles of
 // 64 keys are reconstructed to fp32 (hi + lo) in shared memory; the 8 queries of a warp read the same key row (broadcast).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -111,10 +114,252 @@ __global__ void __launch_bounds__(SQ * 4) attention_split_kernel(const AttnParam
   }
 }
 
+
+// ---- tensor-core variant (default): the same contract on mma.sync m16n8k16 with every product taken as three MMAs,
+// a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (the dropped lo.lo term is 2^-16 relative), fp32 accumulation:
+//   S = Q.K^T from the hi / lo fragments of Q (registers) and K (shared memory); softmax in fp32 on the accumulator
+//   fragments (online max, exp2 with the scale folded into the argument); P split in registers into bf16 hi + lo and
+//   multiplied with the hi / lo planes of V; the row sum is taken from the fp32 P. 64 queries (4 warps x 16 rows) x 32-key
+//   tiles, K/V planes by cp.async, double buffered. ~40x the throughput of the CUDA-core kernel above at the same 1e-5
+//   class error (tests/test_gpu_precision.py gates the mode at 1e-4 end to end).
+constexpr int MQ = 64, MK = 32, M_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16s(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32." DV_MMA_T "." DV_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* smem_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(M_THREADS) attention_split_mma_kernel(const AttnParams p) {
+  constexpr int PITCH = D + 8;           // elements (+16 bytes: conflict-free fragment loads / ldmatrix)
+  constexpr int CHUNKS = D / 8;          // 16-byte pieces per row
+  constexpr int TILE = MK * PITCH;       // elements of one K or V plane tile
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(sm_raw);   // [2 planes][MQ][PITCH]
+  __nv_bfloat16* sK = sQ + 2 * MQ * PITCH;                        // [2 buffers][2 planes][MK][PITCH]
+  __nv_bfloat16* sV = sK + 4 * TILE;
+
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  pdl_wait();
+  const int q0 = blockIdx.x * MQ, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* Qp[2] = {reinterpret_cast<const __nv_bfloat16*>(p.q) + b * p.bs_q + h * D,
+                                reinterpret_cast<const __nv_bfloat16*>(p.q_lo) + b * p.bs_q + h * D};
+  const __nv_bfloat16* Kp[2] = {reinterpret_cast<const __nv_bfloat16*>(p.k) + b * p.bs_k + h * D,
+                                reinterpret_cast<const __nv_bfloat16*>(p.k_lo) + b * p.bs_k + h * D};
+  const __nv_bfloat16* Vp[2] = {reinterpret_cast<const __nv_bfloat16*>(p.v) + b * p.bs_v + h * D,
+                                reinterpret_cast<const __nv_bfloat16*>(p.v_lo) + b * p.bs_v + h * D};
+  for (int i = tid; i < 2 * MQ * CHUNKS; i += M_THREADS) {
+    const int pl = i / (MQ * CHUNKS), r = (i / CHUNKS) % MQ, c = i % CHUNKS;
+    const int row = q0 + r;
+    const bool ok = row < p.Lq;
+    cp_async16s(&sQ[(pl * MQ + r) * PITCH + c * 8], Qp[pl] + static_cast<size_t>(ok ? row : 0) * p.ld_q + c * 8, ok ? 16 : 0);
+  }
+  auto load_kv = [&](int tile, int buf) {
+    const int k0 = tile * MK;
+    for (int i = tid; i < 2 * MK * CHUNKS; i += M_THREADS) {
+      const int pl = i / (MK * CHUNKS), r = (i / CHUNKS) % MK, c = i % CHUNKS;
+      const int row = k0 + r;
+      const bool ok = row < p.Lk;
+      const size_t rr = static_cast<size_t>(ok ? row : 0);
+      cp_async16s(&sK[(buf * 2 + pl) * TILE + r * PITCH + c * 8], Kp[pl] + rr * p.ld_k + c * 8, ok ? 16 : 0);
+      cp_async16s(&sV[(buf * 2 + pl) * TILE + r * PITCH + c * 8], Vp[pl] + rr * p.ld_v + c * 8, ok ? 16 : 0);
+    }
+  };
+  const int ntiles = (p.Lk + MK - 1) / MK;
+  load_kv(0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float sl2 = p.scale * LOG2E;
+  const int kvlen = p.kv_len ? p.kv_len[b] : p.Lk;
+  const float mask_raw = -10000.0f / p.scale;          // the reference's additive -10000 bias, in raw-score units
+  const int kvalid = min(kvlen, p.Lk);
+
+  uint32_t qh[D / 16][4], ql[D / 16][4];
+  float o[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float l0 = 0.f, l1 = 0.f;                            // this lane's share of the row sums (rows g and g + 8)
+  float m0 = -INFINITY, m1 = -INFINITY;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) {
+      load_kv(tile + 1, buf ^ 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (tile == 0) {
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const __nv_bfloat16* qb = &sQ[(pl * MQ + warp * 16) * PITCH];
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t(&f)[4] = pl ? ql[kk] : qh[kk];
+          f[0] = *reinterpret_cast<const uint32_t*>(&qb[g * PITCH + kk * 16 + 2 * t]);
+          f[1] = *reinterpret_cast<const uint32_t*>(&qb[(g + 8) * PITCH + kk * 16 + 2 * t]);
+          f[2] = *reinterpret_cast<const uint32_t*>(&qb[g * PITCH + kk * 16 + 2 * t + 8]);
+          f[3] = *reinterpret_cast<const uint32_t*>(&qb[(g + 8) * PITCH + kk * 16 + 2 * t + 8]);
+        }
+      }
+    }
+    const __nv_bfloat16* kH = &sK[(buf * 2 + 0) * TILE];
+    const __nv_bfloat16* kL = &sK[(buf * 2 + 1) * TILE];
+    const __nv_bfloat16* vH = &sV[(buf * 2 + 0) * TILE];
+    const __nv_bfloat16* vL = &sV[(buf * 2 + 1) * TILE];
+
+    float s[MK / 8][4];
+#pragma unroll
+    for (int j = 0; j < MK / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const int off = (j * 8 + g) * PITCH + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t h0 = *reinterpret_cast<const uint32_t*>(kH + off + kk * 16);
+        const uint32_t h1 = *reinterpret_cast<const uint32_t*>(kH + off + kk * 16 + 8);
+        const uint32_t e0 = *reinterpret_cast<const uint32_t*>(kL + off + kk * 16);
+        const uint32_t e1 = *reinterpret_cast<const uint32_t*>(kL + off + kk * 16 + 8);
+        mma16816(s[j], ql[kk], h0, h1);                // small terms first
+        mma16816(s[j], qh[kk], e0, e1);
+        mma16816(s[j], qh[kk], h0, h1);
+      }
+    }
+    if (tile * MK + MK > kvalid) {
+      const int kbase = tile * MK + 2 * t;
+#pragma unroll
+      for (int j = 0; j < MK / 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = kbase + j * 8 + e;
+          float add = 0.f;
+          if (key >= p.Lk) add = -INFINITY;
+          else if (key >= kvlen) add = mask_raw;
+          s[j][e] += add;
+          s[j][2 + e] += add;
+        }
+      }
+    }
+    float mx0 = fmaxf(s[0][0], s[0][1]), mx1 = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+    for (int j = 1; j < MK / 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 key < Lk
+    const float c0 = ex2a((m0 - mn0) * sl2), c1 = ex2a((m1 - mn1) * sl2);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+
+    uint32_t ph[MK / 16][4], pl_[MK / 16][4];
+#pragma unroll
+    for (int j = 0; j < MK / 8; ++j) {
+      const float p0 = ex2a((s[j][0] - mn0) * sl2), p1 = ex2a((s[j][1] - mn0) * sl2);
+      const float p2 = ex2a((s[j][2] - mn1) * sl2), p3 = ex2a((s[j][3] - mn1) * sl2);
+      l0 += p0 + p1; l1 += p2 + p3;
+      const uint32_t a = pack_bf16(p0, p1), c = pack_bf16(p2, p3);
+      ph[j >> 1][(j & 1) * 2 + 0] = a;
+      ph[j >> 1][(j & 1) * 2 + 1] = c;
+      pl_[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0 - bf16_lo(a), p1 - bf16_hi(a));
+      pl_[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 - bf16_lo(c), p3 - bf16_hi(c));
+    }
+#pragma unroll
+    for (int kk = 0; kk < MK / 16; ++kk) {
+      const int krow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int jd = 0; jd < D / 8; jd += 2) {
+        uint32_t vh[4], vl[4];
+        ldsm_x4_t(vh, &vH[krow * PITCH + (jd + (lane >> 4)) * 8]);
+        ldsm_x4_t(vl, &vL[krow * PITCH + (jd + (lane >> 4)) * 8]);
+        mma16816(o[jd], pl_[kk], vh[0], vh[1]);
+        mma16816(o[jd], ph[kk], vl[0], vl[1]);
+        mma16816(o[jd], ph[kk], vh[0], vh[1]);
+        mma16816(o[jd + 1], pl_[kk], vh[2], vh[3]);
+        mma16816(o[jd + 1], ph[kk], vl[2], vl[3]);
+        mma16816(o[jd + 1], ph[kk], vh[2], vh[3]);
+      }
+    }
+    __syncthreads();
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* O = reinterpret_cast<__nv_bfloat16*>(p.o) + b * p.bs_o + h * D;
+  __nv_bfloat16* Ol = reinterpret_cast<__nv_bfloat16*>(p.o_lo) + b * p.bs_o + h * D;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) {
+    if (r0 < p.Lq) {
+      const float y0 = o[j][0] * i0, y1 = o[j][1] * i0;
+      const uint32_t hi = pack_bf16(y0, y1);
+      const size_t at = static_cast<size_t>(r0) * p.ld_o + j * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(&O[at]) = hi;
+      *reinterpret_cast<uint32_t*>(&Ol[at]) = pack_bf16(y0 - bf16_lo(hi), y1 - bf16_hi(hi));
+    }
+    if (r1 < p.Lq) {
+      const float y0 = o[j][2] * i1, y1 = o[j][3] * i1;
+      const uint32_t hi = pack_bf16(y0, y1);
+      const size_t at = static_cast<size_t>(r1) * p.ld_o + j * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(&O[at]) = hi;
+      *reinterpret_cast<uint32_t*>(&Ol[at]) = pack_bf16(y0 - bf16_lo(hi), y1 - bf16_hi(hi));
+    }
+  }
+}
+
+template <int D>
+constexpr int split_mma_smem() { return (2 * MQ + 8 * MK) * (D + 8) * 2; }
+template <int D>
+cudaError_t launch_split_mma(const AttnParams& p, cudaStream_t st) {
+  if (split_mma_smem<D>() > 48 * 1024) {   // per device, host-side only (not a stream operation: legal during graph capture)
+    cudaError_t e = cudaFuncSetAttribute(attention_split_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, split_mma_smem<D>());
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((p.Lq + MQ - 1) / MQ, p.H, p.B);
+  return launch_k(attention_split_mma_kernel<D>, grid, dim3(M_THREADS), split_mma_smem<D>(), st, p);
+}
+
 }  // namespace
 
 cudaError_t launch_attention_split(const AttnParams& p, cudaStream_t st) {
   if (p.Lk < 1 || p.Lq < 1 || !p.q_lo || !p.k_lo || !p.v_lo || !p.o_lo) return cudaErrorInvalidValue;
+  // DV_ATTN_SPLIT=cuda selects the first, CUDA-core kernel (kept as the cross-check of the tensor-core one)
+  const char* se = getenv("DV_ATTN_SPLIT");          // read per launch (launches are captured on the hot path): tests flip it
+  const bool cuda_core = se && se[0] == 'c';
+  if (!cuda_core) {
+    switch (p.D) {
+      case 16: return launch_split_mma<16>(p, st);
+      case 32: return launch_split_mma<32>(p, st);
+      case 48: return launch_split_mma<48>(p, st);
+      case 64: return launch_split_mma<64>(p, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   dim3 grid((p.Lq + SQ - 1) / SQ, p.H, p.B);
   switch (p.D) {
     case 16: return launch_k(attention_split_kernel<16>, grid, dim3(SQ * 4), 0, st, p);

@@ -119,6 +119,31 @@ def test_sampling_loops_and_per_step_vs_reference_golden(env):
         assert torch.equal(lat, again)
 
 
+def test_split_attention_tensor_core_kernel_vs_cuda_core_kernel(env, monkeypatch):
+    """The attention core of this mode runs on the tensor cores (three mma.sync products per contraction over the hi / lo
+    planes, csrc/attention_split.cu); the first, all-fp32 CUDA-core kernel stays selectable (DV_ATTN_SPLIT=cuda) as its
+    cross-check: every transformer block output of one call must agree to the hi + lo operand resolution, on full,
+    ragged-masked and odd-length shapes (all four head dims: the levels use d = 16 / 32 / 48 / 64)."""
+    import diffvits_b200
+    U, unet = env["U"], env["unet"]
+    for (B, T, Tp, seed, ragged) in ((2, 200, 282, 5, True), (1, 203, 40, 6, False), (3, 72, 50, 7, True)):
+        x_T, cond, ehs = env["inputs"].make_inputs(B, T, Tp, seed=seed)
+        kv = torch.tensor([Tp - 17 * i for i in range(B)], dtype=torch.int32) if ragged else None
+        t = torch.tensor([433.0], device="cuda")
+        outs, named = [], []
+        for mode in ("", "cuda"):
+            monkeypatch.setenv("DV_ATTN_SPLIT", mode)
+            nat = diffvits_b200.NativeDenoiser(unet, cond.cuda(), ehs.cuda(), kv.cuda() if ragged else None)
+            outs.append(nat(x_T.cuda(), t).clone())
+            torch.cuda.synchronize()
+            named.append({k: v.float().clone() for k, v in nat.engine.named_tensors().items()})
+            nat.close()
+        worst = max(U.rel_l2(named[0][k], named[1][k]) for k in named[0])
+        rel = U.rel_l2(outs[0], outs[1])
+        print(f"fp32x3 attention, tensor-core vs CUDA-core kernel (B={B}, T={T}, Tp={Tp}): call rel {rel:.3e}, worst block {worst:.3e}")
+        assert torch.isfinite(outs[0]).all() and rel < 5e-5 and worst < 5e-5     # each kernel is ~1e-5 from the fp32 truth
+
+
 def test_batch_consistency_and_bf16_mode_coexist(env, seeded_unet):
     """A batch equals its samples run alone in this mode too; a BF16-mode module next to it is unaffected."""
     import diffvits_b200
