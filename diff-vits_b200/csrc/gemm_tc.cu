@@ -734,6 +734,12 @@ cudaError_t gemm_tc_init() {
   e = cudaFuncSetAttribute(gemm_tc_kernel<128, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            SmemLayout<128, 16>::dyn_bytes(MAX_NPAD));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<256, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<192, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           SmemLayout<192, 16>::dyn_bytes(MAX_NPAD));
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(gemm_tc_kernel<256, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               SmemLayout<256, 16>::dyn_bytes(MAX_NPAD));
 }
@@ -754,15 +760,21 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   for (int i = 0; i < GEMM_MAX_SRC; ++i)
     if (p.map_rows[i] != 128) return cudaErrorInvalidValue;
   const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
-  if (p.out_lo != nullptr) {                             // split precision: one tile shape (128 x 128, 16 epilogue warps)
+  const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
+  if (p.out_lo != nullptr) {                             // split precision (hi + lo output planes): the same tile shapes
     if (p.res != nullptr && p.res_lo == nullptr) return cudaErrorInvalidValue;
+    if (p.gn.out != nullptr) return cudaErrorInvalidValue;
     if (p.trim_col > 0 || !dense) {
       if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
       return launch_bn<128, 16, true, true>(p, st);
     }
+    static const bool one_shape = getenv("DV_GEMM_SPLIT128") != nullptr;     // A/B: the single 128 x 128 shape of the first version
+    if (!one_shape) {
+      if (bn == 256 && p.n_pad % 256 == 0) return launch_bn<256, 16, false, true>(p, st);
+      if (bn == 192 && p.n_pad % 192 == 0 && p.out_mode != GEMM_OUT_GEGLU) return launch_bn<192, 16, false, true>(p, st);
+    }
     return launch_bn<128, 16, false, true>(p, st);
   }
-  const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
   if (p.gn.out != nullptr) {
     // fused output GroupNorm: plain bf16 epilogue with statistics, and every tile of a batch item must be co-scheduled in one
     // round of the persistent tile loop (the item barrier waits on them)
