@@ -502,6 +502,7 @@ def run_native(args):
                 lv["launches"] += 1
                 lv["roof_ms"] += max(t_tensor, t_hbm)
         call_ms_eager = sum(acc)
+        n_fused_gn = sum(1 for o in ops if "+gn:" in o["tag"])
         g = by_kind["gemm_tc"]
         gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12
         kernels = {}
@@ -606,7 +607,11 @@ def run_native(args):
             "how": f"achieved = algorithmic FLOPs of the {g['launches']} gemm_tc launches of one denoiser call / the SUM OF "
                    f"THEIR KERNEL DURATIONS: the call replayed as a CUDA graph with an event-record node between launches, "
                    f"CUDA events on the launching stream, mean of {reps} replays (each launch pays its own fill and drain, "
-                   f"no PDL overlap with its neighbours)",
+                   f"no PDL overlap with its neighbours)" +
+                   (f"; {n_fused_gn} of these launches also apply the GroupNorm (+SiLU, +scale/shift) of their own output in "
+                    f"their epilogue (per-item arrival counter): that tail is inside the durations while no FLOPs are counted "
+                    f"for it (DV_GN_OUT=0 runs it as {n_fused_gn} stand-alone gn_apply launches instead)" if n_fused_gn else ""),
+            "fused_groupnorm_launches": n_fused_gn,
             "whole_step": {"algorithmic_tflop_per_step_per_gpu": round(total_flops / 1e12, 2),
                            "achieved_tflops": round(step_tflops, 2),
                            "frac_of_burst_peak": round(step_tflops / peak_tf, 4),

@@ -80,6 +80,7 @@ SIGNATURES = {
     "dv_plan_launches_per_forward": (_i, [_vp]),
     "dv_plan_last_sample_launches": (_i, [_vp]),
     "dv_plan_sample_diag": (_i, [_vp, C.POINTER(_sz), C.POINTER(_i)]),
+    "dv_plan_health_flag": (_i, [_vp, C.POINTER(_sz)]),
     "dv_plan_bind": (_i, [_vp, _vp, _vp, _vp]),
     "dv_prompt_prepare": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "dv_set_cond": (_i, [_vp, _vp, _vp]),

@@ -86,6 +86,11 @@ int dv_plan_sample_diag(const dv_plan* plan, size_t* offset, int* rows) {
   *rows = plan->impl.last_diag_rows;
   return DV_OK;
 }
+int dv_plan_health_flag(const dv_plan* plan, size_t* offset) {
+  if (!plan || !offset) return fail(DV_ERR_INVALID, "null argument");
+  *offset = plan->impl.off_gncnt + static_cast<size_t>(plan->impl.B) * 4;
+  return DV_OK;
+}
 
 int dv_plan_bind(dv_plan* plan, void* workspace, const void* params, void* stream) {
   if (!plan) return fail(DV_ERR_INVALID, "null plan");

@@ -731,7 +731,7 @@ int Plan::build(std::string& err) {
   off_h0 = b.ws_alloc(obytes);
   off_h1 = b.ws_alloc(obytes);
   off_ttab = b.ws_alloc(4096 * 4);
-  off_gncnt = b.ws_alloc(static_cast<size_t>(B) * 4);
+  off_gncnt = b.ws_alloc(static_cast<size_t>(B + 1) * 4);   // + the sticky "a wait gave up" flag
   diag_ctas = sampler_diag_ctas(static_cast<size_t>(B) * c.x_channels * T);
   off_diag_part = b.ws_alloc(static_cast<size_t>(DIAG_MAX_ROWS) * diag_ctas * 16);
   off_diag_rows = b.ws_alloc(static_cast<size_t>(DIAG_MAX_ROWS) * 16);

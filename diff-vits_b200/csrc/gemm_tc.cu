@@ -49,13 +49,23 @@ struct SmemLayout {
   static_assert(dyn_bytes(MAX_NPAD) <= (EW == 8 ? 116224 : 232448), "exceeds the shared memory budget");
 };
 
-// debug timeline (enabled only when p.trace != nullptr): CTA 0, one lane per role
+// debug timeline (debug library only, enabled when p.trace != nullptr): CTA 0; every role (0 producer thread, 1 MMA thread,
+// 2 lane 0 of the first epilogue warp) appends (event, tile, SM clock) records to its own region of the buffer with plain
+// stores (no atomics: the probe must not add a round trip to what it measures); role 3 holds %globaltimer at kernel entry /
+// after griddepcontrol.wait / at exit, which places consecutive launches on one time axis.
+constexpr int TRACE_REGION = 160;
 __device__ __forceinline__ void trace_ev(const GemmParams& p, int role, int tile, int ev) {
 #ifdef DV_DEBUG_HOOKS
   if (p.trace && blockIdx.x == 0) {
-    const unsigned long long i = atomicAdd(p.trace, 1ULL);
-    if (i < 4000) p.trace[1 + i] = (static_cast<unsigned long long>(role) << 60) | (static_cast<unsigned long long>(tile & 0xFFFF) << 44) |
-                                   (static_cast<unsigned long long>(ev & 0xF) << 40) | (clock64() & 0xFFFFFFFFFFULL);
+    unsigned long long* reg = p.trace + 1 + role * TRACE_REGION;
+    const unsigned long long i = reg[0];
+    if (i + 1 < TRACE_REGION) {
+      unsigned long long t;
+      if (role == 3) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); else t = clock64();
+      reg[1 + i] = (static_cast<unsigned long long>(role) << 60) | (static_cast<unsigned long long>(tile & 0xFFFF) << 44) |
+                   (static_cast<unsigned long long>(ev & 0xF) << 40) | (t & 0xFFFFFFFFFFULL);
+      reg[0] = i + 1;
+    }
   }
 #endif
 }
@@ -199,13 +209,15 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {   // named barrier 
 // One thread per CTA: arrive on the batch item's counter, wait for all `S` tiles of the item, depart; the last departure
 // resets the counter for the next launch. The wait is bounded (a few ms) so that a scheduling assumption that does not hold
 // produces wrong numbers (caught by the parity tests) instead of a hung GPU.
-__device__ __forceinline__ void gn_item_arrive_wait(unsigned* c, unsigned S) {
-  __threadfence();                    // (after the CTA barrier) the tile's stores and partials are visible before the arrival
-  atomicAdd(c, 1u);
+__device__ __forceinline__ void gn_item_arrive_wait(unsigned* c, unsigned S, unsigned* gave_up) {
+  // release: (after the CTA barrier) the tile's raw store and partials are visible before the arrival is. A release RMW instead
+  // of __threadfence() + atomicAdd: the latter compiles to MEMBAR.SC.GPU, the sequentially-consistent fence.
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
   for (int spins = 0; spins < (1 << 20); ++spins) {
-    if (ld_acquire_u32(c) >= S) break;
+    if (ld_acquire_u32(c) >= S) return;
     if (spins > 4) __nanosleep(40);
   }
+  atomicExch(gave_up, 1u);            // sticky: the host side refuses the plan's results (engine.py check_finite / sample_diag)
 }
 __device__ __forceinline__ void gn_item_depart(unsigned* c, unsigned S) {   // off the critical path: after the CTA barrier
   if (atomicAdd(c, 1u) == 2u * S - 1u) atomicExch(c, 0u);
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   constexpr int PARTS = EW / 4;                       // epilogue warps per TMEM lane quarter
   constexpr int STAGES = SL::STAGES;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) { trace_ev(p, 3, 0, 0); trace_ev(p, 0, 0, 8); }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
@@ -344,6 +357,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_ev(p, 0, 0, 9);      // prologue (barriers, TMEM, bias) done
   // everything above touched only static data (weights, descriptors); activations of earlier kernels are read only after
   // griddepcontrol.wait. The producer first puts the W panels of its first ring of stages in flight (weights are static):
   // with PDL that load latency overlaps the previous kernel's tail instead of following it.
@@ -368,6 +382,8 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
         }
       }
       pdl_wait();
+      trace_ev(p, 0, 0, 10);                              // previous kernel complete
+      trace_ev(p, 3, 0, 1);
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;                                     // panels issued by this CTA so far (across tiles)
@@ -424,6 +440,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
         for (int kp = 0; kp < total_panels; ++kp) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kp == 0) trace_ev(p, 1, tile, 3);           // first panel landed
           const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + SL::A_BYTES);
@@ -594,10 +611,12 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           // ---- GroupNorm of the output, applied here: wait for the other tiles of this batch item, then normalise this tile
           float* s_mean = reinterpret_cast<float*>(smem + SL::GNS_OFF);
           float* s_rstd = s_mean + 32;
+          if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 3);    // pass 1 done
           epi_bar_sync(EW * 32);                          // every warp's raw store and partials are issued
           if (warp == 2 && lane == 0)
-            gn_item_arrive_wait(p.gn.counter + b, static_cast<unsigned>(p.tiles_per_batch * n_tiles_n));
+            gn_item_arrive_wait(p.gn.counter + b, static_cast<unsigned>(p.tiles_per_batch * n_tiles_n), p.gn.counter + p.B);
           epi_bar_sync(EW * 32);
+          if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 4);    // item complete
           if (warp == 2 + EW - 1 && lane == 0)              // (a warp that folds no group unless the tile spans EW groups)
             gn_item_depart(p.gn.counter + b, static_cast<unsigned>(p.tiles_per_batch * n_tiles_n));
           const int cpg = p.N / p.gn.G;
@@ -618,6 +637,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
             }
           }
           epi_bar_sync(EW * 32);
+          if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 5);    // statistics folded
 #pragma unroll 1
           for (int ch = part; ch < NCH; ch += PARTS) {
             const int gcol = n0 + ch * 32;
@@ -636,6 +656,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) { trace_ev(p, 0, 0, 11); trace_ev(p, 3, 0, 2); }
 }
 
 // ---------------------------------------------------------------- CUDA-core reference of the same contract

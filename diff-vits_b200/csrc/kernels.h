@@ -94,7 +94,8 @@ struct GemmXf {
 // copy of its own tile. Only the epilogue warps wait; the producer / MMA warps go on with the CTA's next tile.
 struct GemmGnOut {
   void* out;                                  // normalised 16-bit [B, L, ld_out] (same geometry as the raw output)
-  unsigned* counter;                          // [B], zero between launches (arrivals then departures; the last departure resets it)
+  unsigned* counter;                          // [B], zero between launches (arrivals then departures; the last departure resets it);
+                                              // counter[B] is a sticky flag: set when a wait gave up (results of that plan are then invalid)
   int G; float eps; int silu;
   const float* gamma; const float* beta;      // [N]
   const float* scale_shift; int ss_ld;        // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + N + c]

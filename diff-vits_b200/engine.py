@@ -318,10 +318,16 @@ class DenoiserEngine:
         check(self.lib.dv_plan_sample_diag(self._plan, C.byref(off), C.byref(rows)))
         return self.workspace[off.value: off.value + rows.value * 16].view(torch.float32).view(rows.value, 4)
 
+    def health_flag(self) -> torch.Tensor:
+        """uint32 view into the workspace (device): non-zero once a bounded in-kernel wait gave up (dv_plan_health_flag)."""
+        off = C.c_size_t()
+        check(self.lib.dv_plan_health_flag(self._plan, C.byref(off)))
+        return self.workspace[off.value: off.value + 4].view(torch.int32)
+
     def check_finite(self) -> None:
         """The reference asserts `torch.isnan(x).any() == False` on every denoiser call (model3.py:903, one device sync per
         step); here the update kernels count non-finite values and one read after the loop raises the same AssertionError."""
-        _raise_nonfinite([self.sample_diag()])
+        _raise_nonfinite([self.sample_diag()], [self.health_flag()])
 
     # ---- debug: block outputs left in the workspace by the last denoiser call
     def named_tensors(self) -> Dict[str, torch.Tensor]:
@@ -371,7 +377,10 @@ class DenoiserEngine:
         return self.lib.dv_plan_last_sample_launches(self._plan)
 
 
-def _raise_nonfinite(diags) -> None:
+def _raise_nonfinite(diags, flags=()) -> None:
+    if flags and int(torch.stack([f.reshape(()) for f in flags]).sum()) != 0:
+        raise RuntimeError("diffvits_b200: an in-kernel wait of the fused GroupNorm gave up (CTAs of one launch were not "
+                           "co-scheduled); the results of this plan are invalid. Rebind the plan; DV_GN_OUT=0 disables the fusion")
     if not diags or diags[0].numel() == 0:
         return
     bad = torch.stack([d[:, 0] for d in diags]).sum(0).cpu()      # one small D2H (<= 2 KB) after the loop
@@ -479,7 +488,7 @@ class DenoiserGroup:
         return out
 
     def check_finite(self) -> None:
-        _raise_nonfinite([e.sample_diag() for e in self.engines])
+        _raise_nonfinite([e.sample_diag() for e in self.engines], [e.health_flag() for e in self.engines])
 
     def named_tensors(self) -> Dict[str, torch.Tensor]:
         outs = [e.named_tensors() for e in self.engines]

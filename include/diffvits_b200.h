@@ -140,6 +140,11 @@ DV_API int dv_plan_last_sample_launches(const dv_plan* plan);
  * (0 DPM-Solver++ update, 1 UniPC predictor, 2 UniPC corrector)}. Valid once the stream has passed the loop; the caller reads
  * them with the latent (the drop-in raises the reference's AssertionError from them). */
 DV_API int dv_plan_sample_diag(const dv_plan* plan, size_t* offset, int* rows);
+/* One uint32 at byte `offset` of the workspace, zero while the plan is healthy. The GroupNorm that the producing GEMM applies
+ * in its epilogue waits (bounded) for the other tiles of a batch item; if such a wait ever gives up (the CTAs of one launch
+ * were not co-scheduled: not observed, but the hardware gives no guarantee when several plans run concurrently on one
+ * device) the kernel sets this flag instead of hanging the GPU and the plan's results must be discarded (rebind to clear). */
+DV_API int dv_plan_health_flag(const dv_plan* plan, size_t* offset);
 
 /* ---- PromptEncoder (model3.py:382-433; model.py:72-97, 137-171; operations.py:644-714, 784-821) ---------------------------
  * The speech-prompt encoder whose output is the UNet's encoder_hidden_states: ConvLayer pre (LayerNorm + 1x1), n_layers x

@@ -9,5 +9,5 @@ timeout 600 python bench.py --steps 3 --no-cpu --no-gpu-ref --no-modes > gpurun_
 python -c "
 import json
 d=json.loads(open('gpurun_out/${TAG}_bench.json').read().strip().splitlines()[-1])
-print('step ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], {k:(v['launches_per_call'], v['ms_per_call']) for k,v in d['roofline']['kernels'].items()})
+print('step ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], {k:(v.get('launches_per_call'), v.get('ms_per_call')) for k,v in d['roofline']['kernels'].items()})
 "
