@@ -81,6 +81,7 @@ struct EpiCtx {
   uint32_t coal;    // smem address for the row-contiguous phase (row = lane/4, 16-byte piece = lane%4)
   uint32_t sbias;   // smem address of the bias vector
   int lane, srow, spiece;
+  bool trace_warp;  // debug timeline: this is the warp that records epilogue events
 };
 
 __device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& e, int gcol, int lq, size_t rowbase, uint4 (&rv)[4],
@@ -110,6 +111,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     for (int i = 0; i < 4; ++i) sts128(e.coal + i * 8 * EPI_PITCH, rv[i]);
   }
   tmem_ld_wait();
+  if (e.trace_warp && e.lane == 0) trace_ev(p, 2, gcol, 6);      // TMEM load complete
   if (last) {                                           // last TMEM read of this tile by this warp
     tc_fence_before();
     if (e.lane == 0) mbar_arrive(empty_bar);
@@ -176,6 +178,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     if (e.lane == 0)
       *reinterpret_cast<float4*>(p.stats + (stat_chunk * p.stats_nblk + (gcol >> 4)) * 2) = make_float4(a0, b0, a1, b1);
   }
+  if (e.trace_warp && e.lane == 0) trace_ev(p, 2, gcol, 7);      // math done
 #pragma unroll
   for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
     const uint32_t* pk = (SPLIT && pl) ? packed_lo : packed;
@@ -194,6 +197,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     }
     __syncwarp();
   }
+  if (e.trace_warp && e.lane == 0) trace_ev(p, 2, gcol, 8);      // stores issued
 }
 
 
@@ -381,17 +385,21 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           }
         }
       }
+      // tile coordinates (two integer divisions by run-time values, a dependent chain of ~300 clk for one thread) are taken
+      // BEFORE the wait on the previous kernel for the first tile and one tile ahead afterwards: they sit on the critical path
+      // between "previous kernel complete" and the first A load otherwise
+      int tile = blockIdx.x;
+      int mi = tile / n_tiles_n, n0 = (tile % n_tiles_n) * BN;
+      int b = mi / p.tiles_per_batch, l0 = (mi % p.tiles_per_batch) * BM;
+      asm volatile("" ::"r"(mi), "r"(n0), "r"(b), "r"(l0));    // (keeps the compiler from sinking them below the wait)
       pdl_wait();
       trace_ev(p, 0, 0, 10);                              // previous kernel complete
       trace_ev(p, 3, 0, 1);
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;                                     // panels issued by this CTA so far (across tiles)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mi = tile / n_tiles_n;
-        const int n0 = (tile % n_tiles_n) * BN;
-        const int b = mi / p.tiles_per_batch;
-        const int l0 = (mi % p.tiles_per_batch) * BM;
+      for (; tile < num_tiles; tile += gridDim.x, mi = tile / n_tiles_n, n0 = (tile % n_tiles_n) * BN,
+                               b = mi / p.tiles_per_batch, l0 = (mi % p.tiles_per_batch) * BM) {
         int kp = 0;
         trace_ev(p, 0, tile, 0);
         for (int s = 0; s < p.nseg; ++s) {
@@ -471,6 +479,11 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     e.mine = slab + lane * EPI_PITCH;
     e.coal = slab + e.srow * EPI_PITCH + e.spiece * 16;
     e.sbias = smem_u32(smem + SL::BIAS_OFF);
+#ifdef DV_DEBUG_HOOKS
+    e.trace_warp = warp == 2 && p.trace != nullptr;
+#else
+    e.trace_warp = false;
+#endif
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {

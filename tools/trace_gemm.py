@@ -16,6 +16,7 @@ NAMES = {(0, 8): "kernel entry", (0, 9): "prologue done (barriers, TMEM, bias)",
          (0, 0): "producer: tile start (A loads issued)", (0, 11): "kernel exit",
          (1, 0): "mma: wait tmem_empty", (1, 1): "mma: got accumulator", (1, 3): "mma: first panel landed", (1, 2): "mma: all panels issued + commit",
          (2, 0): "epi: wait accumulator", (2, 1): "epi: got accumulator", (2, 2): "epi: tile done",
+         (2, 6): "epi chunk: TMEM load complete", (2, 7): "epi chunk: math done", (2, 8): "epi chunk: stores issued",
          (2, 3): "epi: pass 1 done", (2, 4): "epi: item complete", (2, 5): "epi: statistics folded"}
 CASES = [  # (B, L, K, N, mode, with_res, bn)
     (32, 250, 384, 384, 0, False, 192), (32, 250, 384, 384, 0, True, 192), (32, 500, 256, 768, 0, False, 256),
