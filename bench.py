@@ -389,7 +389,15 @@ def run_native(args):
     torch.manual_seed(1234)
     unet = UNet1DConditionModel(**UNET_KW).eval().to(dev)
     # noise / conditioning are drawn for the GLOBAL batch with one seed, then sharded (bit-identical to 1 GPU)
-    from diffvits_b200.dist import gather_latents, shard_inputs
+    from diffvits_b200.dist import gather_latents, init_native_comm, shard_inputs
+    gather_how = "single GPU: no collective"
+    if world > 1:
+        gather_how = ("ncclAllGather issued in-stream through the C ABI (dv_comm_all_gather, library-owned communicator)"
+                      if init_native_comm(dev) and not os.environ.get("DV_TORCH_GATHER")
+                      else "torch.distributed.all_gather_into_tensor (NCCL)")
+        if os.environ.get("DV_TORCH_GATHER"):
+            from diffvits_b200.dist import close_native_comm
+            close_native_comm()
     x_h, cond_h, _unused = (t.pin_memory() for t in shard_inputs(inputs.make_inputs(Bg * world, T, Tp), rank, world))
     # the speech prompt (mel, model3.py:906) and its encoder: encoded ONCE per job by the native PromptEncoder plan
     # (the reference re-encodes it in every denoiser call); random-init parameters in the reference's state_dict layout
@@ -632,6 +640,7 @@ def run_native(args):
                        "order": 2, "weights": "random init seed 1234 (64.7 M params)", "inputs": "N(0,1) seed 0",
                        "l2": "no flush: per-step working set (workspace %.2f GB + weights 0.15 GB) >> 126 MB L2" %
                              (eng.ws_bytes / 1e9),
+                       "gather": gather_how,
                        "graph": "whole loop = one CUDA graph (%d kernel nodes, %d concurrent lanes of %s utterances)" %
                                 (eng.last_sample_launches, eng.lanes, "/".join(map(str, eng.sizes)))},
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
@@ -669,6 +678,8 @@ def run_native(args):
         line["precision_modes"] = modes
     if world > 1:
         dist.barrier()
+        from diffvits_b200.dist import close_native_comm
+        close_native_comm()
         dist.destroy_process_group()
     if rank == 0:
         # free this process's GPU memory before the reference legs run in their own processes

@@ -94,6 +94,10 @@ SIGNATURES = {
     "dv_prompt_plan_manifest_json": (C.c_char_p, [_vp]),
     "dv_prompt_plan_bind": (_i, [_vp, _vp, _vp, _vp]),
     "dv_prompt_encode": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "dv_comm_unique_id": (_i, [C.c_char_p, _vp]),
+    "dv_comm_init": (_i, [C.c_char_p, _vp, _i, _i, C.POINTER(_vp)]),
+    "dv_comm_all_gather": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "dv_comm_destroy": (None, [_vp]),
     "dv_plan_tensor_count": (_i, [_vp]),
     "dv_plan_tensor_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_sz), C.POINTER(_i), C.POINTER(_i)]),
     "dv_plan_op_count": (_i, [_vp]),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 DEBUG = os.environ.get("DV_DEBUG", "0") == "1"
 BUILD = os.path.join(HERE, "build_dbg" if DEBUG else "build")
 LIB = os.path.join(HERE, "libdiffvits_b200_dbg.so" if DEBUG else "libdiffvits_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu", "elementwise.cu", "engine.cu", "prompt_encoder.cu", "api.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu", "elementwise.cu", "engine.cu", "prompt_encoder.cu", "comm.cu", "api.cu"]
 KERNEL_SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "chain_tc.cu", "attention.cu", "attention_tc.cu", "attention_split.cu", "norm.cu",
                   "elementwise.cu"]
 NVCC_FLAGS = [
@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(compile_one, jobs))
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-cudart", "static"]
+               "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -383,6 +383,28 @@ int dv_unipc_correct(float* x, const float* base, const float* mt, const float* 
   if (rc != DV_OK) return rc;
   return ck(dv::launch_unipc_corr(x, base, mt, m1, d, n, S(stream)), "unipc_correct");
 }
+// ---- multi-GPU gather (csrc/comm.cu)
+int dv_comm_unique_id(const char* nccl_path, void* id128) {
+  if (!id128) return fail(DV_ERR_INVALID, "null id buffer");
+  std::string err;
+  int rc = dv::comm_unique_id(nccl_path, id128, err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+int dv_comm_init(const char* nccl_path, const void* id128, int rank, int nranks, dv_comm** out) {
+  std::string err;
+  dv::Comm* c = nullptr;
+  int rc = dv::comm_init(nccl_path, id128, rank, nranks, &c, err);
+  if (rc != DV_OK) return fail(rc, err);
+  *out = reinterpret_cast<dv_comm*>(c);
+  return DV_OK;
+}
+int dv_comm_all_gather(dv_comm* comm, const float* send, float* recv, size_t count, void* stream) {
+  std::string err;
+  int rc = dv::comm_all_gather(reinterpret_cast<dv::Comm*>(comm), send, recv, count, S(stream), err);
+  return rc == DV_OK ? rc : fail(rc, err);
+}
+void dv_comm_destroy(dv_comm* comm) { dv::comm_destroy(reinterpret_cast<dv::Comm*>(comm)); }
+
 int dv_nct_to_ntc(const float* src, void* dst, int B, int C, int T, int ld, int col0, void* stream) {
   int rc = require_device();
   if (rc != DV_OK) return rc;

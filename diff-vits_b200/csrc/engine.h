@@ -247,6 +247,13 @@ struct PromptPlan {
   int encode(const float* prompt, const int32_t* lengths, float* ehs_out, cudaStream_t st, std::string& err);
 };
 
+// ---- multi-GPU: the single collective of the path (csrc/comm.cu), NCCL resolved at run time
+struct Comm;
+int comm_unique_id(const char* nccl_path, void* id128, std::string& err);
+int comm_init(const char* nccl_path, const void* id128, int rank, int nranks, Comm** out, std::string& err);
+int comm_all_gather(Comm* c, const float* send, float* recv, size_t count, cudaStream_t st, std::string& err);
+void comm_destroy(Comm* c);
+
 bool make_tmap_3d(CUtensorMap* m, const void* base, int view_c, int ld, int L, int B, size_t batch_stride_elems,
                   std::string& err, int box_rows = 128);
 bool make_tmap_2d(CUtensorMap* m, const void* base, int k_tot, int rows, int box_rows, std::string& err);

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DV_VERSION 102
+#define DV_VERSION 103
 
 #if defined(__GNUC__)
 #define DV_API __attribute__((visibility("default")))
@@ -170,6 +170,20 @@ DV_API int dv_prompt_plan_bind(dv_prompt_plan* plan, void* workspace, const void
  * (device), ehs_out [B, Tp, hidden] fp32 = the encoder_hidden_states Diffusion_Encoder.forward passes to the UNet
  * (model3.py:905-912), rows >= lengths[b] zero. */
 DV_API int dv_prompt_encode(dv_prompt_plan* plan, const float* prompt, const int32_t* lengths, float* ehs_out, void* stream);
+
+/* ---- multi-GPU -----------------------------------------------------------------------------------------
+ * Independent utterances are batch-sharded, one process per GPU; the only collective of the path is ONE all-gather of the
+ * output latents per job (the reference has no cross-sample reduction). It is issued in-stream, right behind dv_sample, on a
+ * communicator this library owns. NCCL is resolved at run time (`nccl_path`, else $DV_NCCL_LIB, else libnccl.so.2 - pass the
+ * path of the libnccl the host framework already loaded so that both use one instance); nothing is linked.
+ *   rank 0: dv_comm_unique_id(path, id)  ->  the 128 bytes travel to every rank by any means (the drop-in broadcasts them
+ *   through torch.distributed)  ->  every rank: dv_comm_init(path, id, rank, nranks, &comm) (collective call)
+ *   dv_comm_all_gather: recv[r * count .. (r + 1) * count) = rank r's `send` (count fp32 elements per rank, equal on all). */
+typedef struct dv_comm dv_comm;
+DV_API int dv_comm_unique_id(const char* nccl_path, void* id128);
+DV_API int dv_comm_init(const char* nccl_path, const void* id128, int rank, int nranks, dv_comm** out);
+DV_API int dv_comm_all_gather(dv_comm* comm, const float* send, float* recv, size_t count, void* stream);
+DV_API void dv_comm_destroy(dv_comm* comm);
 
 /* ---- measurement support ------------------------------------------------------------------------------------- */
 /* Block outputs (bf16 [B, L, C] at byte `offset` of the workspace, named by reference module path) that are still
