@@ -629,10 +629,11 @@ def run_native(args):
         line = {
             "metric": "denoised latent frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_res, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16s": "fp16", "fp32x3": "bf16x3"}[args.precision],
+            "scaling": args.scaling, "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "fp16", "fp16s": "fp16", "fp32x3": "bf16x3"}[args.precision],
             "data": "synthetic",
             "rtf": (ms_res * 1e-3) / (frames * 256 / 24000.0),
             "config": {"workload": desc + {"bf16": ", BF16 operands / FP32 accumulate",
+                                           "fp16": ", FP16 operands / FP32 accumulate",
                                            "fp16s": ", FP16 operands / FP32 accumulate, hi+lo residual stream",
                                            "fp32x3": ", hi+lo BF16 operand split (3 MMAs), FP32-class"}[args.precision]
                                    + ", FP32 sampler state",
@@ -657,10 +658,12 @@ def run_native(args):
         import copy
         modes = {"bf16": {"ms_per_step": round(ms_res, 2), "frames_per_s": round(value, 1),
                           "parity_vs_fp32_reference": "per call 8.3e-3 rel-L2 / 1.4e-2 max-abs (the reference under autocast-bf16: 1.05e-2)"}}
-        notes = {"fp16s": "FP16 operands + hi/lo residual stream, one MMA per product: per call 8.1e-4 rel-L2 / 1.3e-3 max-abs, "
+        notes = {"fp16": "FP16 operands in place of the BF16 ones (same launches, chains and fused norms): see "
+                         "tests/test_gpu_precision.py for the measured parity (~1e-3 rel-L2 per call)",
+                 "fp16s": "FP16 operands + hi/lo residual stream, one MMA per product: per call 8.1e-4 rel-L2 / 1.3e-3 max-abs, "
                           "10-step UniPC latent 9.0e-4, 50-step DPM-Solver++ latent 1.9e-3",
-                 "fp32x3": "hi+lo BF16 split, three MMAs per product, FP32 attention core: per call 1.5e-5 rel-L2, 50-step latent 3.8e-5"}
-        for mode in ("fp16s", "fp32x3"):
+                 "fp32x3": "hi+lo BF16 split, three MMAs per product (GEMMs and attention): per call 1.5e-5 rel-L2, 50-step latent 3.8e-5"}
+        for mode in ("fp16", "fp16s", "fp32x3"):
             u2 = copy.deepcopy(unet)
             u2.native_precision = mode
             n2 = diffvits_b200.NativeDenoiser(u2, cond_d, ehs_d)
@@ -713,7 +716,7 @@ def main():
                          "(default for --workload c4)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong: global batch (default: the workload's); weak: overrides the per-GPU batch")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16s", "fp32x3"],
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp16s", "fp32x3"],
                     help="bf16: BF16 operands (headline); fp16s: FP16 operands + hi/lo residual stream (1e-3 gate); "
                          "fp32x3: hi+lo BF16 operand split, FP32-class accuracy")
     ap.add_argument("--cpu-target", type=float, default=10.0, help="reference arm: seconds of CPU work per timed step")

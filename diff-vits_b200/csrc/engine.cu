@@ -687,13 +687,14 @@ int Plan::build(std::string& err) {
   if (c.cross_attention_dim % 64 != 0) { err = "cross_attention_dim must be a multiple of 64"; return DV_ERR_UNSUPPORTED; }
   if (c.x_channels < 1 || c.x_channels > c.in_channels) { err = "x_channels out of range"; return DV_ERR_INVALID; }
   if (c.out_channels > 128) { err = "out_channels > 128 not supported"; return DV_ERR_UNSUPPORTED; }
-  if (c.precision != DV_PRECISION_BF16 && c.precision != DV_PRECISION_FP32X3 && c.precision != DV_PRECISION_FP16S) {
+  if (c.precision != DV_PRECISION_BF16 && c.precision != DV_PRECISION_FP32X3 && c.precision != DV_PRECISION_FP16S &&
+      c.precision != DV_PRECISION_FP16) {
     err = "unknown precision";
     return DV_ERR_INVALID;
   }
   triple = c.precision == DV_PRECISION_FP32X3;
-  f16 = c.precision == DV_PRECISION_FP16S;
-  split = triple || f16;
+  f16 = c.precision == DV_PRECISION_FP16S || c.precision == DV_PRECISION_FP16;
+  split = triple || c.precision == DV_PRECISION_FP16S;
   K = &kernel_api(f16);
   emb_dim = 4 * c.block_out_channels[0];
   if (emb_dim != 512) { err = "time_embed_dim must be 512 (block_out_channels[0] == 128)"; return DV_ERR_UNSUPPORTED; }

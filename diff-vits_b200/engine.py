@@ -148,12 +148,13 @@ def pack_params(manifest: List[dict], sd: Dict[str, torch.Tensor], nbytes: int) 
     return blob
 
 
-PRECISIONS = {"bf16": 0, "fp32x3": 1, "fp16s": 2}
+PRECISIONS = {"bf16": 0, "fp32x3": 1, "fp16s": 2, "fp16": 3}
 
 
 def default_precision() -> str:
-    """DV_PRECISION=bf16 (default, fast path) | fp16s (FP16 operands + hi/lo residual stream, meets the 1e-3 gate) |
-    fp32x3 (hi + lo BF16 operand split, three MMAs per product, FP32-class accuracy)."""
+    """DV_PRECISION=bf16 (default, fast path) | fp16 (FP16 operands, the BF16 mode's speed, ~1e-3 per call, narrower range) |
+    fp16s (FP16 operands + hi/lo residual stream, meets the 1e-3 gate) | fp32x3 (hi + lo BF16 operand split, three MMAs per
+    product, FP32-class accuracy)."""
     import os
     p = os.environ.get("DV_PRECISION", "bf16").lower()
     if p not in PRECISIONS:
@@ -338,7 +339,7 @@ class DenoiserEngine:
         for i in range(self.lib.dv_plan_tensor_count(self._plan)):
             check(self.lib.dv_plan_tensor_info(self._plan, i, buf, 160, C.byref(off), C.byref(L), C.byref(Cc)))
             n = self.B * L.value * Cc.value * 2
-            dt = torch.float16 if self.precision == "fp16s" else torch.bfloat16
+            dt = torch.float16 if self.precision in ("fp16s", "fp16") else torch.bfloat16
             t = self.workspace[off.value: off.value + n].view(dt).view(self.B, L.value, Cc.value)
             if self.precision in ("fp32x3", "fp16s"):      # hi + lo planes -> the fp32 value they carry
                 lo = self.workspace[off.value + n: off.value + 2 * n].view(dt).view(self.B, L.value, Cc.value)

@@ -54,7 +54,7 @@ typedef struct dv_unet_cfg {
   int num_heads;              /* `attention_head_dim` in the reference ctor (it is the head COUNT): 8 */
   float norm_eps;             /* 1e-5 */
   int x_channels;             /* leading input channels that change every step (the noisy latent): 100 */
-  int precision;              /* DV_PRECISION_BF16 (0) or DV_PRECISION_FP32X3 (1), see below */
+  int precision;              /* DV_PRECISION_BF16 (0), _FP32X3 (1), _FP16S (2) or _FP16 (3), see below */
 } dv_unet_cfg;
 
 /* Arithmetic of the contractions. The reference computes in FP32 (unet1d/lora.py:99-104, attention_processor.py:1032).
@@ -71,6 +71,11 @@ typedef struct dv_unet_cfg {
  *                        emulation at 8.0e-4 rel-L2 per call vs the FP32 reference (plain FP16 operands: 1.0e-3): the mode
  *                        that meets north_star's 1e-3 gate of the 16-bit tier. */
 #define DV_PRECISION_FP16S 2
+/*  DV_PRECISION_FP16   : FP16 operands everywhere the BF16 mode has BF16 ones (single planes, the same launches, chains and
+ *                        fused norms: the BF16 mode's speed) - 3 more mantissa bits per rounding: ~1e-3 rel-L2 per call instead
+ *                        of 8e-3. Conversions saturate at +-65504; the narrower exponent range is the price (the sampler
+ *                        diagnostics report non-finite values). */
+#define DV_PRECISION_FP16 3
 
 typedef struct dv_plan dv_plan;
 
