@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5|c1]
                     [--impl native|reference|gpu-reference] [--scaling weak|strong] [--global-batch B]
-                    [--precision bf16|fp32x3]
+                    [--precision bf16|fp16|fp16s|fp32x3]
 
 One "step" = one complete sampling loop (all denoiser calls + sampler updates) over one batch of synthetic
 utterances. N > 1: launched under torchrun, one rank per GPU, independent utterances batch-sharded, one all-gather of the
@@ -658,8 +658,8 @@ def run_native(args):
         import copy
         modes = {"bf16": {"ms_per_step": round(ms_res, 2), "frames_per_s": round(value, 1),
                           "parity_vs_fp32_reference": "per call 8.3e-3 rel-L2 / 1.4e-2 max-abs (the reference under autocast-bf16: 1.05e-2)"}}
-        notes = {"fp16": "FP16 operands in place of the BF16 ones (same launches, chains and fused norms): see "
-                         "tests/test_gpu_precision.py for the measured parity (~1e-3 rel-L2 per call)",
+        notes = {"fp16": "FP16 operands in place of the BF16 ones (same launches, chains and fused norms): per call 1.0e-3 rel-L2 / "
+                         "1.6e-3 max-abs, 10-step UniPC latent 1.1e-3, 50-step DPM-Solver++ latent 2.6e-3",
                  "fp16s": "FP16 operands + hi/lo residual stream, one MMA per product: per call 8.1e-4 rel-L2 / 1.3e-3 max-abs, "
                           "10-step UniPC latent 9.0e-4, 50-step DPM-Solver++ latent 1.9e-3",
                  "fp32x3": "hi+lo BF16 split, three MMAs per product (GEMMs and attention): per call 1.5e-5 rel-L2, 50-step latent 3.8e-5"}
@@ -717,8 +717,8 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong: global batch (default: the workload's); weak: overrides the per-GPU batch")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp16s", "fp32x3"],
-                    help="bf16: BF16 operands (headline); fp16s: FP16 operands + hi/lo residual stream (1e-3 gate); "
-                         "fp32x3: hi+lo BF16 operand split, FP32-class accuracy")
+                    help="bf16: BF16 operands (headline); fp16: FP16 operands, same program; fp16s: FP16 operands + hi/lo "
+                         "residual stream (1e-3 gate); fp32x3: hi+lo BF16 operand split, FP32-class accuracy")
     ap.add_argument("--cpu-target", type=float, default=10.0, help="reference arm: seconds of CPU work per timed step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-ref", action="store_true", help="skip the gpu_reference leg")
