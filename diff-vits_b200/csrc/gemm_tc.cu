@@ -211,13 +211,13 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {   // named barrier 
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 // One thread per CTA: arrive on the batch item's counter, wait for all `S` tiles of the item, depart; the last departure
-// resets the counter for the next launch. The wait is bounded (a few ms) so that a scheduling assumption that does not hold
+// resets the counter for the next launch. The wait is bounded (~0.1 s) so that a scheduling assumption that does not hold
 // produces wrong numbers (caught by the parity tests) instead of a hung GPU.
 __device__ __forceinline__ void gn_item_arrive_wait(unsigned* c, unsigned S, unsigned* gave_up) {
   // release: (after the CTA barrier) the tile's raw store and partials are visible before the arrival is. A release RMW instead
   // of __threadfence() + atomicAdd: the latter compiles to MEMBAR.SC.GPU, the sequentially-consistent fence.
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
-  for (int spins = 0; spins < (1 << 20); ++spins) {
+  for (int spins = 0; spins < (1 << 17); ++spins) {   // ~0.1 s at the L2 round-trip rate; an item completes within ~50 us
     if (ld_acquire_u32(c) >= S) return;
     if (spins > 4) __nanosleep(40);
   }
