@@ -129,8 +129,8 @@ struct Builder {
   int bound_n = 0;
   TRef boundary(int L, int C) {
     TRef t;
-    t.L = L; t.C = C; t.lo = false;
-    const size_t bytes = tensor_bytes(L, C, false);
+    t.L = L; t.C = C; t.lo = P.triple;           // GEMM operands carry a lo plane in FP32X3 only (as tmp() does)
+    const size_t bytes = tensor_bytes(L, C, t.lo);
     if (bytes > bound_max) bound_max = bytes;
     t.off = BOUND_TAG | ((bound_n++ & 1) ? BOUND_PAR : 0);
     return t;
@@ -143,7 +143,7 @@ struct Builder {
     if (pr.kind != OP_GEMM) return false;
     const GemmDesc& g = pr.g;
     if (g.out_mode != GEMM_OUT_BF16 || g.gnout.on || g.out_bs != 0 || g.trim_col != 0 || g.out_dynamic || g.stats_off < 0 ||
-        g.out.off != x0.off || g.out.lo || g.n != x0.C)
+        g.out.off != x0.off || g.n != x0.C)
       return false;
     return ((g.l_out + 127) / 128) * (g.n_pad / 64) <= 128;
   }
@@ -711,7 +711,9 @@ int Plan::build(std::string& err) {
     const char* g2 = getenv("DV_GEMM2");
     gemm2 = fuse_gn || (g2 && g2[0] == '1');
     const char* go = getenv("DV_GN_OUT");
-    gn_out = !split && !gemm2 && !(go && go[0] == '0');
+    // default: on in the single-plane modes (BF16 / FP16: C2 step -0.8 %), off in the split modes where the tail re-reads and
+    // rewrites two planes and measured slower (fp16s 239.6 vs 235.8 ms, fp32x3 414.3 vs 412.7); DV_GN_OUT=1 / 0 forces it
+    gn_out = !gemm2 && (go ? go[0] != '0' : !split);
   }
   Builder b(*this);
   const int C0 = c.block_out_channels[0];
@@ -988,6 +990,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
         if (g.gnout.on) {
           GemmGnOut& n = p.gn;
           n.out = ws + g.gnout.out.off;
+          n.out_lo = g.gnout.out.lo ? ws + g.gnout.out.off + plane(g.gnout.out) : nullptr;
           n.counter = reinterpret_cast<unsigned*>(ws + off_gncnt);
           n.G = cfg.norm_num_groups; n.eps = g.gnout.eps; n.silu = g.gnout.silu ? 1 : 0;
           n.gamma = pf(g.gnout.gamma); n.beta = pf(g.gnout.beta);

@@ -146,7 +146,7 @@ struct Plan {
   bool gemm2 = false;        // DV_GEMM2=1: k=3 convs as ONE shared-tap segment on the two-ring kernel (csrc/gemm_tc2.cu) instead of
                              // three single-tap segments on the one-ring kernel (measured 4 % slower per C2 step: off)
   bool gn_out = true;        // single-source GroupNorms applied by the PRODUCING GEMM's epilogue (per-batch-item arrival counter, GemmGnOut):
-                             // 47 of the 61 gn_apply launches of a call disappear; DV_GN_OUT=0 keeps them stand-alone. BF16 mode only.
+                             // 47 of the 61 gn_apply launches of a call disappear; DV_GN_OUT=0 keeps them stand-alone. Default in the single-plane modes; parity-tested in all.
   bool fuse_gn = false;      // DV_FUSE_GN=1 (implies gemm2): GroupNorm (+SiLU, +scale/shift) applied inside the consuming conv / 1x1 GEMM (operand transform in
                              // shared memory) instead of a stand-alone gn_apply pass. Parity-tested; measured 13 % slower per C2 step (gemm_tc2.cu header): off
   std::vector<ParamSlot> slots;

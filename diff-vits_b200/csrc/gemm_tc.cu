@@ -254,17 +254,24 @@ __device__ __forceinline__ void gn_group_fold(const float* base, int chunks, int
 }
 // Normalise one 32-row x 32-column chunk of the tile this warp has just stored: read back in the row-contiguous layout
 // (each lane: 8 columns of 4 rows), y = SiLU?(x * ca + cb) with the coefficients built exactly like gn_apply_kernel's.
+// SPLIT: the raw tensor is hi + lo (both planes were just stored by this warp); the normalised tensor gets a lo plane where
+// the mode carries one for GEMM operands (p.gn.out_lo, FP32X3) - the same arithmetic as gn_apply_kernel<true>.
+template <bool SPLIT>
 __device__ __forceinline__ void gn_apply_chunk(const GemmParams& p, const EpiCtx& e, int gcol, int lq, int b, size_t obase,
                                                const float* s_mean, const float* s_rstd, int gfirst, int cpg) {
   const int c8 = gcol + e.spiece * 8;
   if (c8 >= p.N) return;
   const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(p.out);
+  const __nv_bfloat16* raw_lo = reinterpret_cast<const __nv_bfloat16*>(p.out_lo);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.gn.out);
   uint4 v[4];
+  uint4 vl[SPLIT ? 4 : 1];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int l = lq + i * 8 + e.srow;
     v[i] = l < p.L ? __ldcg(reinterpret_cast<const uint4*>(raw + obase + static_cast<size_t>(l) * p.ld_out + c8)) : make_uint4(0, 0, 0, 0);
+    if (SPLIT)
+      vl[i] = l < p.L ? __ldcg(reinterpret_cast<const uint4*>(raw_lo + obase + static_cast<size_t>(l) * p.ld_out + c8)) : make_uint4(0, 0, 0, 0);
   }
   const int grp = c8 / cpg - gfirst;
   const float mean = s_mean[grp], rstd = s_rstd[grp];
@@ -301,15 +308,25 @@ __device__ __forceinline__ void gn_apply_chunk(const GemmParams& p, const EpiCtx
     const int l = lq + i * 8 + e.srow;
     if (l >= p.L) continue;
     const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-    uint32_t y[4];
+    uint32_t y[4], yl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float a = fmaf(bf16_lo(w[j]), ca[2 * j], cb[2 * j]);
-      float c = fmaf(bf16_hi(w[j]), ca[2 * j + 1], cb[2 * j + 1]);
+      float xa = bf16_lo(w[j]), xc = bf16_hi(w[j]);
+      if (SPLIT) {
+        const uint32_t wl = j == 0 ? vl[i].x : (j == 1 ? vl[i].y : (j == 2 ? vl[i].z : vl[i].w));
+        xa += bf16_lo(wl);
+        xc += bf16_hi(wl);
+      }
+      float a = fmaf(xa, ca[2 * j], cb[2 * j]);
+      float c = fmaf(xc, ca[2 * j + 1], cb[2 * j + 1]);
       if (p.gn.silu) { a = silu_f(a); c = silu_f(c); }
       y[j] = pack_bf16(a, c);
+      if (SPLIT) yl[j] = pack_bf16(a - bf16_lo(y[j]), c - bf16_hi(y[j]));
     }
     *reinterpret_cast<uint4*>(dst + obase + static_cast<size_t>(l) * p.ld_out + c8) = make_uint4(y[0], y[1], y[2], y[3]);
+    if (SPLIT && p.gn.out_lo != nullptr)
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.gn.out_lo) + obase + static_cast<size_t>(l) * p.ld_out + c8) =
+          make_uint4(yl[0], yl[1], yl[2], yl[3]);
   }
 }
 
@@ -620,7 +637,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (!TRIM && !SPLIT && p.gn.out != nullptr) {
+        if (!TRIM && p.gn.out != nullptr) {
           // ---- GroupNorm of the output, applied here: wait for the other tiles of this batch item, then normalise this tile
           float* s_mean = reinterpret_cast<float*>(smem + SL::GNS_OFF);
           float* s_rstd = s_mean + 32;
@@ -655,7 +672,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           for (int ch = part; ch < NCH; ch += PARTS) {
             const int gcol = n0 + ch * 32;
             if (gcol >= p.N) continue;
-            gn_apply_chunk(p, e, gcol, lq, b, obase, s_mean, s_rstd, gfirst, cpg);
+            gn_apply_chunk<SPLIT>(p, e, gcol, lq, b, obase, s_mean, s_rstd, gfirst, cpg);
           }
         }
       }
@@ -795,9 +812,17 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
     if (p.map_rows[i] != 128) return cudaErrorInvalidValue;
   const bool dense = p.out_bs == static_cast<long long>(p.L) * p.ld_out;
   const int bn = p.bn ? p.bn : gemm_pick_bn(p.tiles_per_batch * p.B, p.n_pad);
+  if (p.gn.out != nullptr) {
+    // fused output GroupNorm: plain 16-bit epilogue with statistics, and every tile of a batch item must be co-scheduled in one
+    // round of the persistent tile loop (the item barrier waits on them): checked for the narrowest tile any branch below picks
+    if (p.out_mode != GEMM_OUT_BF16 || !p.stats || !p.gn.counter || p.relu || p.row_len || p.trim_col > 0 || !dense ||
+        p.gn.G < 1 || p.N % (16 * p.gn.G) != 0)
+      return cudaErrorInvalidValue;
+    if (p.tiles_per_batch * (p.n_pad / 64) > g_num_sms) return cudaErrorInvalidValue;
+    if ((min_i(256, p.N) + p.N / p.gn.G - 1) / (p.N / p.gn.G) + 1 > 32) return cudaErrorInvalidValue;
+  }
   if (p.out_lo != nullptr) {                             // split precision (hi + lo output planes): the same tile shapes
     if (p.res != nullptr && p.res_lo == nullptr) return cudaErrorInvalidValue;
-    if (p.gn.out != nullptr) return cudaErrorInvalidValue;
     if (p.trim_col > 0 || !dense) {
       if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;
       return launch_bn<128, 16, true, true>(p, st);
@@ -808,15 +833,6 @@ cudaError_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t st) {
       if (bn == 192 && p.n_pad % 192 == 0 && p.out_mode != GEMM_OUT_GEGLU) return launch_bn<192, 16, false, true>(p, st);
     }
     return launch_bn<128, 16, false, true>(p, st);
-  }
-  if (p.gn.out != nullptr) {
-    // fused output GroupNorm: plain bf16 epilogue with statistics, and every tile of a batch item must be co-scheduled in one
-    // round of the persistent tile loop (the item barrier waits on them)
-    if (p.out_mode != GEMM_OUT_BF16 || !p.stats || !p.gn.counter || p.relu || p.row_len || p.trim_col > 0 || !dense ||
-        p.gn.G < 1 || p.N % (16 * p.gn.G) != 0)
-      return cudaErrorInvalidValue;
-    if (p.tiles_per_batch * (p.n_pad / bn) > g_num_sms) return cudaErrorInvalidValue;
-    if ((min_i(bn, p.N) + p.N / p.gn.G - 1) / (p.N / p.gn.G) + 1 > 32) return cudaErrorInvalidValue;
   }
   if (p.relu || p.row_len) {                             // prompt-encoder epilogue options live in the rare-path instantiation
     if (p.out_mode != GEMM_OUT_BF16) return cudaErrorInvalidValue;

@@ -94,6 +94,7 @@ struct GemmXf {
 // copy of its own tile. Only the epilogue warps wait; the producer / MMA warps go on with the CTA's next tile.
 struct GemmGnOut {
   void* out;                                  // normalised 16-bit [B, L, ld_out] (same geometry as the raw output)
+  void* out_lo;                               // split precision: lo plane of the normalised tensor (FP32X3), or nullptr
   unsigned* counter;                          // [B], zero between launches (arrivals then departures; the last departure resets it);
                                               // counter[B] is a sticky flag: set when a wait gave up (results of that plan are then invalid)
   int G; float eps; int silu;

@@ -14,12 +14,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _engine(unet, B, T, Tp, fuse):
+def _engine(unet, B, T, Tp, fuse, precision="bf16"):
     from diffvits_b200.engine import DenoiserEngine
     old = os.environ.get("DV_FUSE")
     os.environ["DV_FUSE"] = "1" if fuse else "0"
     try:
-        return DenoiserEngine(unet, B, T, Tp, "cuda:0", x_channels=100)
+        return DenoiserEngine(unet, B, T, Tp, "cuda:0", x_channels=100, precision=precision)
     finally:
         if old is None:
             os.environ.pop("DV_FUSE", None)
@@ -98,23 +98,25 @@ def test_fused_deterministic(unet):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("B,T,Tp,fuse", [(2, 256, 40, True), (3, 203, 282, True), (5, 1000, 64, False), (2, 40, 16, True),
-                                         (40, 1000, 33, True)])
-def test_groupnorm_in_producer_epilogue_matches_standalone_pass(unet, monkeypatch, B, T, Tp, fuse):
+@pytest.mark.parametrize("B,T,Tp,fuse,precision", [(2, 256, 40, True, "bf16"), (3, 203, 282, True, "bf16"), (5, 1000, 64, False, "bf16"),
+                                                   (2, 40, 16, True, "bf16"), (40, 1000, 33, True, "bf16"), (3, 203, 282, True, "fp16"),
+                                                   (3, 203, 282, True, "fp16s"), (2, 256, 40, True, "fp32x3"),
+                                                   (5, 1000, 64, True, "fp32x3")])
+def test_groupnorm_in_producer_epilogue_matches_standalone_pass(unet, monkeypatch, B, T, Tp, fuse, precision):
     """GroupNorm applied by the PRODUCING GEMM's CTAs (per-batch-item arrival counter, kernels.h GemmGnOut; default) against
     the stand-alone gn_apply launches (DV_GN_OUT=0): same stored bf16 input, same partial statistics folded in the same
     order, same coefficient arithmetic, so every block output must be bit-identical. Shapes: one and several row tiles
     per item, ragged last tiles, odd lengths, more tiles than CTA slots (B = 40 x 8 tiles at level 0 = 320 tiles on 296
     slots: the persistent tile loop goes round twice and an item straddles the rounds), and the one-kernel-per-op
-    transformer program (GroupNorm fused into proj_out / conv2 at every level). The plan's health flag (a bounded
-    in-kernel wait that gave up) must stay clear."""
+    transformer program (GroupNorm fused into proj_out / conv2 at every level), and every precision mode (hi + lo planes of
+    the split modes included). The plan's health flag (a bounded in-kernel wait that gave up) must stay clear."""
     from oracle import inputs
     x, cond, ehs = (t.cuda() for t in inputs.make_inputs(B, T, Tp, seed=21))
     t = torch.tensor([611.0], device="cuda")
     outs, named, n_gn = [], [], []
     for flag in ("1", "0"):
         monkeypatch.setenv("DV_GN_OUT", flag)
-        eng = _engine(unet, B, T, Tp, fuse)
+        eng = _engine(unet, B, T, Tp, fuse, precision)
         ops = eng.op_table()
         n_gn.append(sum(1 for o in ops if o["kind"] == 2))
         assert any("+gn:" in o["tag"] for o in ops) == (flag == "1")
