@@ -120,6 +120,7 @@ DEBUG_SIGNATURES = {
     "dv_gemm_test_trace": (None, [_vp]),
     "dv_gemm_test_flags": (None, [_i]),
     "dv_debug_skip_kinds": (_i, [_i]),
+    "dv_debug_trace_op": (_i, [_vp, _i, _vp]),
 }
 
 _lib = None

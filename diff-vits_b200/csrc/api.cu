@@ -250,6 +250,12 @@ static thread_local int g_test_flags = 0;
 void dv_gemm_test_trace(unsigned long long* buf) { g_test_trace = buf; }
 void dv_gemm_test_flags(int flags) { g_test_flags = flags; }
 int dv_debug_skip_kinds(int mask) { int& m = dv::skip_kinds_mask(); const int old = m; m = mask; return old; }
+// CTA timeline of op `op` of the plan's denoiser call (tap-GEMM ops only): every later launch of that op records into `buf`
+int dv_debug_trace_op(dv_plan* plan, int op, unsigned long long* buf) {
+  if (!plan || op < 0 || op >= static_cast<int>(plan->impl.ops.size()) || plan->impl.ops[op].kind != dv::OP_GEMM) return DV_ERR_INVALID;
+  plan->impl.ops[op].gp.trace = buf;
+  return DV_OK;
+}
 #endif
 
 int dv_gemm(const dv_gemm_src* srcs, int nsrc, const dv_gemm_seg* segs, int nseg, const void* w, int k_tot, int n,

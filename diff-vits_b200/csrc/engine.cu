@@ -996,6 +996,7 @@ int Plan::bind(void* workspace, const void* prm, cudaStream_t st, std::string& e
           n.gamma = pf(g.gnout.gamma); n.beta = pf(g.gnout.beta);
           n.scale_shift = g.gnout.ss < 0 ? nullptr : reinterpret_cast<const float*>(ws + off_ss) + g.gnout.ss;
           n.ss_ld = n_all;
+          { const char* se = getenv("DV_GN_STASH"); n.no_stash = (se && se[0] == '0') ? 1 : 0; }
         }
 #ifdef DV_DEBUG_HOOKS
         { const char* de = getenv("DV_GEMM_DBG"); p.dbg_flags = de ? atoi(de) : 0; }   // timing experiments only

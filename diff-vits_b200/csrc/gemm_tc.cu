@@ -82,6 +82,7 @@ struct EpiCtx {
   uint32_t sbias;   // smem address of the bias vector
   int lane, srow, spiece;
   bool trace_warp;  // debug timeline: this is the warp that records epilogue events
+  uint32_t stash;   // fused output GroupNorm: shared-memory copy of the chunk being stored (row-contiguous layout), or 0
 };
 
 __device__ __forceinline__ void epi_load_res(const GemmParams& p, const EpiCtx& e, int gcol, int lq, size_t rowbase, uint4 (&rv)[4],
@@ -191,9 +192,10 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const EpiCtx
     for (int i = 0; i < 4; ++i) {
       const int rrow = i * 8 + e.srow;
       const bool keep = !(TRIM && lq + rrow == p.L - 1 && gcol + e.spiece * 8 >= p.trim_col);
+      const uint4 val = lds128(e.coal + i * 8 * EPI_PITCH);
       if (lq + rrow < p.L && keep && !DV_DBG(p, 8))
-        *reinterpret_cast<uint4*>(o + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) =
-            lds128(e.coal + i * 8 * EPI_PITCH);
+        *reinterpret_cast<uint4*>(o + obase + static_cast<size_t>(lq + rrow) * p.ld_out + gcol + e.spiece * 8) = val;
+      if (!SPLIT && !TRIM && e.stash) sts128(e.stash + (i * 32 + e.lane) * 16, val);   // kept on chip for the normalisation pass
     }
     __syncwarp();
   }
@@ -258,7 +260,8 @@ __device__ __forceinline__ void gn_group_fold(const float* base, int chunks, int
 // the mode carries one for GEMM operands (p.gn.out_lo, FP32X3) - the same arithmetic as gn_apply_kernel<true>.
 template <bool SPLIT>
 __device__ __forceinline__ void gn_apply_chunk(const GemmParams& p, const EpiCtx& e, int gcol, int lq, int b, size_t obase,
-                                               const float* s_mean, const float* s_rstd, int gfirst, int cpg) {
+                                               const float* s_mean, const float* s_rstd, int gfirst, int cpg, uint32_t stash,
+                                               uint32_t coef, int n0) {
   const int c8 = gcol + e.spiece * 8;
   if (c8 >= p.N) return;
   const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(p.out);
@@ -269,13 +272,25 @@ __device__ __forceinline__ void gn_apply_chunk(const GemmParams& p, const EpiCtx
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int l = lq + i * 8 + e.srow;
-    v[i] = l < p.L ? __ldcg(reinterpret_cast<const uint4*>(raw + obase + static_cast<size_t>(l) * p.ld_out + c8)) : make_uint4(0, 0, 0, 0);
+    if (!SPLIT && stash) v[i] = lds128(stash + (i * 32 + e.lane) * 16);      // this warp's own copy from pass 1
+    else v[i] = l < p.L ? __ldcg(reinterpret_cast<const uint4*>(raw + obase + static_cast<size_t>(l) * p.ld_out + c8)) : make_uint4(0, 0, 0, 0);
     if (SPLIT)
       vl[i] = l < p.L ? __ldcg(reinterpret_cast<const uint4*>(raw_lo + obase + static_cast<size_t>(l) * p.ld_out + c8)) : make_uint4(0, 0, 0, 0);
   }
+  float ca[8], cb[8];
+  if (!SPLIT && coef) {
+    // per-column y = x * ca + cb of this tile, computed ONCE per column by the CTA (gn_tile_coefficients below) instead of
+    // once per lane and chunk behind eight global loads: [BN] ca then [BN] cb floats in shared memory
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 a4 = lds128f(coef + (c8 - n0 + j) * 4);
+      const float4 b4 = lds128f(coef + (256 + c8 - n0 + j) * 4);
+      ca[j] = a4.x; ca[j + 1] = a4.y; ca[j + 2] = a4.z; ca[j + 3] = a4.w;
+      cb[j] = b4.x; cb[j + 1] = b4.y; cb[j + 2] = b4.z; cb[j + 3] = b4.w;
+    }
+  } else {
   const int grp = c8 / cpg - gfirst;
   const float mean = s_mean[grp], rstd = s_rstd[grp];
-  float ca[8], cb[8];
 #pragma unroll
   for (int j = 0; j < 8; j += 4) {
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gn.gamma + c8 + j));
@@ -302,6 +317,7 @@ __device__ __forceinline__ void gn_apply_chunk(const GemmParams& p, const EpiCtx
         cb[j + k] = cb[j + k] * s1 + shv[k];
       }
     }
+  }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -496,6 +512,7 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
     e.mine = slab + lane * EPI_PITCH;
     e.coal = slab + e.srow * EPI_PITCH + e.spiece * 16;
     e.sbias = smem_u32(smem + SL::BIAS_OFF);
+    e.stash = 0;
 #ifdef DV_DEBUG_HOOKS
     e.trace_warp = warp == 2 && p.trace != nullptr;
 #else
@@ -618,12 +635,21 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
         const size_t stat_chunk = (static_cast<size_t>(b) * p.tiles_per_batch + mt) * 4 + quad;
         const bool has_res = p.res != nullptr, has_stats = p.stats != nullptr;
         bool arrived = false;
+        // Fused output GroupNorm on the LAST tile of this CTA (every tile, when the launch is a single wave): the operand ring
+        // is idle by now (all panels consumed: the accumulator is complete), so the stored 16-bit tile is also kept there,
+        // 2 KB per (warp, chunk) in the row-contiguous layout, and the normalisation pass reads it back from shared memory
+        // instead of from L2 behind its own stores. Earlier tiles of a multi-tile CTA re-read from global.
+        constexpr int STASH_K = (NCH + PARTS - 1) / PARTS;
+        static_assert(EW * STASH_K * 2048 <= SL::STAGES * SL::STAGE_BYTES, "stash does not fit the operand ring");
+        const bool use_stash = !TRIM && !SPLIT && p.gn.out != nullptr && !p.gn.no_stash && tile + static_cast<int>(gridDim.x) >= num_tiles;
+        const uint32_t stash_base = smem_u32(smem) + static_cast<uint32_t>((warp - 2) * STASH_K) * 2048u;
 #pragma unroll 1
         for (int ch = part; ch < NCH; ch += PARTS) {
           const int gcol = n0 + ch * 32;
           const bool last = ch + PARTS >= NCH;
           if (gcol >= p.N) continue;                      // padded output columns are neither read nor written
           arrived |= last;
+          e.stash = use_stash ? stash_base + static_cast<uint32_t>(ch / PARTS) * 2048u : 0u;
           const uint32_t tc = taddr + ch * 32;
           if (has_res) {
             if (has_stats) epi_chunk_bf16<true, true, TRIM, SPLIT>(p, e, tc, gcol, lq, rowbase, obase, valid, stat_chunk, last, &tmem_empty_bar[acc], rv, preloaded && ch == part);
@@ -641,6 +667,24 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           // ---- GroupNorm of the output, applied here: wait for the other tiles of this batch item, then normalise this tile
           float* s_mean = reinterpret_cast<float*>(smem + SL::GNS_OFF);
           float* s_rstd = s_mean + 32;
+          // with the stash (idle operand ring) the CTA also keeps a per-column coefficient table there: thread `etid` owns
+          // column n0 + etid and fetches its affine / time-modulation parameters NOW, so that their latency hides behind the
+          // item wait; the table sits behind the stash
+          const int etid = static_cast<int>(threadIdx.x) - 64;
+          const int ecol = n0 + etid;
+          const bool coef_thread = use_stash && etid < BN && ecol < p.N;
+          const uint32_t coef_base = use_stash ? smem_u32(smem) + static_cast<uint32_t>(EW * STASH_K) * 2048u : 0u;
+          static_assert(EW * STASH_K * 2048 + 2 * 256 * 4 <= SL::STAGES * SL::STAGE_BYTES, "coefficient table does not fit the ring");
+          float cg = 0.f, cbt = 0.f, csc = 0.f, csh = 0.f;
+          if (coef_thread) {
+            cg = __ldg(p.gn.gamma + ecol);
+            cbt = __ldg(p.gn.beta + ecol);
+            if (p.gn.scale_shift) {
+              const float* ssp = p.gn.scale_shift + static_cast<size_t>(b) * p.gn.ss_ld;
+              csc = __ldg(ssp + ecol);
+              csh = __ldg(ssp + p.N + ecol);
+            }
+          }
           if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 3);    // pass 1 done
           epi_bar_sync(EW * 32);                          // every warp's raw store and partials are issued
           if (warp == 2 && lane == 0)
@@ -668,11 +712,28 @@ __global__ void __launch_bounds__(64 + EW * 32, EW == 8 ? 2 : 1) gemm_tc_kernel(
           }
           epi_bar_sync(EW * 32);
           if (warp == 2 && lane == 0) trace_ev(p, 2, tile, 5);    // statistics folded
+          if (use_stash) {
+            if (coef_thread) {                                    // the same arithmetic, in the same order, as the per-lane path
+              const int grp = ecol / cpg - gfirst;
+              const float mean = s_mean[grp], rstd = s_rstd[grp];
+              float a = rstd * cg;
+              float bb = cbt - mean * a;
+              if (p.gn.scale_shift) {
+                const float s1 = 1.0f + csc;
+                a *= s1;
+                bb = bb * s1 + csh;
+              }
+              sts_f32(coef_base + etid * 4, a);
+              sts_f32(coef_base + (256 + etid) * 4, bb);
+            }
+            epi_bar_sync(EW * 32);
+          }
 #pragma unroll 1
           for (int ch = part; ch < NCH; ch += PARTS) {
             const int gcol = n0 + ch * 32;
             if (gcol >= p.N) continue;
-            gn_apply_chunk<SPLIT>(p, e, gcol, lq, b, obase, s_mean, s_rstd, gfirst, cpg);
+            gn_apply_chunk<SPLIT>(p, e, gcol, lq, b, obase, s_mean, s_rstd, gfirst, cpg,
+                                  use_stash ? stash_base + static_cast<uint32_t>(ch / PARTS) * 2048u : 0u, coef_base, n0);
           }
         }
       }

@@ -100,6 +100,7 @@ struct GemmGnOut {
   int G; float eps; int silu;
   const float* gamma; const float* beta;      // [N]
   const float* scale_shift; int ss_ld;        // optional per-(b, c): scale at [b*ss_ld + c], shift at [b*ss_ld + N + c]
+  int no_stash;                               // A/B switch (DV_GN_STASH=0): normalisation pass re-reads the tile from global memory
 };
 
 struct alignas(64) GemmParams {

@@ -22,6 +22,9 @@ DV_API void dv_gemm_test_flags(int flags);
  * dv_plan_op_info's `kind`) are NOT launched by later dv_unet_forward / dv_sample calls, so the difference in step time
  * is that class's cost inside the captured loop. Initial value: DV_SKIP_KINDS (default 0). Returns the previous mask. */
 DV_API int dv_debug_skip_kinds(int mask);
+/* CTA-0 timeline (csrc/gemm_tc.cu trace_ev) of tap-GEMM op `op` of the plan's per-call program, for every later launch of it;
+ * buf: device, 1 + 4 * 160 uint64 (NULL switches it off). tools/trace_plan_op.py reads it. */
+DV_API int dv_debug_trace_op(dv_plan* plan, int op, unsigned long long* buf);
 #ifdef __cplusplus
 }
 #endif
