@@ -134,3 +134,31 @@ def test_groupnorm_in_producer_epilogue_matches_standalone_pass(unet, monkeypatc
     for k in named[0]:
         assert torch.equal(named[0][k], named[1][k]), k
     assert torch.equal(outs[0], outs[1])
+
+
+def test_fused_groupnorm_with_two_plans_running_concurrently(unet):
+    """The item wait of the fused output GroupNorm assumes that the CTAs of one launch become co-resident. Two plans enqueued on
+    two streams at the same time compete for the SMs: the waits must still complete (a straddling item only delays the CTAs of
+    that item; everything else finishes and frees SMs), the health flags stay clear and the results equal the ones computed alone."""
+    import diffvits_b200
+    from oracle import inputs
+    B, T, Tp = 16, 1000, 282
+    betas = inputs.betas_linear()
+    data = [tuple(t.cuda() for t in inputs.make_inputs(B, T, Tp, seed=40 + i)) for i in range(2)]
+    nats = [diffvits_b200.NativeDenoiser(unet, d[1], d[2]) for d in data]
+    alone = [diffvits_b200.sample_native(unet, d[0], d[1], d[2], sampler="unipc", steps=4, betas=betas, native=n, graph=False).clone()
+             for d, n in zip(data, nats)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(3):
+        outs = []
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream())
+        for d, n, s in zip(data, nats, streams):
+            with torch.cuda.stream(s):
+                outs.append(diffvits_b200.sample_native(unet, d[0], d[1], d[2], sampler="unipc", steps=4, betas=betas, native=n,
+                                                        graph=(rep > 0)))
+        torch.cuda.synchronize()
+        for o, a, n in zip(outs, alone, nats):
+            n.engine.check_finite()                      # raises if a bounded wait gave up
+            assert torch.equal(o, a)
